@@ -1,0 +1,235 @@
+"""Evolutionary candidate generation.  TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Restates tvo/variational/evo.py with the reference's sampling semantics but a counter-based
+stream (oracle/philox.py) in place of torch's / numpy's global generators:
+
+  batch_randparents      evo.py:436-451   P distinct candidates = first P of a random permutation
+  batch_fitparents       evo.py:397-433   fitness-proportional, with replacement, batch-global
+                                          normalisation and the S-1-count index (quirk Q3)
+  batch_randflip         evo.py:248-279   C distinct bit positions per parent, one flip per child
+  batch_sparseflip       evo.py:282-331   per-bit independent flips with p0 / p1
+  batch_cross            evo.py:335-380   one-point crossover over combinations(range(P), 2)
+  batch_cross_randflip   evo.py:383-387
+  batch_cross_sparseflip evo.py:390-394
+  evolve_states          evo.py:118-211
+  get_n_new_states       evo.py:214-218
+
+All functions take/return uint8 (N, ., H) arrays like the reference.  ``n_glob`` is the (N,) array
+of global datapoint indices that addresses the stream.
+"""
+from itertools import combinations
+
+import numpy as np
+
+from . import philox as px
+from .states import pack_states, unpack_states, n_words, set_redundant_lpj_to_low
+
+
+def get_n_new_states(mutation, n_parents, n_children, n_gen):
+    if mutation[:5] == "cross":
+        return n_parents * (n_parents - 1) * n_gen
+    return n_parents * n_children * n_gen
+
+
+# ----------------------------------------------------------------------------- selection
+def randparents_idx(n_glob, S_c, P, seed, step, gen):
+    """(N,P) indices: partial Fisher-Yates = first P entries of a uniform random permutation."""
+    n_glob = np.asarray(n_glob, dtype=np.uint32)
+    N = len(n_glob)
+    tag = px.make_tag(step, gen, px.PUR_SELECT)
+    perm = np.tile(np.arange(S_c, dtype=np.int64), (N, 1))
+    rows = np.arange(N)
+    for i in range(P):
+        r = px.stream_u32(seed, n_glob, np.uint32(0), tag, np.uint32(i))
+        k = i + px.randint_u32(r, S_c - i)
+        tmp = perm[rows, i].copy()
+        perm[rows, i] = perm[rows, k]
+        perm[rows, k] = tmp
+    return perm[:, :P]
+
+
+def fit_norm(lpj):
+    """(m, T) of evo.py:404-406: m = min(min(lpj), 0), T = sum(lpj - 2m) over the WHOLE batch.
+
+    `to.tensor([min, 0.0])` (:404) is a float32 tensor, so the reference rounds m through
+    float32 even for fp64 lpj; restated as such."""
+    lpj = np.asarray(lpj, dtype=np.float64)
+    m = float(np.float32(min(float(lpj.min()), 0.0)))
+    T = float((lpj - 2.0 * m).sum())
+    return m, T
+
+
+def fitparents_idx(lpj, n_glob, P, seed, step, gen, norm=None, corrected=False):
+    """(N,P) indices.  Reference-compatible mode reproduces evo.py:404-425 including the
+    batch-global normaliser and the `S-1-count` index that wraps -1 to the last candidate.
+    ``corrected=True`` is the documented alternative: per-datapoint normaliser and the
+    inverse-CDF index (first j with x < cum_p[j])."""
+    lpj = np.asarray(lpj, dtype=np.float64)
+    N, S_c = lpj.shape
+    n_glob = np.asarray(n_glob, dtype=np.uint32)
+    tag = px.make_tag(step, gen, px.PUR_SELECT)
+    if corrected:
+        m = np.minimum(lpj.min(axis=1, keepdims=True), 0.0).astype(np.float32).astype(np.float64)
+        f = lpj - 2.0 * m
+        T = np.zeros((N, 1))
+        for j in range(S_c):  # sequential sum, same order as the kernel
+            T[:, 0] = T[:, 0] + f[:, j]
+    else:
+        m, T = fit_norm(lpj) if norm is None else norm
+        f = lpj - 2.0 * m
+    fn = f / T
+    cum = np.zeros_like(fn)
+    acc = np.zeros(N)
+    for j in range(S_c):  # sequential cumsum (torch.cumsum order)
+        acc = acc + fn[:, j]
+        cum[:, j] = acc
+    i = np.arange(P, dtype=np.uint32)[None, :]
+    x = px.u64_to_unit_double(px.stream_u64(seed, n_glob[:, None], np.uint32(0), tag, i))  # (N,P)
+    count = (x[:, :, None] < cum[:, None, :]).sum(axis=-1)
+    if corrected:
+        return np.minimum(S_c - count, S_c - 1)
+    chosen = S_c - 1 - count
+    chosen[chosen < 0] += S_c
+    return chosen
+
+
+def take_parents(candidates, idx):
+    return candidates[np.arange(candidates.shape[0])[:, None], idx]
+
+
+# ----------------------------------------------------------------------------- mutation
+def _distinct_positions(seed, n, slot, tag, H, C):
+    """C distinct positions in [0,H) by virtual Fisher-Yates (scalar)."""
+    swapped = {}
+    out = []
+    for i in range(C):
+        r = int(px.stream_u32(seed, np.uint32(n), np.uint32(slot), tag, np.uint32(i)))
+        k = i + ((r * (H - i)) >> 32)
+        vk = swapped.get(k, k)
+        vi = swapped.get(i, i)
+        out.append(vk)
+        swapped[k] = vi
+    return out
+
+
+def randflip(parents, C, n_glob, seed, step, gen):
+    """(N,P,H) -> (N,P*C,H); child p*C+c = parent p with bit pos[p][c] flipped."""
+    N, P, H = parents.shape
+    tag = px.make_tag(step, gen, px.PUR_RANDFLIP)
+    children = np.repeat(parents, C, axis=1).copy()
+    for n in range(N):
+        for p in range(P):
+            pos = _distinct_positions(seed, n_glob[n], p, tag, H, C)
+            for c, h in enumerate(pos):
+                children[n, p * C + c, h] ^= 1
+    return children
+
+
+def sparseflip_probs(a, H, sparsity, p_bf):
+    """p0, p1 of evo.py:310-316 in fp64, operation for operation."""
+    eps = 1e-100
+    Hf = float(H)
+    a = np.asarray(a, dtype=np.float64)
+    crowd = float(sparsity) * H
+    with np.errstate(all="ignore"):
+        alpha = (Hf - a) * ((Hf * p_bf) - (crowd - a)) / ((crowd - a + Hf * p_bf) * a + eps)
+        p0 = (Hf * p_bf) / (Hf + (alpha - 1.0) * a) + eps
+        p1 = alpha * p0
+    return p0, p1
+
+
+def sparseflip(parents, C, sparsity, p_bf, n_glob, seed, step, gen):
+    """(N,P,H) -> (N,P*C,H); every bit flips independently with p1 if set else p0."""
+    N, P, H = parents.shape
+    W = n_words(H)
+    tag0 = px.make_tag(step, gen, px.PUR_FLIP0)
+    tag1 = px.make_tag(step, gen, px.PUR_FLIP1)
+    a = parents.sum(axis=2)
+    p0, p1 = sparseflip_probs(a, H, sparsity, p_bf)
+    packed = pack_states(np.repeat(parents, C, axis=1))  # (N,P*C,W)
+    out = packed.copy()
+    for n in range(N):
+        for j in range(P * C):
+            p = j // C
+            for w in range(W):
+                valid = (1 << min(64, H - 64 * w)) - 1
+                s = int(packed[n, j, w])
+                slot = (j << 8) | w
+                m0 = px.bernoulli_mask64(seed, np.uint32(n_glob[n]), np.uint32(slot), tag0, p0[n, p], ~s & valid)
+                m1 = px.bernoulli_mask64(seed, np.uint32(n_glob[n]), np.uint32(slot), tag1, p1[n, p], s)
+                out[n, j, w] = np.uint64(s ^ (m0 | m1))
+    return unpack_states(out, H)
+
+
+def cross(parents, n_glob, seed, step, gen):
+    """(N,P,H) -> (N,P(P-1),H); child 2k = p1[:c] | p2[c:], child 2k+1 = p2[:c] | p1[c:]."""
+    N, P, H = parents.shape
+    pairs = list(combinations(range(P), 2))
+    tag = px.make_tag(step, gen, px.PUR_CROSS)
+    n_glob = np.asarray(n_glob, dtype=np.uint32)
+    children = np.empty((N, 2 * len(pairs), H), dtype=np.uint8)
+    for k, (a, b) in enumerate(pairs):
+        r = px.stream_u32(seed, n_glob, np.uint32(0), tag, np.uint32(k))
+        cut = 1 + px.randint_u32(r, H - 1)  # in [1, H-1]
+        low = np.arange(H)[None, :] < cut[:, None]
+        children[:, 2 * k] = np.where(low, parents[:, a], parents[:, b])
+        children[:, 2 * k + 1] = np.where(low, parents[:, b], parents[:, a])
+    return children
+
+
+def mutate(parents, mutation, n_children, sparsity, p_bf, n_glob, seed, step, gen):
+    if mutation == "randflip":
+        return randflip(parents, n_children, n_glob, seed, step, gen)
+    if mutation == "sparseflip":
+        return sparseflip(parents, n_children, sparsity, p_bf, n_glob, seed, step, gen)
+    if mutation == "cross":
+        return cross(parents, n_glob, seed, step, gen)
+    if mutation == "cross_randflip":
+        return randflip(cross(parents, n_glob, seed, step, gen), 1, n_glob, seed, step, gen)
+    if mutation == "cross_sparseflip":
+        return sparseflip(cross(parents, n_glob, seed, step, gen), 1, sparsity, p_bf, n_glob, seed, step, gen)
+    raise ValueError(f'Mutation operator "{mutation}" not supported.')
+
+
+# ----------------------------------------------------------------------------- generations
+def evolve_states(lpj, states, lpj_fn, n_parents, n_children, n_generations, parent_selection,
+                  mutation, sparsity, p_bf, n_glob, seed, step, fit_corrected=False, dedup=True):
+    """evo.py:118-211.  Returns (new_states (N,S',H) uint8, new_lpj (N,S'))."""
+    N, S, H = states.shape
+    S_new = get_n_new_states(mutation, n_parents, n_children, n_generations)
+    per_gen = S_new // n_generations
+    new_states = np.empty((N, S_new, H), dtype=np.uint8)
+    new_lpj = np.empty((N, S_new), dtype=lpj.dtype)
+    for g in range(n_generations):
+        if g == 0:
+            cand, cand_lpj = states, lpj
+        else:
+            sl = slice((g - 1) * per_gen, g * per_gen)
+            cand, cand_lpj = new_states[:, sl], new_lpj[:, sl]
+        if parent_selection == "randparents":
+            pidx = randparents_idx(n_glob, cand.shape[1], n_parents, seed, step, g)
+        elif parent_selection == "batch_fitparents":
+            pidx = fitparents_idx(cand_lpj, n_glob, n_parents, seed, step, g, corrected=fit_corrected)
+        else:
+            raise ValueError(f'Parent selection "{parent_selection}" not supported.')
+        parents = take_parents(cand, pidx)
+        sl = slice(g * per_gen, (g + 1) * per_gen)
+        new_states[:, sl] = mutate(parents, mutation, n_children, sparsity, p_bf, n_glob, seed, step, g)
+        new_lpj[:, sl] = lpj_fn(new_states[:, sl])
+    if dedup:
+        set_redundant_lpj_to_low(new_states, new_lpj, states)
+    return new_states, new_lpj
+
+
+def random_states(N, S_new, H, sparsity, n_glob, seed, step):
+    """RandomSampledVarStates.py:57-59: every bit ~ Bernoulli(sparsity), no dedup."""
+    W = n_words(H)
+    tag = px.make_tag(step, 0, px.PUR_SAMPLE)
+    out = np.zeros((N, S_new, W), dtype=np.uint64)
+    for n in range(N):
+        for j in range(S_new):
+            for w in range(W):
+                valid = (1 << min(64, H - 64 * w)) - 1
+                out[n, j, w] = np.uint64(
+                    px.bernoulli_mask64(seed, np.uint32(n_glob[n]), np.uint32((j << 8) | w), tag, sparsity, valid))
+    return unpack_states(out, H)

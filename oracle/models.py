@@ -1,0 +1,271 @@
+"""Model maths (log-pseudo-joint, log-joint, free energy, M-step).  TEST INFRASTRUCTURE.
+
+numpy restatement of
+  tvo/models/bsc.py:100-204        BSC
+  tvo/models/noisyor.py:67-162     NoisyOR
+  tvo/models/sssc.py:175-540       SSSC
+  tvo/utils/model_protocols.py:179-193   Optimized.free_energy
+  tvo/utils/sanity.py:14-86        fix_theta (clamps / non-finite replacement)
+
+Each class keeps ``theta`` (dict of numpy arrays, updated in place) and the reference's
+accumulators under the reference's names.  ``K`` is uint8 (N,S,H) as in the reference.
+"""
+import math
+
+import numpy as np
+
+from .states import lpj2pjc, mean_posterior, logsumexp
+
+
+def _fix(new, old, lo, hi):
+    """sanity.py:43-86: replace non-finite entries by `old`, then clamp to [lo, hi]."""
+    new = np.array(new, copy=True)
+    bad = ~np.isfinite(new)
+    if bad.any():
+        new[bad] = np.broadcast_to(old, new.shape)[bad]
+    if lo is not None:
+        new = np.maximum(new, lo)
+    if hi is not None:
+        new = np.minimum(new, hi)
+    return new
+
+
+class BSC:
+    def __init__(self, H, D, W_init, sigma2_init, pies_init, individual_priors=True, precision=np.float64):
+        self.H, self.D, self.individual_priors, self.precision = H, D, individual_priors, precision
+        self.theta = {
+            "pies": np.array(pies_init, dtype=precision),
+            "W": np.array(W_init, dtype=precision),
+            "sigma2": np.array(sigma2_init, dtype=precision).reshape(1),
+        }
+        self.my_Wp = np.zeros((D, H), precision)
+        self.my_Wq = np.zeros((H, H), precision)
+        self.my_pies = np.zeros(H, precision)
+        self.my_sigma2 = np.zeros(1, precision)
+        self.my_N = 0
+
+    def log_pseudo_joint(self, data, states):  # bsc.py:100-119
+        th = self.theta
+        Kf = states.astype(th["W"].dtype)
+        Wbar = Kf @ th["W"].T
+        lr = np.log(th["pies"] / (1 - th["pies"]))
+        prior = Kf @ lr if self.individual_priors else lr * Kf.sum(axis=2)
+        return np.nansum((Wbar - data[:, None, :]) ** 2, axis=2) * (-1 / 2 / th["sigma2"]) + prior
+
+    def log_joint(self, data, states, lpj=None):  # bsc.py:121-132
+        th = self.theta
+        if lpj is None:
+            lpj = self.log_pseudo_joint(data, states)
+        Dn = np.sum(~np.isnan(data), axis=1)
+        prior = np.log(1 - th["pies"]).sum() if self.individual_priors else self.H * np.log(1 - th["pies"])
+        return lpj + prior - Dn[:, None] / 2 * np.log(2 * math.pi * th["sigma2"])
+
+    def free_energy(self, data, states, lpj):  # model_protocols.py:179-193
+        return float(logsumexp(self.log_joint(data, states, lpj), axis=1).sum())
+
+    def update_param_batch(self, batch, K, lpj):  # bsc.py:134-158
+        Kf = K.astype(lpj.dtype)
+        Wbar = Kf @ self.theta["W"].T
+        s_pjc = mean_posterior(Kf, lpj)
+        q = lpj2pjc(lpj)
+        self.my_pies += s_pjc.sum(axis=0)
+        self.my_Wp += batch.T @ s_pjc
+        self.my_Wq += np.einsum("ijk,ijl->kl", Kf * q[:, :, None], Kf)
+        self.my_sigma2 += mean_posterior(((batch[:, None, :] - Wbar) ** 2).sum(axis=2), lpj).sum()
+        self.my_N += batch.shape[0]
+
+    def update_param_epoch(self):  # bsc.py:160-204 (the always-drawn randn of :174 only matters
+        th = self.theta            # as the non-finite replacement for W and is omitted)
+        N, D, H = self.my_N, self.D, self.H
+        W_new = np.linalg.lstsq(self.my_Wq, self.my_Wp.T, rcond=None)[0].T
+        pies_new = self.my_pies / N if self.individual_priors else self.my_pies.sum(keepdims=True) / N / H
+        sigma2_new = self.my_sigma2 / N / D
+        eps = 1.0e-5
+        th["W"][:] = _fix(W_new, th["W"], None, None)
+        th["pies"][:] = _fix(pies_new, th["pies"], eps, 1.0 - eps)
+        th["sigma2"][:] = _fix(sigma2_new, th["sigma2"], eps, None)
+        self.my_Wp[:] = 0
+        self.my_Wq[:] = 0
+        self.my_pies[:] = 0
+        self.my_sigma2[:] = 0
+        self.my_N = 0
+
+
+class NoisyOR:
+    eps = 1e-7
+
+    def __init__(self, H, D, W_init, pi_init, precision=np.float64):
+        self.H, self.D, self.precision = H, D, precision
+        self.theta = {"pies": np.array(pi_init, dtype=precision), "W": np.array(W_init, dtype=precision)}
+        self.new_pi = np.zeros(H, precision)
+        self.Btilde = np.zeros((D, H), precision)
+        self.Ctilde = np.zeros((D, H), precision)
+        self.n_train = 0
+
+    def log_pseudo_joint(self, data, states):  # noisyor.py:67-106
+        K, Y = states, data
+        assert K.dtype == np.uint8 and Y.dtype == np.uint8
+        pi, W = self.theta["pies"], self.theta["W"]
+        one = self.precision(1.0)
+        logPriors = K.astype(pi.dtype) @ np.log(pi / (1 - pi))
+        zero = (K == 0).all(axis=2)  # (N,S)
+        Kw = K.copy()
+        Kw[zero] = 1
+        prods = (one - W[None, None] * Kw.astype(W.dtype)[:, :, None, :]).prod(axis=-1)  # (N,S,D)
+        prods = np.clip(prods, self.precision(self.eps), self.precision(1 - self.eps))
+        f1 = np.log(one / prods - one)
+        f1 = np.where(Y[:, None, :] == 1, f1, 0.0).astype(self.precision)
+        logPy = f1.sum(axis=-1) + np.log(prods).sum(axis=2)
+        lpj = logPriors + logPy
+        any_y = Y.any(axis=1)
+        lpj[zero] = (-1e30 * np.broadcast_to(any_y[:, None], zero.shape)[zero]).astype(lpj.dtype)
+        assert not np.isnan(lpj).any() and not np.isinf(lpj).any()
+        return lpj
+
+    def log_joint(self, data, states, lpj=None):  # noisyor.py:157-162
+        if lpj is None:
+            lpj = self.log_pseudo_joint(data, states)
+        return np.log(1 - self.theta["pies"]).sum() + lpj
+
+    def free_energy(self, data, states, lpj):
+        return float(logsumexp(self.log_joint(data, states, lpj), axis=1).sum())
+
+    def update_param_batch(self, batch, K, lpj):  # noisyor.py:108-138
+        Kf = K.astype(lpj.dtype)
+        W = self.theta["W"]
+        one = lpj.dtype.type(1.0)
+        self.new_pi += mean_posterior(Kf, lpj).sum(axis=0)
+        Ws = one - W[None, None, :, :] * Kf[:, :, None, :]  # (N,S,D,H)
+        Ws_prod = Ws.prod(axis=3, keepdims=True)
+        B = Kf[:, :, None, :] / (Ws * (one - Ws_prod) + lpj.dtype.type(self.eps))
+        self.Btilde += (mean_posterior(B, lpj) * (batch.astype(lpj.dtype) - 1)[:, :, None]).sum(axis=0)
+        C = B * Ws_prod / Ws
+        self.Ctilde += mean_posterior(C, lpj).sum(axis=0)
+        self.n_train += batch.shape[0]
+
+    def update_param_epoch(self):  # noisyor.py:140-155
+        th, eps = self.theta, self.precision(self.eps)
+        th["pies"][:] = np.clip(self.new_pi / self.n_train, eps, 1 - eps)
+        th["W"][:] = np.clip(1 + self.Btilde / (self.Ctilde + eps), eps, 1 - eps)
+        self.new_pi[:] = 0
+        self.Btilde[:] = 0
+        self.Ctilde[:] = 0
+        self.n_train = 0
+
+
+class SSSC:
+    def __init__(self, H, D, W_init, sigma2_init, mus_init, Psi_init, pies_init,
+                 reformulated_psi_update=False, precision=np.float64):
+        self.H, self.D, self.precision = H, D, precision
+        self.reformulated_psi_update = reformulated_psi_update
+        p = precision
+        self.theta = {
+            "W": np.array(W_init, dtype=p), "sigma2": np.array(sigma2_init, dtype=p).reshape(1),
+            "mus": np.array(mus_init, dtype=p), "Psi": np.array(Psi_init, dtype=p),
+            "pies": np.array(pies_init, dtype=p),
+        }
+        self._zero()
+
+    def _zero(self):
+        D, H, p = self.D, self.H, self.precision
+        self.sum_y_szT = np.zeros((D, H), p)
+        self.sum_xpt_sz_xpt_szT = np.zeros((H, H), p)
+        self.sum_xpt_szszT = np.zeros((H, H), p)
+        self.sum_xpt_s = np.zeros(H, p)
+        self.sum_xpt_sz = np.zeros(H, p)
+        self.sum_xpt_ssT = np.zeros((H, H), p)
+        self.sum_xpt_ssz = np.zeros((H, H), p)
+        self.sum_diag_yyT = np.zeros(D, p)
+        self.my_N = 0
+
+    def _terms(self, state, notnan):  # sssc.py:216-248
+        th = self.theta
+        W_s = th["W"][notnan][:, state]
+        Psi_s = th["Psi"][state][:, state]
+        mus_s = th["mus"][state]
+        Inv_Lambda_s = W_s.T @ W_s / th["sigma2"] + np.linalg.inv(Psi_s)
+        Lambda_s = np.linalg.inv(Inv_Lambda_s)
+        return W_s, mus_s, Psi_s, Inv_Lambda_s, Lambda_s, Lambda_s @ W_s.T / th["sigma2"]
+
+    def log_pseudo_joint(self, data, states):  # sssc.py:266-346 (default, reformulated form)
+        th = self.theta
+        sigma2 = th["sigma2"]
+        pies = np.clip(th["pies"], 1e-2, 1 - 1e-2)
+        Kb = states.astype(bool)
+        notnan = ~np.isnan(data)
+        lpj = states.astype(self.precision) @ np.log(pies / (1.0 - pies))
+        N, S = lpj.shape
+        for n in range(N):
+            y = data[n][notnan[n]]
+            Dn = int(notnan[n].sum())
+            for s in range(S):
+                W_s, mus_s, Psi_s, ILam, Lam, LWs = self._terms(Kb[n, s], notnan[n])
+                Inv_C = np.eye(Dn, dtype=self.precision) / sigma2 - W_s @ LWs / sigma2
+                ld = np.linalg.slogdet(ILam)[1] + np.linalg.slogdet(Psi_s)[1]
+                r = y - W_s @ mus_s
+                lpj[n, s] -= 0.5 * (ld + (r * (Inv_C @ r)).sum())
+        mn = np.finfo(self.precision).min
+        lpj[np.isnan(lpj)] = mn
+        lpj[np.isinf(lpj)] = mn
+        return lpj
+
+    def log_joint(self, data, states, lpj=None):  # sssc.py:348-364
+        if lpj is None:
+            lpj = self.log_pseudo_joint(data, states)
+        pies = np.clip(self.theta["pies"], 1e-2, 1 - 1e-2)
+        Dn = np.sum(~np.isnan(data), axis=1)
+        return lpj + np.log(1.0 - pies).sum() - Dn[:, None] / 2.0 * (
+            np.log(2.0 * math.pi) + np.log(self.theta["sigma2"]))
+
+    def free_energy(self, data, states, lpj):
+        return float(logsumexp(self.log_joint(data, states, lpj), axis=1).sum())
+
+    def update_param_batch(self, batch, K, lpj):  # sssc.py:366-452
+        Kb = K.astype(bool)
+        Kf = K.astype(lpj.dtype)
+        N, S, H = K.shape
+        notnan = np.ones(batch.shape[1], bool)
+        kap = np.zeros((N, S, H), self.precision)
+        LpKK = np.zeros((N, S, H, H), self.precision)
+        for n in range(N):
+            for s in range(S):
+                st = Kb[n, s]
+                if st.sum() == 0:
+                    continue
+                W_s, mus_s, _, _, Lam, LWs = self._terms(st, notnan)
+                r = batch[n] - W_s @ mus_s
+                k = mus_s + LWs @ r
+                kap[n, s][st] = k
+                LpKK[n, s][np.outer(st, st)] = (Lam + np.outer(k, k)).flatten()
+        xs = mean_posterior(Kf, lpj)
+        xssT = mean_posterior(Kf[:, :, :, None] * Kf[:, :, None, :], lpj)
+        xsz = mean_posterior(kap, lpj)
+        xszszT = mean_posterior(LpKK, lpj)
+        self.sum_xpt_s += xs.sum(0)
+        self.sum_xpt_ssT += xssT.sum(0)
+        self.sum_xpt_sz += xsz.sum(0)
+        self.sum_xpt_sz_xpt_szT += xsz.T @ xsz
+        self.sum_xpt_szszT += xszszT.sum(0)
+        self.sum_diag_yyT += (batch ** 2).sum(0)
+        self.sum_y_szT += batch.T @ xsz
+        self.sum_xpt_ssz += (xs[:, :, None] * xsz[:, None, :]).sum(0)
+        self.my_N += N
+
+    def update_param_epoch(self):  # sssc.py:467-540
+        th, H, D, N = self.theta, self.H, self.D, self.my_N
+        dtype_eps, eps = np.finfo(self.precision).eps, 1e-5
+        eps_eye = np.eye(H, dtype=self.precision) * 1e-6
+        Inv_ssT = np.linalg.inv(self.sum_xpt_ssT)
+        th["W"][:] = self.sum_y_szT @ np.linalg.inv(self.sum_xpt_szszT)
+        th["pies"][:] = self.sum_xpt_s / N
+        th["mus"][:] = self.sum_xpt_sz / (self.sum_xpt_s + dtype_eps)
+        mus = th["mus"]
+        if self.reformulated_psi_update:
+            _Psi = (np.outer(mus, mus) * self.sum_xpt_ssT + self.sum_xpt_szszT
+                    - 2.0 * mus[:, None] * self.sum_xpt_ssz)
+            th["Psi"][:] = _Psi * Inv_ssT + eps_eye
+        else:
+            th["Psi"][:] = (self.sum_xpt_szszT - self.sum_xpt_ssT * np.outer(mus, mus)) * Inv_ssT + eps_eye
+        W = th["W"]
+        th["sigma2"][:] = (self.sum_diag_yyT.sum() - np.trace(self.sum_xpt_sz_xpt_szT @ (W.T @ W))) / N / D + eps
+        self._zero()

@@ -1,0 +1,386 @@
+"""The oracle against the reference's own known answers (CPU, no GPU).
+
+Sources of truth:
+ * inline known-answer vectors of the reference's tests (cited per test),
+ * SURVEY.md Appendix A (outputs of the unmodified reference on exactly representable inputs),
+ * tests/golden/*.npz produced by tools/make_golden.py from the unmodified reference,
+ * the reference's compiled Cython dedup (oracle/_ref, when built).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import evo as oevo
+from oracle import models as om
+from oracle import states as ost
+from oracle.ref_loader import load_ref_dedup
+
+
+# ------------------------------------------------------------------ inline KATs of the reference
+def test_kat_update_states_for_batch():
+    # test/variationalutils_test.py:51-73
+    idx = np.arange(2)
+    new_states = np.ones((2, 2, 1), np.uint8)
+    all_states = np.zeros((4, 3, 1), np.uint8)
+    new_lpj = np.ones((2, 2))
+    all_lpj = np.zeros((4, 3))
+    nsubs = ost.update_states_for_batch(new_states, new_lpj, idx, all_states, all_lpj)
+    want = np.array([[[0], [1], [1]], [[0], [1], [1]], [[0], [0], [0]], [[0], [0], [0]]], np.uint8)
+    assert np.array_equal(all_states, want)
+    assert nsubs == 4
+
+
+def test_kat_set_redundant_lpj_to_low():
+    # test/variationalutils_test.py:75-102
+    old = np.array([[[0, 1, 1], [1, 0, 0]], [[0, 1, 1], [1, 0, 1]], [[0, 1, 1], [1, 1, 1]]], np.uint8)
+    new = np.array([[[0, 0, 0], [1, 1, 0]], [[0, 0, 0], [1, 0, 1]], [[0, 0, 0], [0, 0, 0]]], np.uint8)
+    for use_c in (True, False):
+        lpj = np.ones((3, 2))
+        ost.set_redundant_lpj_to_low(new, lpj, old, low=None if use_c else ost.LOW_LPJ)
+        assert np.isclose(lpj, 1.0).sum() == 4
+        assert np.allclose(lpj[1, 1], -1e20)
+        assert np.allclose(lpj[2].sum(), -1e20)
+        assert lpj[2, 0] < -1e19 and lpj[2, 1] == 1.0  # the LAST copy survives (pyx:22-25)
+
+
+def test_kat_bsc_closed_form():
+    # test/bsc_test.py:23-84 (N=2, D=1, H=2, FullEM states)
+    for indiv in (True, False):
+        H, D = 2, 1
+        m = om.BSC(H, D, np.ones((D, H)), [1.0], np.full(H if indiv else 1, 0.5), individual_priors=indiv)
+        K = np.tile(ost.state_matrix(H)[None], (2, 1, 1))
+        data = np.array([[0.0], [1.0]])
+        true_lpj = np.array([[0.0, -0.5, -0.5, -2.0], [-0.5, 0.0, 0.0, -0.5]])
+        lpj = m.log_pseudo_joint(data, K)
+        assert np.allclose(lpj, true_lpj)
+        const = 2 * np.log(0.5) - 0.5 * np.log(2 * math.pi)
+        true_F = np.log(np.exp(true_lpj + const).sum(axis=1)).sum()
+        assert math.isclose(m.free_energy(data, K, lpj), true_F, rel_tol=1e-12)
+
+
+def test_kat_noisyor_closed_form():
+    # test/noisyor_test.py:17-50
+    H, D = 2, 1
+    m = om.NoisyOR(H, D, np.full((D, H), 0.5), np.full(H, 0.5))
+    K = np.tile(ost.state_matrix(H)[None], (2, 1, 1))
+    data = np.array([[0], [1]], np.uint8)
+    true_lpj = np.array([[0, np.log(1 / 2), np.log(1 / 2), np.log(1 / 4)],
+                         [-1e30, np.log(1 / 2), np.log(1 / 2), np.log(3 / 4)]])
+    lpj = m.log_pseudo_joint(data, K)
+    assert np.allclose(lpj, true_lpj, rtol=1e-6)
+    assert math.isclose(m.free_energy(data, K, lpj), -1.4020427180880297, rel_tol=1e-6)
+
+
+# ------------------------------------------------------------------ SURVEY Appendix A
+APP_W = np.array([[1.0, -0.5, 0.25, 2.0], [0.5, 1.5, -1.0, 0.0], [-0.25, 0.75, 0.5, -1.5]])
+APP_PIES = np.array([0.125, 0.25, 0.5, 0.375])
+APP_Y = np.array([[1.0, 0.5, -0.25], [0.0, 2.0, 1.25]])
+APP_K = np.array([[[0, 0, 0, 0], [1, 0, 0, 0], [1, 0, 1, 1]], [[0, 1, 0, 0], [0, 1, 1, 0], [1, 1, 1, 1]]], np.uint8)
+
+
+def test_appendix_bsc():
+    m = om.BSC(4, 3, APP_W, [0.5], APP_PIES)
+    lpj = m.log_pseudo_joint(APP_Y, APP_K)
+    want = np.array([[-1.3125, -1.9459101490553135, -9.519235772821304],
+                     [-1.8486122886681098, -3.41111228866811, -15.180348061489415]])
+    assert np.allclose(lpj, want, rtol=1e-13)
+    assert math.isclose(m.free_energy(APP_Y, APP_K, lpj), -9.147775268998025, rel_tol=1e-13)
+    m.update_param_batch(APP_Y, APP_K, lpj)
+    assert np.allclose(m.my_pies, [0.3468554418508215, 1.0, 0.17346749920566668, 0.00017952566946517786], rtol=1e-12)
+    assert np.allclose(m.my_sigma2, [1.87928946429014], rtol=1e-12)
+    assert np.allclose(m.my_Wp[1], [0.17342973254348804, 2.0, 0.34666772152521286, 9.177445280986586e-05], rtol=1e-12)
+    assert np.allclose(m.my_Wq[2], [0.00017952566946517786, 0.17328931461491967, 0.17346749920566668,
+                                    0.00017952566946517786], rtol=1e-12)
+
+
+def test_appendix_noisyor():
+    W = np.array([[0.5, 0.25, 0.125, 0.75], [0.25, 0.5, 0.5, 0.125], [0.75, 0.125, 0.25, 0.5]])
+    Y = np.array([[1, 0, 1], [0, 0, 0]], np.uint8)
+    m = om.NoisyOR(4, 3, W, APP_PIES)
+    lpj = m.log_pseudo_joint(Y, APP_K)
+    want = np.array([[-1e30, -3.2144214745188204, -3.7853683067959274],
+                     [-2.212972934304359, -3.327333579940608, -10.364165901197886]])
+    assert np.allclose(lpj, want, rtol=1e-13)
+    assert math.isclose(m.free_energy(Y, APP_K, lpj), -7.864258083527527, rel_tol=1e-13)
+    m.update_param_batch(Y, APP_K, lpj)
+    assert np.allclose(m.new_pi, [1.0002170944039035, 1.0, 0.6082406598070094, 0.3612354713656208], rtol=1e-12)
+    assert np.allclose(m.Btilde[0], [-0.00047298855566642957, -4.973208035290325, -0.821482061251512,
+                                     -0.0009459769052307017], rtol=1e-10)
+    assert np.allclose(m.Ctilde[2], [4.005757965337116, 7.498467010883864, 0.9047489776438232,
+                                     0.14946448132162313], rtol=1e-10)
+    m.update_param_epoch()
+    assert np.allclose(m.theta["pies"], [0.5001085472019517, 0.5, 0.3041203299035047, 0.1806177356828104], rtol=1e-12)
+    assert np.allclose(m.theta["W"][0], [0.9998269561761027, 1e-07, 1e-07, 0.9986670366807782], rtol=1e-9)
+
+
+def test_appendix_sssc():
+    mus = np.array([0.5, -0.25, 1.0, 0.0])
+    Psi = np.array([[1, 0.25, 0, 0], [0.25, 2, 0, 0.5], [0, 0, 0.5, 0], [0, 0.5, 0, 1.5]], float)
+    m = om.SSSC(4, 3, APP_W, [0.5], mus, Psi, APP_PIES)
+    lpj = m.log_pseudo_joint(APP_Y, APP_K)
+    want = np.array([[-1.3125, -2.680354534587943, -5.344007104422202],
+                     [-3.435717196959697, -4.09862850737411, -7.485431308356349]])
+    assert np.allclose(lpj, want, rtol=1e-12)
+    lj = m.log_joint(APP_Y, APP_K, lpj)
+    assert np.allclose(lj[1], [-6.737176300615781, -7.4000876110301945, -10.786890412012433], rtol=1e-12)
+
+
+def test_appendix_dedup_merge():
+    old_K = np.array([[[0, 0, 1], [0, 1, 0], [1, 1, 0]], [[1, 0, 0], [1, 0, 1], [0, 1, 1]]], np.uint8)
+    old_lpj = np.array([[-3.0, -2, -1], [-6, -5, -4]])
+    new_K = np.array([[[1, 1, 1], [0, 1, 0], [1, 1, 1], [1, 0, 0]], [[0, 0, 0], [0, 1, 1], [1, 1, 0], [0, 0, 0]]], np.uint8)
+    new_lpj = np.array([[-0.5, -0.25, -0.5, -2.5], [-4.5, -1.0, -7.0, -4.5]])
+    L = -1.0000000200408773e+20
+    ost.set_redundant_lpj_to_low(new_K, new_lpj, old_K)
+    assert np.array_equal(new_lpj, np.array([[L, L, -0.5, -2.5], [L, L, -7.0, -4.5]]))
+    nsubs = ost.update_states_for_batch(new_K, new_lpj, np.arange(2), old_K, old_lpj)
+    assert nsubs == 2
+    assert np.array_equal(old_K, np.array([[[0, 1, 0], [1, 1, 0], [1, 1, 1]], [[1, 0, 1], [0, 0, 0], [0, 1, 1]]]))
+    assert np.array_equal(old_lpj, np.array([[-2.0, -1.0, -0.5], [-5.0, -4.5, -4.0]]))
+
+
+# ------------------------------------------------------------------ reference-generated fixtures
+@pytest.mark.parametrize("tag,indiv,prec,tol", [("ind_f64", True, np.float64, 1e-12),
+                                                ("single_f64", False, np.float64, 1e-12),
+                                                ("ind_f32", True, np.float32, 2e-5)])
+def test_golden_bsc(tag, indiv, prec, tol):
+    g = load_golden(f"bsc_{tag}.npz")
+    D, H = g["W"].shape
+    m = om.BSC(H, D, g["W"], g["sigma2"], g["pies"], individual_priors=indiv, precision=prec)
+    Y, K = g["Y"].astype(prec), g["K"]
+    lpj = m.log_pseudo_joint(Y, K)
+    assert lpj.dtype == prec
+    assert np.allclose(lpj, g["lpj"], rtol=tol, atol=tol)
+    assert np.allclose(m.log_joint(Y, K, lpj), g["log_joint"], rtol=tol, atol=tol)
+    assert math.isclose(m.free_energy(Y, K, lpj), float(g["F"]), rel_tol=max(tol, 1e-12))
+    Yn = g["Ynan"].astype(prec)
+    assert np.allclose(m.log_pseudo_joint(Yn, K), g["lpj_nan"], rtol=tol, atol=tol)
+    assert np.allclose(m.log_joint(Yn, K), g["log_joint_nan"], rtol=tol, atol=tol)
+    m.update_param_batch(Y, K, g["lpj"])
+    for name in ("my_Wp", "my_Wq", "my_pies", "my_sigma2"):
+        assert np.allclose(getattr(m, name), g[name], rtol=10 * tol, atol=10 * tol), name
+    m.update_param_batch(g["Y2"].astype(prec), g["K2"], g["lpj2"])
+    m.update_param_epoch()
+    wt = 1e-8 if prec == np.float64 else 5e-3
+    assert np.allclose(m.theta["W"], g["W_new"], rtol=wt, atol=wt)
+    assert np.allclose(m.theta["pies"], g["pies_new"], rtol=10 * tol)
+    assert np.allclose(m.theta["sigma2"], g["sigma2_new"], rtol=10 * tol)
+
+
+@pytest.mark.parametrize("tag,prec,tol", [("f64", np.float64, 1e-12), ("f32", np.float32, 3e-5)])
+def test_golden_noisyor(tag, prec, tol):
+    g = load_golden(f"noisyor_{tag}.npz")
+    D, H = g["W"].shape
+    m = om.NoisyOR(H, D, g["W"], g["pies"], precision=prec)
+    lpj = m.log_pseudo_joint(g["Y"], g["K"])
+    assert np.allclose(lpj, g["lpj"], rtol=tol, atol=tol)
+    assert (lpj == -1e30).sum() == (g["lpj"] == -1e30).sum() > 0
+    assert math.isclose(m.free_energy(g["Y"], g["K"], lpj), float(g["F"]), rel_tol=max(tol, 1e-12))
+    m.update_param_batch(g["Y"], g["K"], g["lpj"])
+    for name in ("new_pi", "Btilde", "Ctilde"):
+        assert np.allclose(getattr(m, name), g[name], rtol=100 * tol, atol=100 * tol), name
+    m.update_param_epoch()
+    assert np.allclose(m.theta["W"], g["W_new"], rtol=1000 * tol, atol=1000 * tol)
+    assert np.allclose(m.theta["pies"], g["pies_new"], rtol=100 * tol)
+
+
+@pytest.mark.parametrize("tag,reform", [("f64", False), ("f64_psi", True)])
+def test_golden_sssc(tag, reform):
+    g = load_golden(f"sssc_{tag}.npz")
+    D, H = g["W"].shape
+    m = om.SSSC(H, D, g["W"], g["sigma2"], g["mus"], g["Psi"], g["pies"], reformulated_psi_update=reform)
+    lpj = m.log_pseudo_joint(g["Y"], g["K"])
+    assert np.allclose(lpj, g["lpj"], rtol=1e-11, atol=1e-11)
+    assert np.allclose(m.log_joint(g["Y"], g["K"], lpj), g["log_joint"], rtol=1e-11, atol=1e-11)
+    assert math.isclose(m.free_energy(g["Y"], g["K"], lpj), float(g["F"]), rel_tol=1e-11)
+    # quirk Q7: the straightforward form differs by the state-independent -D/2 log sigma2
+    shift = g["lpj_straight"] - g["lpj"]
+    assert np.allclose(shift, -D / 2 * np.log(g["sigma2"]), rtol=1e-8)
+    m.update_param_batch(g["Y"], g["K"], g["lpj"])
+    names = ["sum_y_szT", "sum_xpt_sz_xpt_szT", "sum_xpt_szszT", "sum_xpt_s", "sum_xpt_sz", "sum_xpt_ssT",
+             "sum_diag_yyT"] + (["sum_xpt_ssz"] if reform else [])
+    for name in names:
+        assert np.allclose(getattr(m, name), g[name], rtol=1e-10, atol=1e-10), name
+    m.update_param_batch(g["Y2"], g["K2"], g["lpj2"])
+    m.update_param_epoch()
+    for k in ("W", "pies", "mus", "Psi", "sigma2"):
+        assert np.allclose(m.theta[k], g[k + "_new"], rtol=1e-7, atol=1e-7), k
+
+
+def test_golden_dedup_merge():
+    g = load_golden("dedup_merge.npz")
+    lpj = g["new_lpj"].copy()
+    ost.set_redundant_lpj_to_low(g["new_K"], lpj, g["all_K"][g["idx"]])
+    assert np.array_equal(lpj, g["marked_lpj"])
+    lpj_np = g["new_lpj"].copy()
+    ost.set_redundant_lpj_to_low(g["new_K"], lpj_np, g["all_K"][g["idx"]], low=ost.LOW_LPJ)  # numpy path
+    assert np.array_equal(lpj_np, g["marked_lpj"])
+    K, L = g["all_K"].copy(), g["all_lpj"].copy()
+    nsubs = ost.update_states_for_batch(g["new_K"], lpj, g["idx"], K, L)
+    assert nsubs == int(g["nsubs"])
+    assert np.array_equal(L, g["lpj_after"])
+    # where the cut falls inside the block of marked (equal -1e20) children torch.topk's choice is
+    # unspecified; compare the state rows whose lpj is above the sentinel
+    live = g["lpj_after"] > -1e19
+    assert np.array_equal(K[live], g["K_after"][live])
+    assert np.allclose(ost.lpj2pjc(g["all_lpj"]), g["pjc"], rtol=1e-13)
+    assert np.allclose(ost.mean_posterior(g["g"], g["all_lpj"]), g["mean_post"], rtol=1e-12)
+
+
+def test_compiled_reference_dedup_matches_oracle():
+    ref = load_ref_dedup()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(0)
+    for dt in (np.float64, np.float32):
+        new = (rng.random((50, 12, 5)) < 0.4).astype(np.uint8)
+        old = (rng.random((50, 9, 5)) < 0.4).astype(np.uint8)
+        a = rng.standard_normal((50, 12)).astype(dt)
+        b, c = a.copy(), a.copy()
+        ref(new.view(np.int8), a, old.view(np.int8))
+        ost.set_redundant_lpj_to_low(new, b, old)                      # C restatement
+        ost.set_redundant_lpj_to_low(new, c, old, low=ost.LOW_LPJ)     # numpy restatement
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+        assert (a < -1e19).sum() > 50
+
+
+def test_golden_trainer_bsc_fullem():
+    """BSC + FullEM, 4 EM epochs, batches of 16: F trajectory and theta against the reference."""
+    g = load_golden("trainer_bsc_fullem.npz")
+    Y = g["Y"]
+    N, D = Y.shape
+    H = g["W0"].shape[1]
+    m = om.BSC(H, D, g["W0"], g["sigma20"], g["pies0"])
+    K = np.tile(ost.state_matrix(H)[None], (N, 1, 1))
+    for ep in range(4):
+        for b0 in range(0, N, 16):
+            sl = slice(b0, b0 + 16)
+            lpj = m.log_pseudo_joint(Y[sl], K[sl])
+            m.update_param_batch(Y[sl], K[sl], lpj)
+        m.update_param_epoch()
+        lpj = m.log_pseudo_joint(Y, K)
+        F = m.free_energy(Y, K, lpj)
+        assert math.isclose(F, g["F_after"][ep], rel_tol=1e-9), ep
+        assert np.allclose(m.theta["W"], g["W"][ep], rtol=1e-7, atol=1e-9)
+        assert np.allclose(m.theta["pies"], g["pies"][ep], rtol=1e-9)
+        assert np.allclose(m.theta["sigma2"], g["sigma2"][ep], rtol=1e-9)
+
+
+# ------------------------------------------------------------------ EVO operators (distributional)
+def _chi2_ok(obs_counts, exp_p, slack=5.0):
+    n = obs_counts.sum()
+    exp = np.maximum(exp_p * n, 1e-9)
+    chi2 = ((obs_counts - exp) ** 2 / exp).sum()
+    dof = max(len(exp_p) - 1, 1)
+    return chi2 < dof + slack * math.sqrt(2 * dof) + 10
+
+
+def test_evo_sparseflip_matches_reference_frequencies():
+    g = load_golden("evo_stats.npz")
+    parents, C = g["parents"], int(g["C"])
+    reps = 4000
+    par = np.repeat(parents, reps, axis=0)
+    ch = oevo.sparseflip(par, C, float(g["sparsity"]), float(g["p_bf"]), np.arange(reps), seed=3, step=0, gen=0)
+    freq = (ch != np.repeat(par, C, axis=1)).mean(axis=0)
+    # analytic p0/p1 (evo.py:310-316) and the reference's empirical frequencies (20000 draws)
+    p0, p1 = oevo.sparseflip_probs(parents[0].sum(-1), parents.shape[-1], float(g["sparsity"]), float(g["p_bf"]))
+    want = np.where(np.repeat(parents[0], C, axis=0) == 1, np.repeat(p1, C)[:, None], np.repeat(p0, C)[:, None])
+    want = np.clip(want, 0, 1)
+    sd = np.sqrt(want * (1 - want) / reps) + 1e-4
+    assert (np.abs(freq - want) < 5 * sd).all()
+    sd_ref = np.sqrt(want * (1 - want) / int(g["reps"])) + 1e-4
+    assert (np.abs(g["sparseflip_freq"] - want) < 5 * sd_ref).all()
+
+
+def test_evo_randflip_properties_and_frequencies():
+    g = load_golden("evo_stats.npz")
+    parents, C = g["parents"], int(g["C"])
+    H = parents.shape[-1]
+    reps = 4000
+    par = np.repeat(parents, reps, axis=0)
+    ch = oevo.randflip(par, C, np.arange(reps), seed=5, step=1, gen=0)
+    diff = ch != np.repeat(par, C, axis=1)
+    assert (diff.sum(-1) == 1).all()                       # test/evo_test.py:59-87
+    pos = diff.argmax(-1).reshape(reps, -1, C)
+    assert (pos[:, :, 0] != pos[:, :, 1]).all()            # distinct bits per parent (evo.py:263-268)
+    freq = diff.mean(axis=0)
+    assert np.abs(freq - 1.0 / H).max() < 5 * math.sqrt((1 / H) * (1 - 1 / H) / reps)
+    assert np.abs(g["randflip_freq"] - 1.0 / H).max() < 5 * math.sqrt((1 / H) * (1 - 1 / H) / int(g["reps"]))
+    assert float(g["randflip_pair_same"]) == 0.0
+
+
+def test_evo_cross_properties_and_mean():
+    g = load_golden("evo_stats.npz")
+    parents = g["parents"]
+    P, H = parents.shape[1:]
+    reps = 4000
+    par = np.repeat(parents, reps, axis=0)
+    ch = oevo.cross(par, np.arange(reps), seed=9, step=2, gen=1)
+    from itertools import combinations
+    for k, (a, b) in enumerate(combinations(range(P), 2)):  # test/evo_test.py:155-195
+        assert np.array_equal(ch[:, 2 * k].astype(int) + ch[:, 2 * k + 1], par[:, a].astype(int) + par[:, b])
+        assert np.array_equal(ch[:, 2 * k, 0], par[:, a, 0]) and np.array_equal(ch[:, 2 * k, -1], par[:, b, -1])
+    assert np.abs(ch.mean(axis=0) - g["cross_mean"]).max() < 0.04
+
+
+def test_evo_randparents_uniform_distinct():
+    g = load_golden("evo_stats.npz")
+    S = g["cand"].shape[1]
+    reps = 6000
+    idx = oevo.randparents_idx(np.arange(reps), S, 3, seed=1, step=0, gen=0)
+    assert all(len(set(r)) == 3 for r in idx)
+    for p in range(3):
+        cnt = np.bincount(idx[:, p], minlength=S)
+        assert _chi2_ok(cnt, np.full(S, 1 / S))
+        assert np.abs(g["rand_hist"][p] - 1 / S).max() < 0.03
+
+
+@pytest.mark.parametrize("B", [1, 4])
+def test_evo_fitparents_matches_reference_quirk(B):
+    """Q3: batch-global normaliser + `S-1-count` index; the parent histogram depends on B."""
+    g = load_golden("evo_stats.npz")
+    lpj = np.repeat(g["cand_lpj"], B, axis=0)
+    S = lpj.shape[1]
+    cnt = np.zeros(S)
+    reps = 3000
+    for r in range(reps):
+        idx = oevo.fitparents_idx(lpj, np.arange(B) + B * r, 3, seed=2, step=r % 7, gen=0)
+        cnt += np.bincount(idx.ravel(), minlength=S)
+    assert _chi2_ok(cnt, g[f"fit_hist_B{B}"], slack=8.0)
+
+
+def test_evo_evolve_and_update_invariants():
+    """test/evo_test.py:290-327 with the integer-valued DummyModel."""
+    rng = np.random.default_rng(0)
+    N, S, H = 6, 5, 8
+    weights = 2.0 ** np.arange(H)
+
+    def lpj_fn(states):
+        return (states * weights).sum(-1)
+
+    for mutation, sel in (("randflip", "batch_fitparents"), ("sparseflip", "randparents"),
+                          ("cross_randflip", "randparents"), ("cross_sparseflip", "batch_fitparents"), ("cross", "randparents")):
+        K = np.stack([ost.generate_unique_states(S, H, rng=rng) for _ in range(N)])
+        lpj = lpj_fn(K)
+        before = lpj.sum(1)
+        new_s, new_l = oevo.evolve_states(lpj, K, lpj_fn, 3, 2, 2, sel, mutation, 0.2, 1.0 / H,
+                                          np.arange(N), seed=4, step=0)
+        assert new_s.shape == (N, oevo.get_n_new_states(mutation, 3, 2, 2), H)
+        nsubs = ost.update_states_for_batch(new_s, new_l, np.arange(N), K, lpj)
+        assert 0 <= nsubs <= N * S
+        assert (lpj.sum(1) >= before - 1e-10).all()
+        assert (np.diff(lpj, axis=1) >= 0).all()
+        for n in range(N):  # K_n stays duplicate-free
+            assert len({tuple(r) for r in K[n]}) == S
+
+
+def test_pack_unpack_roundtrip():
+    rng = np.random.default_rng(0)
+    for H in (1, 7, 64, 65, 130, 256):
+        K = (rng.random((3, 4, H)) < 0.5).astype(np.uint8)
+        P = ost.pack_states(K)
+        assert P.shape == (3, 4, ost.n_words(H)) and P.dtype == np.uint64
+        assert np.array_equal(ost.unpack_states(P, H), K)
+    assert np.array_equal(ost.state_matrix(3)[5], [1, 0, 1])  # MSB first (fullem.py:26)
