@@ -1,0 +1,205 @@
+/* tvo_b200 — C ABI of the B200-native TVO hot path (truncated E-step + M-step accumulation).
+ *
+ * This is the drop-in boundary.  The reference (tvlearn/tvo) has no FFI for this path: its
+ * boundary is a duck-typed Python protocol (tvo/utils/model_protocols.py:15-229,
+ * tvo/variational/TVOVariationalStates.py:47-56) plus ONE native routine
+ * (tvo/variational/_set_redundant_lpj_to_low_CPU.pyx:13).  Each entry point below names the
+ * reference code it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a TVO_E* code otherwise; tvo_last_error() returns a
+ *    thread-local message.  Nothing throws across the boundary.
+ *  - all pointers are DEVICE pointers unless the name ends in _host; buffers are borrowed for the
+ *    duration of the call (the caller owns them; typically torch tensors).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
+ *    enqueue work; they never synchronise unless documented.
+ *  - states are bit-packed: state row = W64 = ceil(H/64) uint64 words, bit (h%64) of word (h/64)
+ *    is s_h.  K is (N, S, W64) row-major; lpj is (N, S) row-major.
+ *  - `idx` (int64, may be NULL) selects rows of the dataset-sized arrays K/lpj for a batch;
+ *    NULL means rows 0..B-1.  The global datapoint index that addresses the random stream is
+ *    n_offset + (idx ? idx[b] : b).
+ *  - suffix _f64 / _f32 is the storage AND arithmetic type of Y, theta and lpj ("precision" in
+ *    the reference).  M-step statistics are always accumulated in fp64.
+ */
+#ifndef TVO_B200_H
+#define TVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVO_OK 0
+#define TVO_EINVAL 1     /* bad argument (message says which) */
+#define TVO_ECUDA 2      /* CUDA runtime error (message carries cudaGetErrorString) */
+#define TVO_EUNSUPPORTED 3
+#define TVO_ENONFINITE 4 /* reserved for host-side checks of the nonfinite flag */
+
+#define TVO_ABI_VERSION 1
+
+/* parent selection (tvo/variational/evo.py:223) */
+#define TVO_SEL_RANDPARENTS 0      /* batch_randparents  evo.py:436-451 */
+#define TVO_SEL_FITPARENTS 1       /* batch_fitparents   evo.py:397-433, batch-global normaliser (quirk Q3) */
+#define TVO_SEL_FITPARENTS_FIXED 2 /* per-datapoint normaliser + inverse-CDF index (documented correction) */
+/* mutation (evo.py:224-230) */
+#define TVO_MUT_RANDFLIP 0
+#define TVO_MUT_SPARSEFLIP 1
+#define TVO_MUT_CROSS 2
+#define TVO_MUT_CROSS_RANDFLIP 3
+#define TVO_MUT_CROSS_SPARSEFLIP 4
+/* models */
+#define TVO_MODEL_BSC 0
+#define TVO_MODEL_NOISYOR 1
+#define TVO_MODEL_SSSC 2
+
+typedef struct {
+  int32_t parent_selection; /* TVO_SEL_* */
+  int32_t mutation;         /* TVO_MUT_* */
+  int32_t n_parents;
+  int32_t n_children; /* per parent (ignored for cross*, where it is n_parents-1) */
+  int32_t n_generations;
+  int32_t reserved;
+  double p_bf;       /* bitflip_frequency (sparseflip) */
+  uint64_t seed;     /* Philox key */
+  uint32_t step;     /* E-step counter (epoch * batches + batch), part of the Philox counter */
+  uint32_t n_offset; /* global index of local datapoint 0 (rank offset) */
+} tvo_evo_config;
+
+/* dedup sentinel written for redundant children: (float)-1e20, as the reference's CPU path
+ * (_set_redundant_lpj_to_low_CPU.pyx:17) */
+#define TVO_LOW_LPJ_F32 (-1e20f)
+
+int tvo_abi_version(void);
+const char *tvo_last_error(void);
+/* number of kernels launched by this library in the calling process since load / last reset */
+int64_t tvo_launch_count(void);
+void tvo_reset_launch_count(void);
+int tvo_device_sm_count(int *out);
+
+/* ---- state layout: replaces `states.to(dtype=...)` casts (bsc.py:102, noisyor.py:78) ---- */
+int tvo_pack_states(const uint8_t *K_u8, uint64_t *K_packed, int64_t n_states, int32_t H, void *stream);
+int tvo_unpack_states(const uint64_t *K_packed, uint8_t *K_u8, int64_t n_states, int32_t H, void *stream);
+/* all 2^H states, row i = binary of i MSB first (fullem.py:14-28); out is (2^H, W64) */
+int tvo_state_matrix(uint64_t *K_packed, int32_t H, void *stream);
+
+/* ---- workspace sizes (bytes) ---- */
+int64_t tvo_bsc_theta_ws_bytes(int32_t H, int32_t D, int32_t is_f64);
+
+/* ---- BSC (tvo/models/bsc.py) ---- */
+/* Digest theta into the kernel-friendly form (padded W^T, log-odds prior, constants).  Runs on
+ * the device, no host sync.  W is (D,H) row-major as in the reference; pies has n_pies = H or 1
+ * entries (individual_priors, bsc.py:107-112); sigma2 has 1.  Must be re-run whenever theta
+ * changes (theta is user-rebindable; nothing is cached across calls). */
+int tvo_bsc_prepare_f64(const double *W, const double *pies, int32_t n_pies, const double *sigma2, int32_t H,
+                        int32_t D, void *theta_ws, void *stream);
+int tvo_bsc_prepare_f32(const float *W, const float *pies, int32_t n_pies, const float *sigma2, int32_t H,
+                        int32_t D, void *theta_ws, void *stream);
+
+/* log_pseudo_joint (bsc.py:100-119).  Y is (B, D) with row stride ldY; K row for datapoint b is
+ * K + (idx?idx[b]:b) * k_stride_n words (k_stride_n = 0 broadcasts one state set, as FullEM's
+ * stride-0 view fullem.py:48); out lpj_out[(idx?idx[b]:b) * lpj_stride_n + s].  NaN entries of Y
+ * are skipped (to.nansum, bsc.py:115). */
+int tvo_bsc_lpj_f64(const double *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx,
+                    const void *theta_ws, double *lpj_out, int64_t lpj_stride_n, int64_t B, int32_t S,
+                    int32_t H, int32_t D, void *stream);
+int tvo_bsc_lpj_f32(const float *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx,
+                    const void *theta_ws, float *lpj_out, int64_t lpj_stride_n, int64_t B, int32_t S, int32_t H,
+                    int32_t D, void *stream);
+
+/* ---- candidate generation (tvo/variational/evo.py:118-451) ---- */
+/* One EA generation for a batch: select n_parents from `cand` (B rows of S_c states, lpj cand_lpj)
+ * and mutate them into `children` (B, S_gen, W64), S_gen = P*C or P*(P-1).  cand rows are addressed
+ * through idx/cand_stride_n like K above; cand_lpj may be NULL for randparents.  `sparsity` is a
+ * device scalar (double) = mean(pies) (evo.py:109), read by sparseflip.  fit_norm (device, 2
+ * doubles {m, T}) is the batch-global fitness normaliser of evo.py:404-406, produced by
+ * tvo_fit_norm_*; required for TVO_SEL_FITPARENTS only. */
+int tvo_evo_generation_f64(const uint64_t *cand, int64_t cand_stride_n, const double *cand_lpj,
+                           int64_t cand_lpj_stride_n, const int64_t *idx, int32_t cand_indexed, int32_t S_c,
+                           uint64_t *children, const tvo_evo_config *cfg, int32_t gen, const double *sparsity,
+                           const double *fit_norm, int64_t B, int32_t H, void *stream);
+int tvo_evo_generation_f32(const uint64_t *cand, int64_t cand_stride_n, const float *cand_lpj,
+                           int64_t cand_lpj_stride_n, const int64_t *idx, int32_t cand_indexed, int32_t S_c,
+                           uint64_t *children, const tvo_evo_config *cfg, int32_t gen, const double *sparsity,
+                           const double *fit_norm, int64_t B, int32_t H, void *stream);
+/* {m, T} of evo.py:404-406 over a (B, S_c) lpj block (rows through idx if indexed). */
+int tvo_fit_norm_f64(const double *lpj, int64_t stride_n, const int64_t *idx, int64_t B, int32_t S_c,
+                     double *fit_norm_out, void *stream);
+int tvo_fit_norm_f32(const float *lpj, int64_t stride_n, const int64_t *idx, int64_t B, int32_t S_c,
+                     double *fit_norm_out, void *stream);
+/* RandomSampledVarStates.py:57-59: every bit ~ Bernoulli(sparsity); out (B, S_new, W64) */
+int tvo_random_states(uint64_t *out, const int64_t *idx, int64_t B, int32_t S_new, int32_t H, double sparsity,
+                      uint64_t seed, uint32_t step, uint32_t n_offset, void *stream);
+
+/* ---- dedup: replaces set_redundant_lpj_to_low_CPU (the .pyx, :13-30) and
+ *      _set_redundant_lpj_to_low_GPU (_utils.py:59-83).  new_lpj (B,S_new) is modified in place;
+ *      old states are K rows through idx. ---- */
+int tvo_mark_redundant_f64(const uint64_t *new_states, double *new_lpj, const uint64_t *K, int64_t k_stride_n,
+                           const int64_t *idx, int64_t B, int32_t S_new, int32_t S, int32_t H, void *stream);
+int tvo_mark_redundant_f32(const uint64_t *new_states, float *new_lpj, const uint64_t *K, int64_t k_stride_n,
+                           const int64_t *idx, int64_t B, int32_t S_new, int32_t S, int32_t H, void *stream);
+
+/* ---- top-S merge: replaces update_states_for_batch (_utils.py:124-179).  K/lpj rows (through
+ *      idx) are overwritten with the S best of old+new in ascending lpj order (best last); ties go
+ *      to the lower concatenated index.  *nsubs (device int64) is INCREMENTED by the number of
+ *      selected children. ---- */
+int tvo_select_topS_f64(const uint64_t *new_states, const double *new_lpj, uint64_t *K, double *lpj,
+                        const int64_t *idx, int64_t B, int32_t S_new, int32_t S, int32_t H, int64_t *nsubs,
+                        void *stream);
+int tvo_select_topS_f32(const uint64_t *new_states, const float *new_lpj, uint64_t *K, float *lpj,
+                        const int64_t *idx, int64_t B, int32_t S_new, int32_t S, int32_t H, int64_t *nsubs,
+                        void *stream);
+
+/* ---- fused E-step for BSC: replaces EVOVariationalStates.update (evo.py:80-115) end to end:
+ *      re-score K under theta, G generations of select+mutate+score with the children kept in
+ *      shared memory, dedup against the original K, top-S merge, nsubs.  fit_norm is scratch
+ *      (2 doubles) used only by TVO_SEL_FITPARENTS. ---- */
+int tvo_estep_evo_bsc_f64(const double *Y, int64_t ldY, const int64_t *idx, uint64_t *K, double *lpj,
+                          const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity,
+                          double *fit_norm, int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs,
+                          void *stream);
+int tvo_estep_evo_bsc_f32(const float *Y, int64_t ldY, const int64_t *idx, uint64_t *K, float *lpj,
+                          const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity,
+                          double *fit_norm, int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs,
+                          void *stream);
+
+/* ---- posterior weights: lpj2pjc / mean_posterior (_utils.py:182-230) ---- */
+int tvo_lpj2pjc_f64(const double *lpj, double *pjc, int64_t N, int32_t S, void *stream);
+int tvo_lpj2pjc_f32(const float *lpj, float *pjc, int64_t N, int32_t S, void *stream);
+/* out[n, :] = sum_s softmax(lpj[n,:])_s g[n, s, :]   (g is (N,S,G)) */
+int tvo_mean_posterior_f64(const double *g, const double *lpj, double *out, int64_t N, int32_t S, int64_t G,
+                           void *stream);
+int tvo_mean_posterior_f32(const float *g, const float *lpj, float *out, int64_t N, int32_t S, int64_t G,
+                           void *stream);
+
+/* ---- free energy: replaces Optimized.free_energy (model_protocols.py:179-193) with the model's
+ *      log_joint constant (bsc.py:121-132).  *F_out (device double) is INCREMENTED by
+ *      sum_b logsumexp_s(lpj[b,s]) + const_b, const_b = sum_h log(1-pi_h) - D_b/2 log(2 pi sigma2),
+ *      D_b = #non-NaN of y_b (Y may be NULL => D_b = D). ---- */
+int tvo_bsc_free_energy_f64(const double *Y, int64_t ldY, const double *lpj, int64_t lpj_stride_n,
+                            const int64_t *idx, const void *theta_ws, int64_t B, int32_t S, int32_t D,
+                            double *F_out, void *stream);
+int tvo_bsc_free_energy_f32(const float *Y, int64_t ldY, const float *lpj, int64_t lpj_stride_n,
+                            const int64_t *idx, const void *theta_ws, int64_t B, int32_t S, int32_t D,
+                            double *F_out, void *stream);
+
+/* ---- BSC M-step accumulation: replaces BSC.update_param_batch (bsc.py:134-158).  `stats` is one
+ *      packed fp64 buffer [WpT (H*D, i.e. my_Wp transposed) | Wq (H*H) | pies (H) | sigma2 (1) |
+ *      N (1) | F (1)] that is INCREMENTED; q(s) = softmax(lpj) lives on chip only.  F gets the
+ *      batch free energy (same value as tvo_bsc_free_energy).  exact_residual = 1 recomputes
+ *      ||y - W s||^2 from Y and theta as the reference does (bsc.py:140-150); 0 derives it from
+ *      lpj, valid when lpj was produced from the same Y and theta (the Trainer's E-step/M-step
+ *      order, Trainer.py:239-249). ---- */
+int64_t tvo_bsc_stats_len(int32_t H, int32_t D);
+int tvo_bsc_mstep_f64(const double *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                      const double *lpj, int64_t lpj_stride_n, const void *theta_ws, double *stats, int64_t B,
+                      int32_t S, int32_t H, int32_t D, int32_t exact_residual, void *stream);
+int tvo_bsc_mstep_f32(const float *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                      const float *lpj, int64_t lpj_stride_n, const void *theta_ws, double *stats, int64_t B,
+                      int32_t S, int32_t H, int32_t D, int32_t exact_residual, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVO_B200_H */

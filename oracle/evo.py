@@ -177,6 +177,91 @@ def cross(parents, n_glob, seed, step, gen):
     return children
 
 
+# ----------------------------------------------------------------------------- reference-cost mode
+# The functions below restate the reference's operators WITH the reference's own way of drawing
+# random numbers (one fp64 uniform per bit / per candidate from a global generator, evo.py:263,325,
+# 363,414,440).  They are what bench.py times as the CPU baseline: same arithmetic, same memory
+# traffic and the same number of random draws as the reference's torch-CPU path.  Their output is
+# distributionally identical to the counter-based functions above but not stream-identical, so they
+# are never used for parity checks.
+def randparents_idx_np(rng, N, S_c, P):
+    return np.stack([rng.permutation(S_c)[:P] for _ in range(N)])  # evo.py:440-442 (python loop per datapoint)
+
+
+def fitparents_idx_np(rng, lpj, P):
+    m = float(np.float32(min(float(lpj.min()), 0.0)))
+    f = lpj - 2.0 * m
+    cum = np.cumsum(f / f.sum(), axis=-1)
+    x = rng.random((lpj.shape[0], P))
+    chosen = lpj.shape[1] - 1 - (x[:, :, None] < cum[:, None, :]).sum(axis=-1)
+    chosen[chosen < 0] += lpj.shape[1]
+    return chosen
+
+
+def randflip_np(rng, parents, C):
+    N, P, H = parents.shape
+    ind = np.argpartition(rng.random((N, P, H)), H - C, axis=2)[:, :, H - C:].reshape(N, P * C)  # topk(rand) :263
+    children = np.repeat(parents, C, axis=1).copy()
+    n_idx, s_idx = np.arange(N)[:, None], np.arange(P * C)[None, :]
+    children[n_idx, s_idx, ind] = 1 - children[n_idx, s_idx, ind]
+    return children
+
+
+def sparseflip_np(rng, parents, C, sparsity, p_bf):
+    N, P, H = parents.shape
+    p0, p1 = sparseflip_probs(parents.sum(axis=2), H, sparsity, p_bf)
+    children = np.repeat(parents, C, axis=1).copy()
+    p = np.where(children.astype(bool), np.repeat(p1, C, axis=1)[:, :, None], np.repeat(p0, C, axis=1)[:, :, None])
+    flips = rng.random((N, P * C, H)) < p  # evo.py:325
+    children[flips] = 1 - children[flips]
+    return children
+
+
+def cross_np(rng, parents):
+    N, P, H = parents.shape
+    pairs = list(combinations(range(P), 2))
+    cuts = rng.integers(1, H, size=(N, len(pairs)))  # evo.py:363
+    children = np.empty((N, 2 * len(pairs), H), dtype=np.uint8)
+    for k, (a, b) in enumerate(pairs):
+        low = np.arange(H)[None, :] < cuts[:, k][:, None]
+        children[:, 2 * k] = np.where(low, parents[:, a], parents[:, b])
+        children[:, 2 * k + 1] = np.where(low, parents[:, b], parents[:, a])
+    return children
+
+
+def evolve_states_np(rng, lpj, states, lpj_fn, n_parents, n_children, n_generations, parent_selection, mutation,
+                     sparsity, p_bf):
+    """evolve_states (evo.py:118-211) drawing from a numpy Generator like the reference draws from torch."""
+    N, S, H = states.shape
+    S_new = get_n_new_states(mutation, n_parents, n_children, n_generations)
+    per_gen = S_new // n_generations
+    new_states = np.empty((N, S_new, H), dtype=np.uint8)
+    new_lpj = np.empty((N, S_new), dtype=lpj.dtype)
+    for g in range(n_generations):
+        cand, cand_lpj = (states, lpj) if g == 0 else (new_states[:, (g - 1) * per_gen:g * per_gen],
+                                                       new_lpj[:, (g - 1) * per_gen:g * per_gen])
+        pidx = (randparents_idx_np(rng, N, cand.shape[1], n_parents) if parent_selection == "randparents"
+                else fitparents_idx_np(rng, cand_lpj, n_parents))
+        parents = take_parents(cand, pidx)
+        if mutation == "randflip":
+            ch = randflip_np(rng, parents, n_children)
+        elif mutation == "sparseflip":
+            ch = sparseflip_np(rng, parents, n_children, sparsity, p_bf)
+        elif mutation == "cross":
+            ch = cross_np(rng, parents)
+        elif mutation == "cross_randflip":
+            ch = randflip_np(rng, cross_np(rng, parents), 1)
+        elif mutation == "cross_sparseflip":
+            ch = sparseflip_np(rng, cross_np(rng, parents), 1, sparsity, p_bf)
+        else:
+            raise ValueError(mutation)
+        sl = slice(g * per_gen, (g + 1) * per_gen)
+        new_states[:, sl] = ch
+        new_lpj[:, sl] = lpj_fn(ch)
+    set_redundant_lpj_to_low(new_states, new_lpj, states)
+    return new_states, new_lpj
+
+
 def mutate(parents, mutation, n_children, sparsity, p_bf, n_glob, seed, step, gen):
     if mutation == "randflip":
         return randflip(parents, n_children, n_glob, seed, step, gen)

@@ -70,7 +70,8 @@ class BSC:
         q = lpj2pjc(lpj)
         self.my_pies += s_pjc.sum(axis=0)
         self.my_Wp += batch.T @ s_pjc
-        self.my_Wq += np.einsum("ijk,ijl->kl", Kf * q[:, :, None], Kf)
+        H = Kf.shape[2]
+        self.my_Wq += (Kf * q[:, :, None]).reshape(-1, H).T @ Kf.reshape(-1, H)  # einsum("ijk,ijl->kl") as a GEMM
         self.my_sigma2 += mean_posterior(((batch[:, None, :] - Wbar) ** 2).sum(axis=2), lpj).sum()
         self.my_N += batch.shape[0]
 

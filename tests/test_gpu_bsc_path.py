@@ -1,0 +1,582 @@
+"""GPU parity tests of the BSC hot path: every call goes through the C ABI (libtvo_b200.so) and is
+compared with the CPU oracle on identical seeded inputs and with the reference-generated fixtures.
+
+Bars: bit-exact for states / indices / counts; 1e-10 relative for fp64 floating point, 1e-4 for fp32
+(BASELINE north_star)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch as to
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+cuda = to.cuda.is_available()
+if cuda:
+    import tvo_b200
+    from tvo_b200 import _lib
+    from tvo_b200.models import BSC
+    from tvo_b200.trainer import Trainer
+    from tvo_b200.utils.data import TVODataLoader
+    from tvo_b200.utils.model_protocols import Trainable
+    from tvo_b200.variational import EVOVariationalStates, FullEM, RandomSampledVarStates
+    from tvo_b200.variational import _packed as pk
+    from tvo_b200.variational import _utils as vu
+    from tvo_b200.variational.fullem import state_matrix
+
+from oracle import evo as oevo
+from oracle import models as om
+from oracle import states as ost
+
+DEV = "cuda:0"
+RT64, RT32 = 1e-10, 1e-4
+
+
+def dev(a, dtype=None):
+    t = to.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def packed_np(K):
+    return to.from_numpy(ost.pack_states(K).view(np.int64)).to(DEV)
+
+
+def rand_K(rng, N, S, H, p=0.2):
+    """(N,S,H) uint8 with S distinct states per datapoint."""
+    K = np.zeros((N, S, H), np.uint8)
+    for n in range(N):
+        seen = {}
+        while len(seen) < S:
+            s = (rng.random(H) < p).astype(np.uint8)
+            seen.setdefault(s.tobytes(), s)
+        K[n] = list(seen.values())
+    return K
+
+
+# ----------------------------------------------------------------------------- layout
+@pytest.mark.parametrize("H", [1, 7, 63, 64, 65, 130, 256, 1024])
+def test_pack_unpack_matches_oracle(H):
+    rng = np.random.default_rng(H)
+    K = (rng.random((5, 3, H)) < 0.4).astype(np.uint8)
+    P = pk.pack(dev(K))
+    assert P.shape == (5, 3, ost.n_words(H))
+    assert np.array_equal(P.cpu().numpy().view(np.uint64), ost.pack_states(K))
+    assert np.array_equal(pk.unpack(P, H).cpu().numpy(), K)
+
+
+@pytest.mark.parametrize("H", [1, 3, 6, 11])
+def test_state_matrix(H):
+    assert np.array_equal(state_matrix(H, DEV).cpu().numpy(), ost.state_matrix(H))
+
+
+def test_packedstates_view_semantics():
+    rng = np.random.default_rng(0)
+    K = (rng.random((6, 4, 70)) < 0.3).astype(np.uint8)
+    ps = pk.PackedStates(pk.pack(dev(K)), 70)
+    assert tuple(ps.shape) == (6, 4, 70)
+    assert np.array_equal(ps[2].cpu().numpy(), K[2])
+    assert np.array_equal(ps[to.tensor([4, 1])].cpu().numpy(), K[[4, 1]])
+    assert np.array_equal(ps[1:3, 2].cpu().numpy(), K[1:3, 2])
+    ps[3] = to.ones(4, 70, dtype=to.uint8)
+    assert int(ps[3].sum()) == 280 and int(ps.sum()) == K.sum() - K[3].sum() + 280
+
+
+# ----------------------------------------------------------------------------- candidate generation
+def gen_children(K, lpj, sel, mut, P, Cn, G, gen, seed, step, n_offset, p_bf, sparsity, idx=None, dtype=to.float64):
+    N, S, H = K.shape
+    B = N if idx is None else len(idx)
+    cfg = _lib.EvoConfig(_lib.SEL[sel], _lib.MUT[mut], P, Cn, G, 0, p_bf, seed, step, n_offset)
+    Sgen = P * (P - 1) if mut.startswith("cross") else P * Cn
+    W = ost.n_words(H)
+    out = to.empty((B, Sgen, W), dtype=to.int64, device=DEV)
+    Kp = packed_np(K)
+    lp = dev(lpj, dtype)
+    sp = to.tensor([sparsity], dtype=to.float64, device=DEV)
+    fn = to.zeros(2, dtype=to.float64, device=DEV)
+    sfx = _lib.sfx(dtype)
+    idx_t = None if idx is None else dev(np.asarray(idx, np.int64))
+    if sel == "batch_fitparents":
+        _lib.call(f"tvo_fit_norm_{sfx}", _lib.ptr(lp), S, _lib.ptr(idx_t), B, S, _lib.ptr(fn), _lib.stream())
+    _lib.call(f"tvo_evo_generation_{sfx}", _lib.ptr(Kp), S * W, _lib.ptr(lp), S, _lib.ptr(idx_t), 1, S, _lib.ptr(out),
+              C.byref(cfg), gen, _lib.ptr(sp), _lib.ptr(fn), B, H, _lib.stream())
+    return ost.unpack_states(out.cpu().numpy().view(np.uint64), H), fn.cpu().numpy()
+
+
+@pytest.mark.parametrize("H", [5, 64, 100, 256])
+@pytest.mark.parametrize("sel,mut,P,Cn", [
+    ("randparents", "randflip", 4, 3), ("randparents", "sparseflip", 5, 2), ("randparents", "cross", 4, None),
+    ("randparents", "cross_randflip", 3, None), ("randparents", "cross_sparseflip", 4, None),
+    ("batch_fitparents", "randflip", 3, 2), ("fitparents_fixed", "sparseflip", 4, 2),
+])
+def test_generation_bit_exact(H, sel, mut, P, Cn):
+    rng = np.random.default_rng(H + P)
+    N, S = 9, 7
+    K = (rng.random((N, S, H)) < 0.25).astype(np.uint8)
+    lpj = rng.standard_normal((N, S)) * 3 - 5
+    Cn_eff = P - 1 if mut.startswith("cross") else Cn
+    seed, step, gen, n_off, p_bf, sparsity = 0xDEADBEEF12345, 5, 1, 1000, 1.7 / H, 0.21
+    idx = np.array([8, 0, 3, 3, 5])
+    got, fn = gen_children(K, lpj, sel, mut, P, Cn_eff, 2, gen, seed, step, n_off, p_bf, sparsity, idx=idx)
+    n_glob = n_off + idx
+    Kb, lb = K[idx], lpj[idx]
+    if sel == "randparents":
+        pidx = oevo.randparents_idx(n_glob, S, P, seed, step, gen)
+    elif sel == "batch_fitparents":
+        m, T = oevo.fit_norm(lb)
+        assert fn[0] == m and math.isclose(fn[1], T, rel_tol=1e-13)
+        pidx = oevo.fitparents_idx(lb, n_glob, P, seed, step, gen, norm=(fn[0], fn[1]))
+    else:
+        pidx = oevo.fitparents_idx(lb, n_glob, P, seed, step, gen, corrected=True)
+    want = oevo.mutate(oevo.take_parents(Kb, pidx), mut, Cn_eff, sparsity, p_bf, n_glob, seed, step, gen)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_random_states_bit_exact_and_rate():
+    N, S_new, H = 40, 9, 100
+    out = to.empty((N, S_new, ost.n_words(H)), dtype=to.int64, device=DEV)
+    _lib.call("tvo_random_states", _lib.ptr(out), None, N, S_new, H, 0.3, 77, 2, 10, _lib.stream())
+    got = ost.unpack_states(out.cpu().numpy().view(np.uint64), H)
+    want = oevo.random_states(N, S_new, H, 0.3, 10 + np.arange(N), 77, 2)
+    assert np.array_equal(got, want)
+    assert abs(got.mean() - 0.3) < 0.01
+
+
+# ----------------------------------------------------------------------------- dedup / merge
+def test_dedup_and_merge_golden():
+    g = load_golden("dedup_merge.npz")
+    new_lpj = dev(g["new_lpj"])
+    vu.set_redundant_lpj_to_low(dev(g["new_K"]), new_lpj, dev(g["all_K"][g["idx"]]))
+    assert np.array_equal(new_lpj.cpu().numpy(), g["marked_lpj"])
+    K, L = dev(g["all_K"]), dev(g["all_lpj"])
+    nsubs = vu.update_states_for_batch(dev(g["new_K"]), new_lpj, dev(g["idx"]), K, L)
+    assert nsubs == int(g["nsubs"])
+    assert np.array_equal(L.cpu().numpy(), g["lpj_after"])
+    live = g["lpj_after"] > -1e19
+    assert np.array_equal(K.cpu().numpy()[live], g["K_after"][live])
+    # bit-exact against the oracle, including the tie rule inside the sentinel block
+    Ko, Lo = g["all_K"].copy(), g["all_lpj"].copy()
+    ost.update_states_for_batch(g["new_K"], g["marked_lpj"], g["idx"], Ko, Lo)
+    assert np.array_equal(K.cpu().numpy(), Ko) and np.array_equal(L.cpu().numpy(), Lo)
+
+
+def test_reference_kats_dedup_merge():
+    # test/variationalutils_test.py:51-102 through the drop-in functions
+    all_states = to.zeros((4, 3, 1), dtype=to.uint8, device=DEV)
+    all_lpj = to.zeros((4, 3), dtype=to.float64, device=DEV)
+    n = vu.update_states_for_batch(to.ones((2, 2, 1), dtype=to.uint8, device=DEV),
+                                   to.ones((2, 2), dtype=to.float64, device=DEV), to.arange(2), all_states, all_lpj)
+    assert n == 4
+    assert all_states.cpu().tolist() == [[[0], [1], [1]], [[0], [1], [1]], [[0], [0], [0]], [[0], [0], [0]]]
+    old = dev(np.array([[[0, 1, 1], [1, 0, 0]], [[0, 1, 1], [1, 0, 1]], [[0, 1, 1], [1, 1, 1]]], np.uint8))
+    new = dev(np.array([[[0, 0, 0], [1, 1, 0]], [[0, 0, 0], [1, 0, 1]], [[0, 0, 0], [0, 0, 0]]], np.uint8))
+    lpj = to.ones((3, 2), dtype=to.float64, device=DEV)
+    vu.set_redundant_lpj_to_low(new, lpj, old)
+    L = float(np.float32(-1e20))
+    assert lpj.cpu().tolist() == [[1, 1], [1, L], [L, 1]]
+
+
+@pytest.mark.parametrize("dtype", [to.float64, to.float32])
+@pytest.mark.parametrize("H,S,Snew", [(4, 6, 9), (70, 5, 40), (256, 64, 64), (300, 33, 17)])
+def test_dedup_merge_random_vs_oracle(dtype, H, S, Snew):
+    rng = np.random.default_rng(S * Snew)
+    N, Ntot = 50, 80
+    npd = np.float64 if dtype == to.float64 else np.float32
+    all_K = (rng.random((Ntot, S, H)) < 0.1).astype(np.uint8)
+    all_lpj = rng.standard_normal((Ntot, S)).astype(npd)
+    idx = rng.permutation(Ntot)[:N]
+    new_K = (rng.random((N, Snew, H)) < 0.1).astype(np.uint8)
+    new_K[:, 1] = new_K[:, 0]                      # duplicates among children
+    new_K[:, 2] = all_K[idx, 0]                    # duplicate of an old state
+    new_lpj = rng.standard_normal((N, Snew)).astype(npd)
+    new_lpj[:, 3] = all_lpj[idx, 1]                # exact lpj tie old vs new
+    Kp, L = packed_np(all_K), dev(all_lpj)
+    nl = dev(new_lpj)
+    nsubs = to.zeros((), dtype=to.int64, device=DEV)
+    idx_t = dev(idx.astype(np.int64))
+    vu.mark_redundant_packed(packed_np(new_K), nl, Kp, idx_t, H)
+    want_l = new_lpj.copy()
+    ost.set_redundant_lpj_to_low(new_K, want_l, all_K[idx])
+    assert np.array_equal(nl.cpu().numpy(), want_l)
+    vu.select_topS_packed(packed_np(new_K), nl, Kp, L, idx_t, H, nsubs)
+    want_n = ost.update_states_for_batch(new_K, want_l, idx, all_K, all_lpj)
+    assert int(nsubs) == want_n
+    assert np.array_equal(ost.unpack_states(Kp.cpu().numpy().view(np.uint64), H), all_K)
+    assert np.array_equal(L.cpu().numpy(), all_lpj)
+
+
+# ----------------------------------------------------------------------------- BSC lpj / F / M-step
+@pytest.mark.parametrize("tag,indiv,dtype,tol", [("ind_f64", True, to.float64, RT64), ("single_f64", False, to.float64, RT64),
+                                                 ("ind_f32", True, to.float32, RT32)])
+def test_bsc_golden(tag, indiv, dtype, tol):
+    g = load_golden(f"bsc_{tag}.npz")
+    D, H = g["W"].shape
+    tvo_b200._set_device(to.device(DEV))
+    m = BSC(H, D, dev(g["W"]), dev(g["sigma2"]), dev(g["pies"]), individual_priors=indiv, precision=dtype)
+    Y, K = dev(g["Y"], dtype), dev(g["K"])
+    lpj = m.log_pseudo_joint(Y, K)
+    assert lpj.dtype == dtype and lpj.device == K.device
+    assert np.allclose(lpj.cpu().numpy(), g["lpj"], rtol=tol, atol=tol)
+    assert np.allclose(m.log_joint(Y, K, lpj).cpu().numpy(), g["log_joint"], rtol=tol, atol=tol)
+    N, S = g["K"].shape[:2]
+    st = EVOVariationalStates(N, H, S, dtype, "randparents", "randflip", 2, 1, 1, K_init=K)
+    st.lpj[:] = lpj
+    assert math.isclose(m.free_energy(to.arange(N), Y, st), float(g["F"]), rel_tol=max(tol, 1e-12))
+    Yn = dev(g["Ynan"], dtype)
+    assert np.allclose(m.log_pseudo_joint(Yn, K).cpu().numpy(), g["lpj_nan"], rtol=tol, atol=tol)
+    assert np.allclose(m.log_joint(Yn, K).cpu().numpy(), g["log_joint_nan"], rtol=tol, atol=tol)
+    # M-step (exact residual path: lpj was assigned, not produced by the E-step)
+    st.lpj[:] = dev(g["lpj"], dtype)
+    m.update_param_batch(to.arange(N), Y, st)
+    for name in ("my_Wp", "my_Wq", "my_pies", "my_sigma2"):
+        assert np.allclose(getattr(m, name).cpu().numpy(), g[name], rtol=10 * tol, atol=10 * tol), name
+    assert int(m.my_N.item()) == N
+    N2 = g["K2"].shape[0]
+    st2 = EVOVariationalStates(N2, H, S, dtype, "randparents", "randflip", 2, 1, 1, K_init=dev(g["K2"]))
+    st2.lpj[:] = dev(g["lpj2"], dtype)
+    m.update_param_batch(to.arange(N2), dev(g["Y2"], dtype), st2)
+    for solver in ("cpu", "gpu"):
+        m2 = BSC(H, D, dev(g["W"]), dev(g["sigma2"]), dev(g["pies"]), individual_priors=indiv, precision=dtype)
+        m2._stats.copy_(m._stats)
+        m2.W_solver = solver
+        m2.update_param_epoch()
+        wt = 1e-8 if dtype == to.float64 else 5e-3
+        assert np.allclose(m2.theta["W"].cpu().numpy(), g["W_new"], rtol=wt, atol=wt), solver
+        assert np.allclose(m2.theta["pies"].cpu().numpy(), g["pies_new"], rtol=10 * tol)
+        assert np.allclose(m2.theta["sigma2"].cpu().numpy(), g["sigma2_new"], rtol=10 * tol)
+        assert float(m2._stats.abs().sum()) == 0.0
+
+
+def test_bsc_reference_closed_form_fullem():
+    # test/bsc_test.py:23-99 through FullEM (broadcast state set)
+    tvo_b200._set_device(to.device(DEV))
+    for indiv in (True, False):
+        H, D, N = 2, 1, 2
+        m = BSC(H, D, to.ones(D, H), to.tensor([1.0]), to.full((H if indiv else 1,), 0.5), individual_priors=indiv,
+                precision=to.float32)
+        st = FullEM(N, H, to.float32)
+        data = to.tensor([[0.0], [1.0]], device=DEV)
+        true_lpj = to.tensor([[0.0, -0.5, -0.5, -2.0], [-0.5, 0.0, 0.0, -0.5]], device=DEV)
+        lpj = m.log_pseudo_joint(data, st.K)
+        assert to.allclose(lpj, true_lpj)
+        assert st.update(to.arange(N), data, m) == 0
+        assert to.allclose(st.lpj, true_lpj)
+        const = 2 * np.log(0.5) - 0.5 * np.log(2 * math.pi)
+        true_F = float(to.log(to.exp(true_lpj.double() + const).sum(dim=1)).sum())
+        F0 = m.free_energy(to.arange(N), data, st)
+        assert math.isclose(F0, true_F, rel_tol=1e-6)
+        m.update_param_batch(to.arange(N), data, st)
+        m.update_param_epoch()
+        st.update(to.arange(N), data, m)
+        assert m.free_energy(to.arange(N), data, st) > F0
+
+
+@pytest.mark.parametrize("dtype,tol", [(to.float64, RT64), (to.float32, RT32)])
+@pytest.mark.parametrize("H,D,S", [(10, 3, 5), (64, 32, 8), (100, 144, 16), (256, 144, 64), (130, 300, 6), (1024, 256, 9)])
+def test_bsc_lpj_mstep_random_vs_oracle(dtype, tol, H, D, S):
+    rng = np.random.default_rng(H * D + S)
+    N = 33
+    npd = np.float64 if dtype == to.float64 else np.float32
+    W = rng.standard_normal((D, H)).astype(npd)
+    pies = rng.uniform(0.01, 0.3, H).astype(npd)
+    sigma2 = np.array([1.3], npd)
+    K = (rng.random((N, S, H)) < min(0.2, 6.0 / H)).astype(np.uint8)
+    K[0, 0] = 0
+    K[1, 1] = 1
+    Y = (rng.standard_normal((N, D)) * 2).astype(npd)
+    tvo_b200._set_device(to.device(DEV))
+    m = BSC(H, D, dev(W), dev(sigma2), dev(pies), precision=dtype)
+    o = om.BSC(H, D, W, sigma2, pies, precision=npd)
+    lpj = m.log_pseudo_joint(dev(Y), dev(K))
+    want = o.log_pseudo_joint(Y, K)
+    assert np.allclose(lpj.cpu().numpy(), want, rtol=tol, atol=tol * np.abs(want).max())
+    st = EVOVariationalStates(N, H, S, dtype, "randparents", "randflip", 2, 1, 1, K_init=dev(K))
+    idx = to.tensor(rng.permutation(N)[:20], device=DEV)
+    m._tvo_lpj_rows(st, idx, dev(Y)[idx])
+    assert np.allclose(st.lpj[idx].cpu().numpy(), want[idx.cpu().numpy()], rtol=tol, atol=tol * np.abs(want).max())
+    st.lpj[:] = dev(want)
+    Fw = o.free_energy(Y, K, want.astype(np.float64))
+    assert math.isclose(m.free_energy(to.arange(N), dev(Y), st), Fw, rel_tol=max(tol, 1e-11))
+    od = om.BSC(H, D, W.astype(np.float64), sigma2.astype(np.float64), pies.astype(np.float64))
+    od.update_param_batch(Y.astype(np.float64), K, want.astype(np.float64))
+    for exact in (True, False):
+        m._stats.zero_()
+        if exact:
+            m._fresh = None
+        else:  # pretend the E-step just produced lpj from (Y, theta): residual derived from lpj
+            Yd = dev(Y)
+            m._fresh = (m._theta_token(), Yd.data_ptr(), Yd._version, id(st))
+        Yd = dev(Y) if exact else Yd
+        m.update_param_batch(to.arange(N), Yd, st)
+        mt = 20 * tol
+        assert np.allclose(m.my_Wp.cpu().numpy(), od.my_Wp, rtol=mt, atol=mt * np.abs(od.my_Wp).max()), exact
+        assert np.allclose(m.my_Wq.cpu().numpy(), od.my_Wq, rtol=mt, atol=mt), exact
+        assert np.allclose(m.my_pies.cpu().numpy(), od.my_pies, rtol=mt, atol=mt), exact
+        assert np.allclose(m.my_sigma2.cpu().numpy(), od.my_sigma2, rtol=mt), exact
+        assert math.isclose(float(m._stats[-1]), Fw, rel_tol=max(tol, 1e-11))
+
+
+# ----------------------------------------------------------------------------- fused E-step
+def oracle_estep(o, Y, K, lpj_dtype, sel, mut, P, Cn, G, p_bf, n_glob, seed, step, sparsity=None):
+    lpj = o.log_pseudo_joint(Y, K).astype(lpj_dtype)
+    # sparsity must be the device's mean(pies): torch/numpy means can differ by an ulp and the
+    # reference's p0/p1 formula is singular at popcount == sparsity*H + H*p_bf
+    sparsity = float(o.theta["pies"].mean()) if sparsity is None else sparsity
+    new_s, new_l = oevo.evolve_states(lpj, K, lambda s: o.log_pseudo_joint(Y, s).astype(lpj_dtype), P, Cn, G,
+                                      "batch_fitparents" if "fitparents" in sel else sel, mut, sparsity, p_bf, n_glob, seed, step, fit_corrected=(sel == "fitparents_fixed"))
+    Kc, lc = K.copy(), lpj.copy()
+    nsubs = ost.update_states_for_batch(new_s, new_l, np.arange(len(K)), Kc, lc)
+    return Kc, lc, nsubs
+
+
+@pytest.mark.parametrize("dtype", [to.float64, to.float32])
+@pytest.mark.parametrize("H,D,S,sel,mut,P,Cn,G", [
+    (8, 16, 10, "randparents", "randflip", 3, 2, 2),
+    (40, 20, 12, "randparents", "sparseflip", 4, 2, 2),
+    (70, 33, 9, "fitparents_fixed", "sparseflip", 3, 3, 1),
+    (100, 144, 16, "randparents", "cross_randflip", 4, None, 1),
+    (64, 64, 8, "randparents", "cross_sparseflip", 3, None, 2),
+    (130, 50, 7, "fitparents_fixed", "cross", 3, None, 1),
+    (256, 144, 64, "randparents", "sparseflip", 16, 2, 2),
+])
+def test_fused_estep_bit_exact(dtype, H, D, S, sel, mut, P, Cn, G):
+    rng = np.random.default_rng(H + D + S)
+    N = 24
+    npd = np.float64 if dtype == to.float64 else np.float32
+    W = rng.standard_normal((D, H)).astype(npd)
+    pies = np.full(H, min(0.3, 4.0 / H), npd)
+    sigma2 = np.array([1.0], npd)
+    Y = ((rng.random((N, H)) < pies) @ W.T + rng.standard_normal((N, D))).astype(npd)
+    K = rand_K(rng, N, S, H, p=min(0.3, 4.0 / H))
+    tvo_b200._set_device(to.device(DEV))
+    m = BSC(H, D, dev(W), dev(sigma2), dev(pies), precision=dtype)
+    crossover = mut.startswith("cross")
+    kw = dict(bitflip_frequency=2.0 / H, seed=99, K_init=dev(K))
+    if mut == "cross":
+        st = EVOVariationalStates(N, H, S, dtype, sel, "cross", P, G, n_children=P - 1, **kw)
+    elif crossover:  # the reference's constructor convention: crossover=True prefixes "cross_"
+        st = EVOVariationalStates(N, H, S, dtype, sel, mut[len("cross_"):], P, G, crossover=True, **kw)
+    else:
+        st = EVOVariationalStates(N, H, S, dtype, sel, mut, P, G, n_children=Cn, **kw)
+    assert st.config["mutation"] == mut
+    st.n_offset = 500
+    o = om.BSC(H, D, W, sigma2, pies, precision=npd)
+    Kw, Lw = K, None
+    total = 0
+    for step in range(2):  # two consecutive E-steps: the second starts from the first one's output
+        Cn_eff = P - 1 if crossover else Cn
+        Kw, Lw, nsubs_w = oracle_estep(o, Y, Kw, npd, sel, st.config["mutation"], P, Cn_eff, G, 2.0 / H,
+                                       500 + np.arange(N), 99, step, sparsity=float(m._tvo_sparsity().item()))
+        nsubs = st.update(to.arange(N, device=DEV), dev(Y), m)
+        got_K = st.K.unpack().cpu().numpy()
+        if dtype == to.float64:
+            assert np.array_equal(got_K, Kw), f"K differs at step {step}"
+            assert nsubs == nsubs_w
+            assert np.allclose(st.lpj.cpu().numpy(), Lw, rtol=RT64, atol=RT64)
+        else:
+            # fp32: rounding can reorder near-ties; require set-equality on all but a few datapoints
+            same = [set(map(bytes, got_K[n])) == set(map(bytes, Kw[n])) for n in range(N)]
+            assert sum(same) >= N - 2
+            assert np.allclose(np.sort(st.lpj.cpu().numpy(), 1)[:, S // 2:], np.sort(Lw, 1)[:, S // 2:], rtol=1e-3, atol=1e-3)
+            Kw = got_K
+        total += nsubs
+    assert total > 0
+
+
+def test_unfused_batch_fitparents_matches_oracle():
+    """BASELINE config 1 shape (bars H=8 D=16 S=60 would exceed 2^8 unique init; use S=20): fitness
+    selection with the reference's batch-global normaliser runs through the unfused kernels."""
+    rng = np.random.default_rng(3)
+    N, H, D, S, P, Cn, G = 32, 8, 16, 20, 5, 3, 2
+    W = rng.standard_normal((D, H))
+    pies = np.full(H, 0.25)
+    Y = (rng.random((N, H)) < pies) @ W.T + 0.1 * rng.standard_normal((N, D))
+    K = rand_K(rng, N, S, H, p=0.3)
+    tvo_b200._set_device(to.device(DEV))
+    m = BSC(H, D, dev(W), to.tensor([0.01], dtype=to.float64), dev(pies), precision=to.float64)
+    st = EVOVariationalStates(N, H, S, to.float64, "batch_fitparents", "randflip", P, G, Cn, seed=5, K_init=dev(K))
+    nsubs = st.update(to.arange(N), dev(Y), m)
+    o = om.BSC(H, D, W, [0.01], pies)
+    Kw, Lw, nw = oracle_estep(o, Y, K, np.float64, "batch_fitparents", "randflip", P, Cn, G, None, np.arange(N), 5, 0)
+    assert np.array_equal(st.K.unpack().cpu().numpy(), Kw)
+    assert nsubs == nw
+    assert np.allclose(st.lpj.cpu().numpy(), Lw, rtol=RT64)
+
+
+def test_estep_baseline_shape_properties():
+    """BASELINE configs[1] shape (BSC D=144 H=256 S=64, randparents + sparseflip, fp64) at N=20000:
+    size-independent properties instead of an oracle run."""
+    to.manual_seed(0)
+    np.random.seed(0)
+    N, H, D, S = 20000, 256, 144, 64
+    tvo_b200._set_device(to.device(DEV))
+    g = to.Generator(device=DEV).manual_seed(1)
+    Wgen = to.randn(D, H, dtype=to.float64, device=DEV, generator=g)
+    s = (to.rand(N, H, device=DEV, generator=g) < 5.0 / H).double()
+    Y = s @ Wgen.t() + to.randn(N, D, dtype=to.float64, device=DEV, generator=g)
+    m = BSC(H, D, Wgen + 0.5 * to.randn(D, H, dtype=to.float64, device=DEV, generator=g), to.tensor([1.0]),
+            to.full((H,), 1.0 / H), precision=to.float64)
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", 16, 2, 2, bitflip_frequency=1.0 / H, seed=7)
+    idx = to.arange(N, device=DEV)
+    m._tvo_lpj_rows(st, idx, Y)
+    prev_best = st.lpj.max(dim=1).values.clone()
+    prev_sum = st.lpj.sum(dim=1).clone()
+    for it in range(3):
+        nsubs = st.update(idx, Y, m)
+        assert 0 < nsubs <= N * S
+        lpj = st.lpj
+        assert bool((lpj[:, 1:] >= lpj[:, :-1]).all())                       # ascending, best last
+        assert bool((lpj.max(dim=1).values >= prev_best - 1e-9).all())       # best never gets worse
+        assert bool((lpj.sum(dim=1) >= prev_sum - 1e-6).all())               # test/evo_test.py:290-327
+        prev_best, prev_sum = lpj.max(dim=1).values.clone(), lpj.sum(dim=1).clone()
+        re = m._tvo_lpj_packed(Y, st._Kp, H)                                 # stored lpj == lpj of stored K
+        assert to.allclose(re, lpj, rtol=1e-12, atol=1e-9)
+        # no duplicate states inside any K_n: sort rows by their words and compare neighbours
+        Kp = st._Kp
+        key = Kp[:, :, 0]
+        for w in range(1, Kp.shape[2]):
+            key = key * 1000003 + Kp[:, :, w]
+        ks = key.sort(dim=1).values
+        assert not bool((ks[:, 1:] == ks[:, :-1]).any())
+    # linearity of the accumulators: two half batches == one full batch
+    st.lpj.copy_(m._tvo_lpj_packed(Y, st._Kp, H))
+    m._stats.zero_()
+    m._fresh = None
+    m.update_param_batch(idx[: N // 2], Y[: N // 2], st)
+    m.update_param_batch(idx[N // 2:], Y[N // 2:], st)
+    a = m._stats.clone()
+    m._stats.zero_()
+    m.update_param_batch(idx, Y, st)
+    assert to.allclose(a, m._stats, rtol=1e-11, atol=1e-9)
+    assert int(m.my_N.item()) == N
+
+
+# ----------------------------------------------------------------------------- trainer / generic models
+def test_trainer_golden_bsc_fullem():
+    g = load_golden("trainer_bsc_fullem.npz")
+    tvo_b200._set_device(to.device(DEV))
+    Y = dev(g["Y"])
+    N, D = Y.shape
+    H = g["W0"].shape[1]
+    m = BSC(H, D, dev(g["W0"]), dev(g["sigma20"]), dev(g["pies0"]), precision=to.float64)
+    m.W_solver = "cpu"
+    st = FullEM(N, H, to.float64)
+    tr = Trainer(m, TVODataLoader(Y, batch_size=16), st)
+    prev = None
+    for ep in range(4):
+        res = tr.em_step()
+        assert res["train_subs"] == 0
+        if prev is not None:  # em_step reports F of (K_X, theta_{X-1}) == F_after of the previous epoch
+            assert math.isclose(res["train_F"] * N, prev, rel_tol=1e-9)
+        F = tr.eval_free_energies()["train_F"] * N
+        assert math.isclose(F, g["F_after"][ep], rel_tol=1e-9), ep
+        assert np.allclose(m.theta["W"].cpu().numpy(), g["W"][ep], rtol=1e-7, atol=1e-9)
+        assert np.allclose(m.theta["pies"].cpu().numpy(), g["pies"][ep], rtol=1e-9)
+        assert np.allclose(m.theta["sigma2"].cpu().numpy(), g["sigma2"][ep], rtol=1e-9)
+        prev = F
+
+
+def test_trainer_evo_bsc_free_energy_increases():
+    rng = np.random.default_rng(0)
+    np.random.seed(0)
+    N, H, D, S = 600, 10, 25, 12
+    Wgen = rng.standard_normal((D, H)) * 3
+    Y = (rng.random((N, H)) < 0.2) @ Wgen.T + 0.5 * rng.standard_normal((N, D))
+    tvo_b200._set_device(to.device(DEV))
+    m = BSC(H, D, dev(Wgen + rng.standard_normal((D, H))), to.tensor([1.0]), to.full((H,), 0.2), precision=to.float64)
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", 4, 2, 2, bitflip_frequency=1.0 / H, seed=1)
+    tr = Trainer(m, TVODataLoader(dev(Y), batch_size=128, shuffle=True), st)
+    Fs = [tr.em_step()["train_F"] for _ in range(6)]
+    assert all(np.isfinite(Fs)) and Fs[-1] > Fs[0] + 0.5
+    assert np.all(np.diff(Fs) > -1e-6)
+    e = tr.e_step()
+    assert e["train_F"] >= Fs[-1] - 1e-9 and e["train_subs"] >= 0
+
+
+class DummyModel(Trainable if cuda else object):
+    """test/evo_test.py:26-42: log-joint = integer value of the bit string (fp64)."""
+
+    def update_param_batch(self):
+        pass
+
+    def log_joint(self, data, states, lpj=None):
+        N, S, H = states.shape
+        ids = (2.0 ** to.arange(H, device=states.device, dtype=to.float64))
+        return (states.to(to.float64) * ids).sum(dim=2)
+
+
+class CountModel(Trainable if cuda else object):
+    """test/RandomSampledVarStates_test.py:12-17"""
+
+    def log_joint(self, data, states):
+        return states.sum(dim=2, dtype=to.float32)
+
+    def update_param_batch(self):
+        pass
+
+
+def test_reference_evo_update_with_dummy_model():
+    # test/evo_test.py:290-327
+    tvo_b200._set_device(to.device(DEV))
+    np.random.seed(1)
+    for x in range(10):
+        st = EVOVariationalStates(N=2, H=4, S=3, precision=to.float64, parent_selection="batch_fitparents",
+                                  mutation="randflip", n_parents=2, n_generations=1, n_children=1, seed=x)
+        idx = to.arange(2, device=DEV)
+        st.lpj[:] = DummyModel().log_joint(None, st.K[idx])
+        old = st.lpj.sum(dim=1)
+        nsubs = st.update(idx, to.empty((1,), device=DEV), DummyModel())
+        new = st.lpj.sum(dim=1)
+        assert nsubs >= 0
+        assert int(((new - old) < -1e-10).sum()) == 0
+        if int((new == old).sum()) > 0:
+            assert nsubs < 2 * 3
+        assert to.equal(st.lpj, DummyModel().log_joint(None, st.K[idx]))
+
+
+def test_reference_random_sampled_and_fullem_with_count_model():
+    # test/RandomSampledVarStates_test.py:21-45, test/fullem_test.py:30-43
+    tvo_b200._set_device(to.device(DEV))
+    N, H, S, S_new = 10, 8, 4, 10
+    st = RandomSampledVarStates(N, H, S, to.float32, S_new, seed=3)
+    data = to.rand(N, 1, device=DEV)
+    idx = to.arange(N, device=DEV)
+    before = st.K.sum()
+    st.update(idx, data, CountModel())
+    assert st.K.sum() >= before
+    st.K = to.ones(10, 1, 50, dtype=to.uint8, device=DEV)
+    st.lpj = CountModel().log_joint(None, st.K.unpack())
+    assert st.update(idx, data, CountModel()) == 0
+    assert bool((st.K == 1).all())
+    fe = FullEM(N, H, to.float32)
+    assert tuple(fe.K.shape) == (N, 2 ** H, H)
+    assert to.unique(fe.K[0], dim=0).shape[0] == 2 ** H
+    lpj = CountModel().log_joint(None, fe.K.unpack())
+    assert fe.update(idx, data, CountModel()) == 0
+    assert bool((fe.lpj == lpj).all())
+
+
+def test_errors_are_loud():
+    tvo_b200._set_device(to.device(DEV))
+    with pytest.raises(ValueError):
+        EVOVariationalStates(4, 8, 3, to.float64, "nonsense", "randflip", 2, 1, 1)
+    with pytest.raises(ValueError):
+        EVOVariationalStates(4, 8, 3, to.float64, "randparents", "nonsense", 2, 1, 1)
+    st = EVOVariationalStates(4, 8, 3, to.float64, "randparents", "randflip", n_parents=5, n_generations=1, n_children=1)
+    m = BSC(8, 5, precision=to.float64)
+    with pytest.raises(ValueError, match="n_parents"):
+        st.update(to.arange(4), to.zeros(4, 5, dtype=to.float64, device=DEV), m)
+    with pytest.raises(_lib.TvoError):
+        _lib.ptr(to.zeros(3))
+    with pytest.raises(ValueError):
+        _lib.call("tvo_pack_states", None, None, 3, 5, None)
+
+
+def test_lpj2pjc_mean_posterior_golden():
+    g = load_golden("dedup_merge.npz")
+    assert np.allclose(vu.lpj2pjc(dev(g["all_lpj"])).cpu().numpy(), g["pjc"], rtol=1e-12)
+    assert np.allclose(vu.mean_posterior(dev(g["g"]), dev(g["all_lpj"])).cpu().numpy(), g["mean_post"], rtol=1e-11)
+    assert np.allclose(vu.lpj2pjc(dev(g["all_lpj"], to.float32)).cpu().numpy(), g["pjc"], rtol=1e-4)

@@ -1,0 +1,7 @@
+from .TVOVariationalStates import TVOVariationalStates
+from .fullem import FullEM
+from .RandomSampledVarStates import RandomSampledVarStates
+from .evo import EVOVariationalStates
+from ._packed import PackedStates
+
+__all__ = ["TVOVariationalStates", "FullEM", "RandomSampledVarStates", "EVOVariationalStates", "PackedStates"]
