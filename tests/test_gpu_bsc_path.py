@@ -434,13 +434,10 @@ def test_estep_baseline_shape_properties():
         prev_best, prev_sum = lpj.max(dim=1).values.clone(), lpj.sum(dim=1).clone()
         re = m._tvo_lpj_packed(Y, st._Kp, H)                                 # stored lpj == lpj of stored K
         assert to.allclose(re, lpj, rtol=1e-12, atol=1e-9)
-        # no duplicate states inside any K_n: sort rows by their words and compare neighbours
+        # no duplicate states inside any K_n: (datapoint id, words) rows must all be distinct
         Kp = st._Kp
-        key = Kp[:, :, 0]
-        for w in range(1, Kp.shape[2]):
-            key = key * 1000003 + Kp[:, :, w]
-        ks = key.sort(dim=1).values
-        assert not bool((ks[:, 1:] == ks[:, :-1]).any())
+        rows = to.cat([idx[:, None, None].expand(-1, S, 1), Kp], dim=2).reshape(N * S, -1)
+        assert to.unique(rows, dim=0).shape[0] == N * S
     # linearity of the accumulators: two half batches == one full batch
     st.lpj.copy_(m._tvo_lpj_packed(Y, st._Kp, H))
     m._stats.zero_()
