@@ -153,15 +153,21 @@ int tvo_select_topS_f32(const uint64_t *new_states, const float *new_lpj, uint64
 
 /* ---- fused E-step for BSC: replaces EVOVariationalStates.update (evo.py:80-115) end to end:
  *      re-score K under theta, G generations of select+mutate+score with the children kept in
- *      shared memory, dedup against the original K, top-S merge, nsubs.  fit_norm is scratch
- *      (2 doubles) used only by TVO_SEL_FITPARENTS. ---- */
+ *      shared memory, dedup against the original K, top-S merge, nsubs.
+ *      `scratch` (device, scratch_bytes; see tvo_bsc_estep_scratch_bytes) enables the Gram form
+ *      ||y||^2 - 2 (W^T y).s + s^T (W^T W) s: the batch is processed in chunks of as many datapoints
+ *      as fit (one cuBLAS GEMM a = Y W plus one kernel per chunk).  scratch == NULL selects the direct
+ *      column-walk form (D <= 256).  Datapoints with NaN in y always take the direct form.
+ *      TVO_SEL_FITPARENTS (batch-global normaliser) is not available fused: use the stand-alone
+ *      kernels. ---- */
+int64_t tvo_bsc_estep_scratch_bytes(int64_t B, int32_t H, int32_t is_f64);
 int tvo_estep_evo_bsc_f64(const double *Y, int64_t ldY, const int64_t *idx, uint64_t *K, double *lpj,
-                          const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity,
-                          double *fit_norm, int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs,
+                          const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity, void *scratch,
+                          int64_t scratch_bytes, int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs,
                           void *stream);
 int tvo_estep_evo_bsc_f32(const float *Y, int64_t ldY, const int64_t *idx, uint64_t *K, float *lpj,
-                          const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity,
-                          double *fit_norm, int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs,
+                          const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity, void *scratch,
+                          int64_t scratch_bytes, int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs,
                           void *stream);
 
 /* ---- posterior weights: lpj2pjc / mean_posterior (_utils.py:182-230) ---- */
@@ -185,19 +191,24 @@ int tvo_bsc_free_energy_f32(const float *Y, int64_t ldY, const float *lpj, int64
                             double *F_out, void *stream);
 
 /* ---- BSC M-step accumulation: replaces BSC.update_param_batch (bsc.py:134-158).  `stats` is one
- *      packed fp64 buffer [WpT (H*D, i.e. my_Wp transposed) | Wq (H*H) | pies (H) | sigma2 (1) |
- *      N (1) | F (1)] that is INCREMENTED; q(s) = softmax(lpj) lives on chip only.  F gets the
- *      batch free energy (same value as tvo_bsc_free_energy).  exact_residual = 1 recomputes
- *      ||y - W s||^2 from Y and theta as the reference does (bsc.py:140-150); 0 derives it from
- *      lpj, valid when lpj was produced from the same Y and theta (the Trainer's E-step/M-step
- *      order, Trainer.py:239-249). ---- */
+ *      packed fp64 buffer [WpT (H*D, my_Wp transposed) | WqU (H*H, UPPER triangle incl. diagonal of
+ *      the symmetric my_Wq; the strict lower triangle stays 0) | pies (H) | sigma2 (1) | N (1) | F (1)]
+ *      that is INCREMENTED; q(s) = softmax(lpj) lives on chip only.  F gets the batch free energy
+ *      (same value as tvo_bsc_free_energy).  `scratch` (see tvo_bsc_mstep_scratch_bytes) holds
+ *      E = <s>_q for one chunk of datapoints so that WpT += E^T Y is one cuBLAS GEMM per chunk.
+ *      exact_residual = 1 recomputes ||y - W s||^2 from Y and theta as the reference does
+ *      (bsc.py:140-150); 0 derives it from lpj, valid when lpj was produced from the same Y and theta
+ *      (the Trainer's E-step/M-step order, Trainer.py:239-249). ---- */
 int64_t tvo_bsc_stats_len(int32_t H, int32_t D);
+int64_t tvo_bsc_mstep_scratch_bytes(int64_t B, int32_t H, int32_t D, int32_t is_f64);
 int tvo_bsc_mstep_f64(const double *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
-                      const double *lpj, int64_t lpj_stride_n, const void *theta_ws, double *stats, int64_t B,
-                      int32_t S, int32_t H, int32_t D, int32_t exact_residual, void *stream);
+                      const double *lpj, int64_t lpj_stride_n, const void *theta_ws, double *stats, void *scratch,
+                      int64_t scratch_bytes, int64_t B, int32_t S, int32_t H, int32_t D, int32_t exact_residual,
+                      void *stream);
 int tvo_bsc_mstep_f32(const float *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
-                      const float *lpj, int64_t lpj_stride_n, const void *theta_ws, double *stats, int64_t B,
-                      int32_t S, int32_t H, int32_t D, int32_t exact_residual, void *stream);
+                      const float *lpj, int64_t lpj_stride_n, const void *theta_ws, double *stats, void *scratch,
+                      int64_t scratch_bytes, int64_t B, int32_t S, int32_t H, int32_t D, int32_t exact_residual,
+                      void *stream);
 
 #ifdef __cplusplus
 }

@@ -47,7 +47,7 @@ def main():
     m.W_solver = "cpu"
     st = m._stats
     st[: H * D] = to.tensor(osh.my_Wp.T.reshape(-1))
-    st[H * D: H * D + H * H] = to.tensor(osh.my_Wq.reshape(-1))
+    st[H * D: H * D + H * H] = to.tensor(np.triu(osh.my_Wq).reshape(-1))  # kernel convention: upper triangle
     st[H * D + H * H: H * D + H * H + H] = to.tensor(osh.my_pies)
     st[-3] = float(osh.my_sigma2[0])
     st[-2] = hi - lo

@@ -332,6 +332,7 @@ def oracle_estep(o, Y, K, lpj_dtype, sel, mut, P, Cn, G, p_bf, n_glob, seed, ste
     return Kc, lc, nsubs
 
 
+@pytest.mark.parametrize("gram", [True, False], ids=["gram", "direct"])
 @pytest.mark.parametrize("dtype", [to.float64, to.float32])
 @pytest.mark.parametrize("H,D,S,sel,mut,P,Cn,G", [
     (8, 16, 10, "randparents", "randflip", 3, 2, 2),
@@ -342,7 +343,7 @@ def oracle_estep(o, Y, K, lpj_dtype, sel, mut, P, Cn, G, p_bf, n_glob, seed, ste
     (130, 50, 7, "fitparents_fixed", "cross", 3, None, 1),
     (256, 144, 64, "randparents", "sparseflip", 16, 2, 2),
 ])
-def test_fused_estep_bit_exact(dtype, H, D, S, sel, mut, P, Cn, G):
+def test_fused_estep_bit_exact(gram, dtype, H, D, S, sel, mut, P, Cn, G):
     rng = np.random.default_rng(H + D + S)
     N = 24
     npd = np.float64 if dtype == to.float64 else np.float32
@@ -353,6 +354,7 @@ def test_fused_estep_bit_exact(dtype, H, D, S, sel, mut, P, Cn, G):
     K = rand_K(rng, N, S, H, p=min(0.3, 4.0 / H))
     tvo_b200._set_device(to.device(DEV))
     m = BSC(H, D, dev(W), dev(sigma2), dev(pies), precision=dtype)
+    m.use_gram = gram
     crossover = mut.startswith("cross")
     kw = dict(bitflip_frequency=2.0 / H, seed=99, K_init=dev(K))
     if mut == "cross":
@@ -384,6 +386,36 @@ def test_fused_estep_bit_exact(dtype, H, D, S, sel, mut, P, Cn, G):
             Kw = got_K
         total += nsubs
     assert total > 0
+
+
+def test_fused_estep_gram_nan_rows_and_chunking():
+    """Datapoints with NaN in y take the direct (nansum) form inside the Gram kernel; a scratch smaller
+    than the batch splits it into chunks without changing the result."""
+    rng = np.random.default_rng(11)
+    N, H, D, S, P, Cn, G = 3000, 70, 40, 8, 3, 2, 2
+    W = rng.standard_normal((D, H))
+    pies = np.full(H, 0.05)
+    Y = (rng.random((N, H)) < pies) @ W.T + rng.standard_normal((N, D))
+    Y[5, 3] = np.nan
+    Y[17, :7] = np.nan
+    Y[2999, 39] = np.nan
+    K = rand_K(rng, N, S, H, p=0.05)
+    tvo_b200._set_device(to.device(DEV))
+    outs = []
+    for chunk in (1 << 20, 1100):
+        m = BSC(H, D, dev(W), to.tensor([1.0], dtype=to.float64), dev(pies), precision=to.float64)
+        m.scratch_datapoints = chunk
+        st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", P, G, Cn, bitflip_frequency=1.0 / H,
+                                  seed=3, K_init=dev(K))
+        nsubs = st.update(to.arange(N, device=DEV), dev(Y), m)
+        outs.append((st.K.unpack().cpu().numpy(), st.lpj.cpu().numpy(), nsubs, float(m._tvo_sparsity().item())))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+    o = om.BSC(H, D, W, [1.0], pies)
+    sub = np.r_[0:40, 2990:3000]
+    Kw, Lw, _ = oracle_estep(o, Y[sub], K[sub], np.float64, "randparents", "sparseflip", P, Cn, G, 1.0 / H, sub, 3, 0,
+                             sparsity=outs[0][3])
+    assert np.array_equal(outs[0][0][sub], Kw)
+    assert np.allclose(outs[0][1][sub], Lw, rtol=RT64, atol=RT64)
 
 
 def test_unfused_batch_fitparents_matches_oracle():

@@ -48,6 +48,8 @@ _PROTOS = {
     "tvo_state_matrix": [_P, _I32, _P],
     "tvo_bsc_theta_ws_bytes": [_I32, _I32, _I32],
     "tvo_bsc_stats_len": [_I32, _I32],
+    "tvo_bsc_estep_scratch_bytes": [_I64, _I32, _I32],
+    "tvo_bsc_mstep_scratch_bytes": [_I64, _I32, _I32, _I32],
     "tvo_random_states": [_P, _P, _I64, _I32, _I32, _F64, _U64, _U32, _U32, _P],
 }
 for _sfx in ("f64", "f32"):
@@ -59,12 +61,12 @@ for _sfx in ("f64", "f32"):
         f"tvo_fit_norm_{_sfx}": [_P, _I64, _P, _I64, _I32, _P, _P],
         f"tvo_mark_redundant_{_sfx}": [_P, _P, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
         f"tvo_select_topS_{_sfx}": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P],
-        f"tvo_estep_evo_bsc_{_sfx}": [_P, _I64, _P, _P, _P, _P, C.POINTER(EvoConfig), _P, _P, _I64, _I32, _I32, _I32,
-                                      _P, _P],
+        f"tvo_estep_evo_bsc_{_sfx}": [_P, _I64, _P, _P, _P, _P, C.POINTER(EvoConfig), _P, _P, _I64, _I64, _I32, _I32,
+                                      _I32, _P, _P],
         f"tvo_lpj2pjc_{_sfx}": [_P, _P, _I64, _I32, _P],
         f"tvo_mean_posterior_{_sfx}": [_P, _P, _P, _I64, _I32, _I64, _P],
         f"tvo_bsc_free_energy_{_sfx}": [_P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _P, _P],
-        f"tvo_bsc_mstep_{_sfx}": [_P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _P],
+        f"tvo_bsc_mstep_{_sfx}": [_P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P],
     })
 _RESTYPES = {
     "tvo_last_error": C.c_char_p,
@@ -72,6 +74,8 @@ _RESTYPES = {
     "tvo_reset_launch_count": None,
     "tvo_bsc_theta_ws_bytes": _I64,
     "tvo_bsc_stats_len": _I64,
+    "tvo_bsc_estep_scratch_bytes": _I64,
+    "tvo_bsc_mstep_scratch_bytes": _I64,
 }
 
 _lib = None

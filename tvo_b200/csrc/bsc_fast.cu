@@ -1,0 +1,454 @@
+// tvo_b200 — BSC fast path: Gram-form fused EVO E-step and the M-step accumulation.
+//
+// E-step.  ||y - W s||^2 = ||y||^2 - 2 a.s + s^T G s  with  a = W^T y  (one DGEMM per chunk of
+// datapoints, cuBLAS: a plain library GEMM) and G = W^T W (theta workspace).  For a sparse bit-packed
+// state this is |s| reads of `a` from shared memory and |s|(|s|+1)/2 gathers from G — one LANE per
+// state — instead of |s|*D column adds by a whole warp (bsc.cu, ~48% of that kernel's instructions).
+// Datapoints whose y contains NaN take the direct form (nansum semantics, bsc.py:115).
+//
+// M-step (bsc.py:134-158).  One warp per datapoint: softmax weights on chip, E = <s>_q scattered into
+// shared memory, Wq via one RED per (state, bit pair), sigma2 from lpj (or recomputed).  E is written
+// per chunk so that  WpT += E^T Y  is one DGEMM (the union of active bits per datapoint is ~100 of 256,
+// so the outer product is effectively dense).
+#include <cublas_v2.h>
+
+#include "bsc_device.cuh"
+
+namespace tvo {
+
+constexpr int kMaxSmemFast = 227 * 1024;
+
+int evo_params_from_cfg(const tvo_evo_config *cfg, int S, int H, EvoParams &ep, EstepDims &dims, const char *who);
+template <typename T>
+int estep_evo_bsc_direct(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj, const void *ws,
+                         const tvo_evo_config *cfg, const double *sparsity, int64_t B, int S, int H, int D,
+                         int64_t *nsubs, void *stream);
+
+// ------------------------------------------------------------------------------------ cuBLAS
+static cublasHandle_t g_handles[64];
+static int cublas_for_stream(cudaStream_t st, cublasHandle_t &h) {
+  int dev = 0;
+  TVO_CUDA(cudaGetDevice(&dev));
+  TVO_REQUIRE(dev >= 0 && dev < 64, "cublas: device index %d out of range", dev);
+  if (!g_handles[dev]) {
+    cublasStatus_t s = cublasCreate(&g_handles[dev]);
+    if (s != CUBLAS_STATUS_SUCCESS) return set_error(TVO_ECUDA, "cublasCreate failed (%d)", (int)s);
+  }
+  h = g_handles[dev];
+  cublasStatus_t s = cublasSetStream(h, st);
+  if (s != CUBLAS_STATUS_SUCCESS) return set_error(TVO_ECUDA, "cublasSetStream failed (%d)", (int)s);
+  return TVO_OK;
+}
+#define TVO_CUBLAS(expr)                                                                     \
+  do {                                                                                       \
+    cublasStatus_t s_ = (expr);                                                              \
+    if (s_ != CUBLAS_STATUS_SUCCESS) return set_error(TVO_ECUDA, "%s failed (%d)", #expr, (int)s_); \
+    count_launch();                                                                          \
+  } while (0)
+
+// A (Bc x H, row-major) = Y (Bc x D, ld ldY) * W (D x H), W read from the padded W^T in the workspace
+static int gemm_A(cublasHandle_t h, const double *Wt, int Dpad, const double *Y, int64_t ldY, double *A, int Bc, int H, int D) {
+  const double one = 1.0, zero = 0.0;
+  TVO_CUBLAS(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, H, Bc, D, &one, Wt, Dpad, Y, (int)ldY, &zero, A, H));
+  return TVO_OK;
+}
+static int gemm_A(cublasHandle_t h, const float *Wt, int Dpad, const float *Y, int64_t ldY, float *A, int Bc, int H, int D) {
+  const float one = 1.f, zero = 0.f;
+  TVO_CUBLAS(cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, H, Bc, D, &one, Wt, Dpad, Y, (int)ldY, &zero, A, H));
+  return TVO_OK;
+}
+
+// ------------------------------------------------------------------------------------ Gram lpj
+// lpj of ONE state, evaluated by ONE lane.  a: shared memory (H), G: global (H x H), prior: global.
+template <typename T>
+__device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, const T *a, const double *__restrict__ G,
+                                          const T *__restrict__ prior, double yy, double coef) {
+  double f = 0.0, pr = 0.0;
+  for (int w1 = 0; w1 < W64; ++w1) {
+    uint64_t m1 = st[w1];
+    while (m1) {
+      const int h1 = (w1 << 6) + __ffsll((long long)m1) - 1;
+      m1 &= m1 - 1;
+      const double *Grow = G + (size_t)h1 * H;
+      f += __ldg(Grow + h1) - 2.0 * (double)a[h1];
+      pr += (double)__ldg(prior + h1);
+      double g2 = 0.0;
+      uint64_t m2 = m1;
+      int w2 = w1;
+      while (true) {
+        while (m2) {
+          const int h2 = (w2 << 6) + __ffsll((long long)m2) - 1;
+          m2 &= m2 - 1;
+          g2 += __ldg(Grow + h2);
+        }
+        if (++w2 >= W64) break;
+        m2 = st[w2];
+      }
+      f += 2.0 * g2;
+    }
+  }
+  return (T)((yy + f) * coef + pr);
+}
+
+// direct form for one state, any D, warp-cooperative, y from global memory (NaN rows only)
+template <typename T>
+__device__ inline T bsc_direct_lpj_slow(const uint64_t *st, int W64, const BscTheta<T> &th, const T *__restrict__ y,
+                                        int D, int lane, T coef) {
+  T ss = T(0), pr = T(0);
+  for (int c = 0; c < th.Dpad; c += 32) {
+    T acc = T(0);
+    for (int w = 0; w < W64; ++w) {
+      uint64_t word = st[w];
+      while (word) {
+        const int h = (w << 6) + __ffsll((long long)word) - 1;
+        word &= word - 1;
+        acc += __ldg(th.Wt + (size_t)h * th.Dpad + c + lane);
+        if (c == 0) pr += __ldg(th.prior + h);
+      }
+    }
+    const int d = c + lane;
+    const T yv = d < D ? y[d] : T(0);
+    const T t = acc - yv;
+    if (yv == yv) ss += t * t;
+  }
+  return warp_sum(ss) * coef + pr;
+}
+
+template <typename T>
+__device__ __forceinline__ void score_states(const uint64_t *states, int count, int W64, int H, int D, const BscTheta<T> &th,
+                                             const T *a_sm, const T *__restrict__ y, double yy, bool has_nan, T *out,
+                                             int lane) {
+  if (!has_nan) {
+    for (int s = lane; s < count; s += 32)
+      out[s] = bsc_gram_lpj<T>(states + (size_t)s * W64, W64, H, a_sm, th.G, th.prior, yy, th.hdr->coef);
+  } else {
+    for (int s = 0; s < count; ++s) {
+      const T v = bsc_direct_lpj_slow<T>(states + (size_t)s * W64, W64, th, y, D, lane, (T)th.hdr->coef);
+      if (lane == 0) out[s] = v;
+    }
+  }
+  __syncwarp();
+}
+
+// EVOVariationalStates.update (evo.py:80-115) for BSC, Gram form.  Same structure and same random
+// stream as estep_evo_bsc_kernel (bsc.cu); `A` holds a = W^T y for the B datapoints of this launch.
+template <typename T>
+__global__ void __launch_bounds__(256)
+estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
+                          int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
+                          const double *__restrict__ sparsity_p, EstepDims dims, int64_t B, int H, int D,
+                          unsigned long long *nsubs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
+  const size_t wbytes = warp_buf_bytes<T>(dims) + align16((size_t)H * sizeof(T));
+  unsigned char *base = smem_raw + (size_t)wib * wbytes;
+  const WarpBuf<T> wb = carve_warp_buf<T>(base, dims);
+  T *a_sm = (T *)(base + warp_buf_bytes<T>(dims));
+  const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64;
+  const double sparsity = sparsity_p ? *sparsity_p : 0.0;
+  unsigned long long my_subs = 0;
+
+  for (int64_t b = (int64_t)blockIdx.x * wpb + wib; b < B; b += (int64_t)gridDim.x * wpb) {
+    const int64_t row = idx ? idx[b] : row0 + b;
+    const uint32_t n_glob = ep.n_offset + (uint32_t)row;
+    uint64_t *Krow = K + row * (int64_t)S * W64;
+    T *lrow = lpj + row * (int64_t)S;
+    const T *y = Y + b * ldY;
+    __syncwarp();
+    double yy = 0.0;
+    bool has_nan = false;
+    for (int d = lane; d < D; d += 32) {
+      const double v = (double)y[d];
+      has_nan |= (v != v);
+      yy += v * v;
+    }
+    yy = warp_sum(yy);
+    has_nan = __any_sync(FULL, has_nan);
+    for (int h = lane; h < H; h += 32) a_sm[h] = A[b * (int64_t)H + h];
+    for (int t = lane; t < S * W64; t += 32) wb.oldK[t] = Krow[t];
+    __syncwarp();
+    score_states<T>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, lane);  // evo.py:95
+    for (int g = 0; g < ep.G; ++g) {
+      const uint64_t *cand = g == 0 ? wb.oldK : wb.newK + (size_t)(g - 1) * Sgen * W64;
+      const T *cand_lpj = g == 0 ? wb.lpj : wb.lpj + S + (g - 1) * Sgen;
+      uint64_t *children = wb.newK + (size_t)g * Sgen * W64;
+      evo_generation<T>(wb, cand, cand_lpj, g == 0 ? S : Sgen, children, ep, g, n_glob, W64, H, sparsity, 0.0, 1.0,
+                        lane);
+      score_states<T>(children, Sgen, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj + S + g * Sgen, lane);
+    }
+    mark_redundant<T>(wb, S, Snew, W64, lane);
+    my_subs += (unsigned long long)select_topS<T>(wb, S, Snew, W64, Krow, lrow, lane);
+  }
+  if (lane == 0 && my_subs) atomicAdd(nsubs, my_subs);
+}
+
+// ------------------------------------------------------------------------------------ M-step
+// stats layout: [WpT (H*D) | WqU (H*H, UPPER triangle incl. diagonal of my_Wq) | pies (H) | sigma2 | N | F]
+template <typename T>
+__global__ void __launch_bounds__(256)
+bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx, int64_t row0,
+                 const uint64_t *__restrict__ K, int64_t k_stride_n, const T *__restrict__ lpj, int64_t lpj_stride_n,
+                 const void *ws, double *__restrict__ stats, double *__restrict__ E_out, double *__restrict__ Yd_out,
+                 int64_t B, int S, int H, int D, int exact_resid, size_t warp_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
+  const int W64 = n_words(H);
+  unsigned char *p = smem_raw + (size_t)wib * warp_bytes;
+  uint64_t *Ksm = (uint64_t *)p;
+  p += align16((size_t)S * W64 * 8);
+  double *q = (double *)p;
+  p += align16((size_t)S * 8);
+  double *Esm = (double *)p;
+  p += align16((size_t)H * 8);
+  double *pies_w = (double *)p;  // per-warp running sum of E over this warp's datapoints
+
+  double *WqU = stats + (size_t)H * D, *pies = WqU + (size_t)H * H;
+  double *sig = pies + H, *Ncnt = sig + 1, *Facc = Ncnt + 1;
+  const double coef = th.hdr->coef;
+  double acc_sig = 0.0, acc_F = 0.0, acc_N = 0.0;
+  for (int h = lane; h < H; h += 32) pies_w[h] = 0.0;
+
+  for (int64_t b = (int64_t)blockIdx.x * wpb + wib; b < B; b += (int64_t)gridDim.x * wpb) {
+    const int64_t row = idx ? idx[b] : row0 + b;
+    const uint64_t *Kn = K + row * k_stride_n;
+    const T *l = lpj + row * lpj_stride_n;
+    const T *y = Y + b * ldY;
+    __syncwarp();
+    for (int t = lane; t < S * W64; t += 32) Ksm[t] = Kn[t];
+    for (int h = lane; h < H; h += 32) Esm[h] = 0.0;
+    // softmax weights (lpj2pjc, _utils.py:182-191)
+    double mx = -INFINITY;
+    for (int s = lane; s < S; s += 32) mx = fmax(mx, (double)l[s]);
+    mx = warp_max(mx);
+    double se = 0.0;
+    for (int s = lane; s < S; s += 32) {
+      const double e = exp((double)l[s] - mx);
+      q[s] = e;
+      se += e;
+    }
+    se = warp_sum(se);
+    int dn = 0;
+    for (int d = lane; d < D; d += 32) {
+      const T v = y[d];
+      dn += (v == v) ? 1 : 0;
+      if (Yd_out) Yd_out[b * (int64_t)D + d] = (double)v;
+    }
+    dn = warp_sum(dn);
+    acc_F += mx + log(se) + th.hdr->prior_sum - 0.5 * (double)dn * th.hdr->log_2pi_sigma2;
+    acc_N += 1.0;
+    __syncwarp();
+    // one lane per state: E_h += q_s, WqU[h,h'] += q_s (h <= h'), sigma2 term from lpj
+    double part = 0.0;
+    for (int s = lane; s < S; s += 32) {
+      const double qs = q[s] / se;
+      q[s] = qs;
+      const uint64_t *st = Ksm + (size_t)s * W64;
+      double pr = 0.0;
+      for (int w1 = 0; w1 < W64; ++w1) {
+        uint64_t m1 = st[w1];
+        while (m1) {
+          const int h1 = (w1 << 6) + __ffsll((long long)m1) - 1;
+          pr += (double)__ldg(th.prior + h1);
+          atomicAdd(Esm + h1, qs);
+          double *Wrow = WqU + (size_t)h1 * H;
+          uint64_t m2 = m1;  // includes h1 itself: the diagonal
+          int w2 = w1;
+          while (true) {
+            while (m2) {
+              const int h2 = (w2 << 6) + __ffsll((long long)m2) - 1;
+              m2 &= m2 - 1;
+              atomicAdd(Wrow + h2, qs);
+            }
+            if (++w2 >= W64) break;
+            m2 = st[w2];
+          }
+          m1 &= m1 - 1;
+        }
+      }
+      if (!exact_resid) part += qs * (((double)l[s] - pr) / coef);
+    }
+    if (!exact_resid) acc_sig += warp_sum(part);
+    __syncwarp();
+    for (int h = lane; h < H; h += 32) {
+      const double e = Esm[h];
+      E_out[b * (int64_t)H + h] = e;
+      pies_w[h] += e;
+    }
+    if (exact_resid) {  // <||y - W s||^2>_q recomputed from Y and theta, plain sum (bsc.py:148-150)
+      double part2 = 0.0;
+      for (int s = 0; s < S; ++s) {
+        T ss = T(0);
+        for (int c = 0; c < th.Dpad; c += 32) {
+          T a = T(0);
+          for (int w = 0; w < W64; ++w) {
+            uint64_t word = Ksm[(size_t)s * W64 + w];
+            while (word) {
+              const int h = (w << 6) + __ffsll((long long)word) - 1;
+              word &= word - 1;
+              a += __ldg(th.Wt + (size_t)h * th.Dpad + c + lane);
+            }
+          }
+          const int d = c + lane;
+          const T t = (d < D ? y[d] : T(0)) - a;
+          ss += t * t;
+        }
+        part2 += q[s] * (double)warp_sum(ss);
+      }
+      acc_sig += part2;
+    }
+  }
+  __syncwarp();
+  for (int h = lane; h < H; h += 32) {
+    const double v = pies_w[h];
+    if (v != 0.0) atomicAdd(pies + h, v);
+  }
+  if (lane == 0 && acc_N != 0.0) {
+    atomicAdd(sig, acc_sig);
+    atomicAdd(Ncnt, acc_N);
+    atomicAdd(Facc, acc_F);
+  }
+}
+
+template <typename T>
+static size_t bsc_mstep_warp_bytes(int S, int H) {
+  return align16((size_t)S * n_words(H) * 8) + align16((size_t)S * 8) + 2 * align16((size_t)H * 8);
+}
+
+// ------------------------------------------------------------------------------------ host side
+template <typename T>
+static int64_t estep_scratch_per_dp(int H) {
+  return (int64_t)H * sizeof(T);
+}
+template <typename T>
+static int64_t mstep_scratch_per_dp(int H, int D) {
+  return (int64_t)H * 8 + (sizeof(T) == 8 ? 0 : (int64_t)D * 8);
+}
+
+template <typename T>
+int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj, const void *ws,
+                  const tvo_evo_config *cfg, const double *sparsity, void *scratch, int64_t scratch_bytes, int64_t B,
+                  int S, int H, int D, int64_t *nsubs, void *stream) {
+  TVO_REQUIRE(Y && K && lpj && ws && cfg && nsubs, "estep_evo_bsc: null pointer");
+  const int64_t per = estep_scratch_per_dp<T>(H);
+  int64_t cap = scratch ? scratch_bytes / per : 0;
+  if (cap < 1024 && cap < B)  // no (useful) scratch: direct column-walk form
+    return estep_evo_bsc_direct<T>(Y, ldY, idx, K, lpj, ws, cfg, sparsity, B, S, H, D, nsubs, stream);
+  EvoParams ep;
+  EstepDims dims;
+  int rc = evo_params_from_cfg(cfg, S, H, ep, dims, "estep_evo_bsc");
+  if (rc) return rc;
+  TVO_REQUIRE(ep.sel != TVO_SEL_FITPARENTS,
+              "estep_evo_bsc: batch-global fitparents needs a grid-wide reduction per generation; use the unfused "
+              "kernels (or TVO_SEL_FITPARENTS_FIXED)");
+  TVO_REQUIRE(!(ep.mut == TVO_MUT_SPARSEFLIP || ep.mut == TVO_MUT_CROSS_SPARSEFLIP) || sparsity,
+              "estep_evo_bsc: sparseflip needs the device scalar `sparsity`");
+  TVO_REQUIRE(B >= 0 && D > 0 && ldY >= D && ldY < (1ll << 31), "estep_evo_bsc: bad sizes");
+  if (B == 0) return TVO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cublasHandle_t hb;
+  rc = cublas_for_stream(st, hb);
+  if (rc) return rc;
+  const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
+  const size_t wbytes = warp_buf_bytes<T>(dims) + align16((size_t)H * sizeof(T));
+  int wpb = 8;
+  while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmemFast) wpb >>= 1;
+  TVO_REQUIRE(wbytes * wpb <= (size_t)kMaxSmemFast, "estep_evo_bsc: per-datapoint working set %zu B exceeds shared memory",
+              wbytes);
+  const size_t smem = wbytes * wpb;
+  auto kern = estep_evo_bsc_gram_kernel<T>;
+  TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+  occ = max(occ, 1);
+  T *A = (T *)scratch;
+  for (int64_t c0 = 0; c0 < B; c0 += cap) {
+    const int Bc = (int)min(cap, B - c0);
+    rc = gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, A, Bc, H, D);
+    if (rc) return rc;
+    const int grid = (int)max((int64_t)1, min((int64_t)(Bc + wpb - 1) / wpb, (int64_t)sm_count() * occ));
+    kern<<<grid, wpb * 32, smem, st>>>(Y + c0 * ldY, ldY, A, idx ? idx + c0 : nullptr, c0, K, lpj, ws, ep, sparsity, dims,
+                                       Bc, H, D, (unsigned long long *)nsubs);
+    TVO_AFTER_LAUNCH("estep_evo_bsc_gram");
+  }
+  return TVO_OK;
+}
+
+template <typename T>
+int bsc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n, const T *lpj,
+              int64_t lpj_stride_n, const void *ws, double *stats, void *scratch, int64_t scratch_bytes, int64_t B, int S,
+              int H, int D, int exact, void *stream) {
+  TVO_REQUIRE(Y && K && lpj && ws && stats && scratch, "bsc_mstep: null pointer");
+  TVO_REQUIRE(B >= 0 && S > 0 && H > 0 && D > 0 && ldY >= D && ldY < (1ll << 31), "bsc_mstep: bad sizes");
+  const int64_t per = mstep_scratch_per_dp<T>(H, D);
+  const int64_t cap = scratch_bytes / per;
+  TVO_REQUIRE(cap >= 1, "bsc_mstep: scratch of %lld B holds no datapoint (need %lld B each)", (long long)scratch_bytes,
+              (long long)per);
+  if (B == 0) return TVO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cublasHandle_t hb;
+  int rc = cublas_for_stream(st, hb);
+  if (rc) return rc;
+  const size_t wbytes = bsc_mstep_warp_bytes<T>(S, H);
+  int wpb = 8;
+  while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmemFast) wpb >>= 1;
+  TVO_REQUIRE(wbytes * wpb <= (size_t)kMaxSmemFast, "bsc_mstep: working set %zu B exceeds shared memory", wbytes);
+  const size_t smem = wbytes * wpb;
+  auto kern = bsc_mstep_kernel<T>;
+  TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+  occ = max(occ, 1);
+  const double one = 1.0;
+  for (int64_t c0 = 0; c0 < B; c0 += cap) {
+    const int Bc = (int)min(cap, B - c0);
+    double *E = (double *)scratch;
+    double *Yd = sizeof(T) == 8 ? nullptr : E + (size_t)Bc * H;
+    const int grid = (int)max((int64_t)1, min((int64_t)(Bc + wpb - 1) / wpb, (int64_t)sm_count() * occ));
+    kern<<<grid, wpb * 32, smem, st>>>(Y + c0 * ldY, ldY, idx ? idx + c0 : nullptr, c0, K, k_stride_n, lpj, lpj_stride_n, ws,
+                                       stats, E, Yd, Bc, S, H, D, exact, wbytes);
+    TVO_AFTER_LAUNCH("bsc_mstep");
+    // WpT (H x D, row-major) += E^T (H x Bc) * Y (Bc x D)     (bsc.py:145,153)
+    const double *Yp = sizeof(T) == 8 ? (const double *)(Y + c0 * ldY) : Yd;
+    const int ldy = sizeof(T) == 8 ? (int)ldY : D;
+    TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, D, H, Bc, &one, Yp, ldy, E, H, &one, stats, D));
+  }
+  return TVO_OK;
+}
+
+}  // namespace tvo
+
+using namespace tvo;
+
+extern "C" {
+int64_t tvo_bsc_stats_len(int32_t H, int32_t D) { return (int64_t)H * D + (int64_t)H * H + H + 3; }
+int64_t tvo_bsc_estep_scratch_bytes(int64_t B, int32_t H, int32_t is_f64) { return B * (int64_t)H * (is_f64 ? 8 : 4); }
+int64_t tvo_bsc_mstep_scratch_bytes(int64_t B, int32_t H, int32_t D, int32_t is_f64) {
+  return B * ((int64_t)H * 8 + (is_f64 ? 0 : (int64_t)D * 8));
+}
+int tvo_estep_evo_bsc_f64(const double *Y, int64_t ldY, const int64_t *idx, uint64_t *K, double *lpj, const void *ws,
+                          const tvo_evo_config *cfg, const double *sparsity, void *scratch, int64_t scratch_bytes,
+                          int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs, void *stream) {
+  return estep_evo_bsc<double>(Y, ldY, idx, K, lpj, ws, cfg, sparsity, scratch, scratch_bytes, B, S, H, D, nsubs, stream);
+}
+int tvo_estep_evo_bsc_f32(const float *Y, int64_t ldY, const int64_t *idx, uint64_t *K, float *lpj, const void *ws,
+                          const tvo_evo_config *cfg, const double *sparsity, void *scratch, int64_t scratch_bytes,
+                          int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs, void *stream) {
+  return estep_evo_bsc<float>(Y, ldY, idx, K, lpj, ws, cfg, sparsity, scratch, scratch_bytes, B, S, H, D, nsubs, stream);
+}
+int tvo_bsc_mstep_f64(const double *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                      const double *lpj, int64_t lpj_stride_n, const void *ws, double *stats, void *scratch,
+                      int64_t scratch_bytes, int64_t B, int32_t S, int32_t H, int32_t D, int32_t exact_residual,
+                      void *stream) {
+  return bsc_mstep<double>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, ws, stats, scratch, scratch_bytes, B, S, H, D,
+                           exact_residual, stream);
+}
+int tvo_bsc_mstep_f32(const float *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                      const float *lpj, int64_t lpj_stride_n, const void *ws, double *stats, void *scratch,
+                      int64_t scratch_bytes, int64_t B, int32_t S, int32_t H, int32_t D, int32_t exact_residual,
+                      void *stream) {
+  return bsc_mstep<float>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, ws, stats, scratch, scratch_bytes, B, S, H, D,
+                          exact_residual, stream);
+}
+}

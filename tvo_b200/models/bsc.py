@@ -12,8 +12,8 @@ Beneath it:
  * EVO E-step -> tvo_estep_evo_bsc (one fused kernel);
  * update_param_batch -> tvo_bsc_mstep (softmax weights on chip, sparse accumulation);
  * all sufficient statistics + N + F live in ONE fp64 buffer `_stats` = [WpT | Wq | pies | sigma2 |
-   N | F], all-reduced once per EM iteration (the reference issues 5 all_reduce + 4 broadcasts,
-   bsc.py:164-175, sanity.py:40).
+   N | F], all-reduced once per EM iteration, followed by one packed broadcast of the new theta
+   (the reference issues 5 all_reduce + 4 broadcasts, bsc.py:164-175, sanity.py:40).
 """
 import ctypes as C
 import math
@@ -75,6 +75,9 @@ class BSC(Optimized, Sampler, Reconstructor):
         self._ws = None
         self._fresh = None  # (theta versions, batch ptr/version): lpj in `states` was computed from these
         self._last_F = None
+        self.use_gram = True  # Gram-form fused E-step (False: direct column-walk form, D <= 256)
+        self.scratch_datapoints = 131072  # chunk size of the Gram E-step / M-step GEMMs (scratch = chunk*H*8 B)
+        self._scratch = None
         self.W_solver = "gpu"  # "gpu": torch.linalg.lstsq on the device (as the reference under TVO_GPU);
         #                        "cpu": rank-revealing gelsy on the host (as the reference's CPU path)
 
@@ -86,8 +89,18 @@ class BSC(Optimized, Sampler, Reconstructor):
 
     @property
     def my_Wq(self) -> Tensor:
+        """Symmetric sum_n <s s^T>_n (bsc.py:146-147).  The kernel accumulates the upper triangle only."""
         D, H = self._shape
-        return self._stats[H * D: H * D + H * H].view(H, H)
+        U = self._stats[H * D: H * D + H * H].view(H, H)
+        return U + U.t() - to.diag(to.diagonal(U))
+
+    def _get_scratch(self, B: int) -> Tensor:
+        D, H = self._shape
+        n = min(max(int(B), 1), int(self.scratch_datapoints))
+        nbytes = n * (H * 8 + (0 if self._precision == to.float64 else D * 8))
+        if self._scratch is None or self._scratch.numel() < nbytes or self._scratch.device != self._stats.device:
+            self._scratch = to.empty(nbytes, dtype=to.uint8, device=self._stats.device)
+        return self._scratch
 
     @property
     def my_pies(self) -> Tensor:
@@ -163,15 +176,19 @@ class BSC(Optimized, Sampler, Reconstructor):
     def _tvo_estep_evo(self, states, idx: Tensor, batch: Tensor, cfg) -> bool:
         """Fused EVO E-step; returns False when the configuration needs the unfused kernels."""
         D, H = self._shape
-        if D > 256 or cfg.parent_selection == _lib.SEL["batch_fitparents"] or states.lpj.dtype != self._precision:
+        if cfg.parent_selection == _lib.SEL["batch_fitparents"] or states.lpj.dtype != self._precision:
+            return False
+        if D > 256 and not self.use_gram:
             return False
         Y = self._batch(batch)
         ws = self._prepare()
         S = states._Kp.shape[1]
         sparsity = self._tvo_sparsity() if cfg.mutation in (_lib.MUT["sparseflip"], _lib.MUT["cross_sparseflip"]) else None
+        scratch = self._get_scratch(idx.numel()) if self.use_gram else None
         _lib.call(f"tvo_estep_evo_bsc_{_lib.sfx(self._precision)}", _lib.ptr(Y), Y.stride(0), _lib.ptr(idx),
-                  _lib.ptr(states._Kp), _lib.ptr(states.lpj), _lib.ptr(ws), C.byref(cfg), _lib.ptr(sparsity), None,
-                  idx.numel(), S, H, D, _lib.ptr(states._nsubs_dev), _lib.stream())
+                  _lib.ptr(states._Kp), _lib.ptr(states.lpj), _lib.ptr(ws), C.byref(cfg), _lib.ptr(sparsity),
+                  _lib.ptr(scratch), scratch.numel() if scratch is not None else 0, idx.numel(), S, H, D,
+                  _lib.ptr(states._nsubs_dev), _lib.stream())
         self._fresh = (self._theta_token(), batch.data_ptr(), batch._version, id(states))
         return True
 
@@ -221,9 +238,11 @@ class BSC(Optimized, Sampler, Reconstructor):
         assert lpj.dtype == self._precision and lpj.is_contiguous()
         fresh = self._fresh == (self._theta_token(), batch.data_ptr(), batch._version, id(states))
         ws = self._prepare()
+        scratch = self._get_scratch(idx.numel())
         _lib.call(f"tvo_bsc_mstep_{_lib.sfx(self._precision)}", _lib.ptr(Y), Y.stride(0), _lib.ptr(idx), _lib.ptr(Kp),
                   0 if Kp.shape[0] == 1 and lpj.shape[0] != 1 else S * W, _lib.ptr(lpj), lpj.shape[1], _lib.ptr(ws),
-                  _lib.ptr(self._stats), idx.numel(), S, H, D, 0 if fresh else 1, _lib.stream())
+                  _lib.ptr(self._stats), _lib.ptr(scratch), scratch.numel(), idx.numel(), S, H, D, 0 if fresh else 1,
+                  _lib.stream())
         return None
 
     def update_param_epoch(self) -> None:
@@ -256,8 +275,16 @@ class BSC(Optimized, Sampler, Reconstructor):
         policy["pies"][0] = theta["pies"]
         policy["sigma2"][0] = theta["sigma2"]
         fix_theta(theta_new, policy)
+        # every rank solved the same reduced system, but LAPACK/cuSOLVER are not guaranteed to be
+        # bit-reproducible across processes: one small packed broadcast keeps theta identical
+        # everywhere (the reference broadcasts W, pies, sigma2 separately, sanity.py:40)
+        flat = to.cat([theta_new[k].reshape(-1) for k in theta])
+        broadcast(flat)
+        o = 0
         for key in theta:
-            theta[key][:] = theta_new[key]
+            n = theta[key].numel()
+            theta[key][:] = flat[o:o + n].view_as(theta[key])
+            o += n
         self._stats.zero_()
 
     def generate_data(self, N: int = None, hidden_state: Tensor = None) -> Union[Tensor, Tuple[Tensor, Tensor]]:
