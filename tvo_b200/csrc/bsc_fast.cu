@@ -133,7 +133,7 @@ __device__ __forceinline__ void score_states(const uint64_t *states, int count, 
 // EVOVariationalStates.update (evo.py:80-115) for BSC, Gram form.  Same structure and same random
 // stream as estep_evo_bsc_kernel (bsc.cu); `A` holds a = W^T y for the B datapoints of this launch.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                           int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
                           const double *__restrict__ sparsity_p, EstepDims dims, int64_t B, int H, int D,

@@ -28,26 +28,26 @@ struct WarpBuf {
   uint64_t *newK;     // Snew*W64
   uint64_t *parents;  // P*W64
   uint64_t *keys;     // S+Snew
-  uint64_t *thr;      // 2*Sgen   (T0 | T1)
+  uint64_t *fmask;    // Sgen*W64 (sparseflip flip masks)
   double *dscr;       // Scmax (fitparents cum_p) or 0
   T *lpj;             // S+Snew
   uint32_t *hash;     // S+Snew
   int32_t *iscr;      // max(Scmax, 2*Sgen)
-  uint8_t *flags;     // Sgen
 };
 
 template <typename T>
 __host__ __device__ inline size_t warp_buf_bytes(const EstepDims &d) {
   size_t b = 0;
   b += align16((size_t)d.S * d.W64 * 8) + align16((size_t)d.Snew * d.W64 * 8) + align16((size_t)d.P * d.W64 * 8);
-  b += align16((size_t)(d.S + d.Snew) * 8);
-  b += align16((size_t)2 * d.Sgen * 8);
+  {  // keys (select) and fmask (mutation) are never live at the same time: one region
+    const size_t k = (size_t)(d.S + d.Snew) * 8, f = (size_t)d.Sgen * d.W64 * 8;
+    b += align16(k > f ? k : f);
+  }
   b += align16(d.need_fit ? (size_t)d.Scmax * 8 : 0);
   b += align16((size_t)(d.S + d.Snew) * sizeof(T));
   b += align16((size_t)(d.S + d.Snew) * 4);
   const int isz = d.Scmax > 2 * d.Sgen ? d.Scmax : 2 * d.Sgen;
   b += align16((size_t)isz * 4);
-  b += align16((size_t)d.Sgen);
   return b;
 }
 
@@ -61,19 +61,18 @@ __device__ inline WarpBuf<T> carve_warp_buf(unsigned char *p, const EstepDims &d
   w.parents = (uint64_t *)p;
   p += align16((size_t)d.P * d.W64 * 8);
   w.keys = (uint64_t *)p;
-  p += align16((size_t)(d.S + d.Snew) * 8);
-  w.thr = (uint64_t *)p;
-  p += align16((size_t)2 * d.Sgen * 8);
+  w.fmask = (uint64_t *)p;
+  {
+    const size_t k = (size_t)(d.S + d.Snew) * 8, f = (size_t)d.Sgen * d.W64 * 8;
+    p += align16(k > f ? k : f);
+  }
   w.dscr = (double *)p;
   p += align16(d.need_fit ? (size_t)d.Scmax * 8 : 0);
   w.lpj = (T *)p;
   p += align16((size_t)(d.S + d.Snew) * sizeof(T));
   w.hash = (uint32_t *)p;
   p += align16((size_t)(d.S + d.Snew) * 4);
-  const int isz = d.Scmax > 2 * d.Sgen ? d.Scmax : 2 * d.Sgen;
   w.iscr = (int32_t *)p;
-  p += align16((size_t)isz * 4);
-  w.flags = (uint8_t *)p;
   return w;
 }
 
@@ -82,17 +81,25 @@ __device__ inline WarpBuf<T> carve_warp_buf(unsigned char *p, const EstepDims &d
 // candidates, by a partial Fisher-Yates shuffle driven by u32 stream elements 0..P-1.
 __device__ inline void select_randparents(const uint64_t *cand, int S_c, int P, int W64, const Stream &st,
                                           int32_t *perm, uint64_t *parents, int lane) {
+  // the P u32 draws come from ceil(P/4) Philox blocks: lanes compute them in parallel (32 blocks per
+  // round), lane 0 then runs the P dependent swaps reading the draws by shuffle
   for (int i = lane; i < S_c; i += 32) perm[i] = i;
   __syncwarp();
-  if (lane == 0) {
+  for (int i0 = 0; i0 < P; i0 += 128) {
+    const int nblk = (min(P - i0, 128) + 3) >> 2;
     uint4 r = make_uint4(0, 0, 0, 0);
-    for (int i = 0; i < P; ++i) {
-      if ((i & 3) == 0) r = st.block(0, i >> 2);
-      const uint32_t ri = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-      const int k = i + (int)randint_u32(ri, (uint32_t)(S_c - i));
-      const int32_t t = perm[i];
-      perm[i] = perm[k];
-      perm[k] = t;
+    if (lane < nblk) r = st.block(0, (uint32_t)((i0 >> 2) + lane));
+    const int iend = min(P, i0 + 128);
+    for (int i = i0; i < iend; ++i) {
+      const int src = (i - i0) >> 2, q = i & 3;
+      const uint32_t pick = q == 0 ? r.x : q == 1 ? r.y : q == 2 ? r.z : r.w;
+      const uint32_t ri = __shfl_sync(FULL, pick, src);
+      if (lane == 0) {
+        const int k = i + (int)randint_u32(ri, (uint32_t)(S_c - i));
+        const int32_t t = perm[i];
+        perm[i] = perm[k];
+        perm[k] = t;
+      }
     }
   }
   __syncwarp();
@@ -192,48 +199,142 @@ __device__ __forceinline__ void sparseflip_probs(double a, double Hf, double cro
   p1 = __dmul_rn(alpha, p0);
 }
 
-// batch_sparseflip (evo.py:282-331): child j = parent j/C with every bit flipped independently,
-// probability p1 if the bit is set in the parent, p0 otherwise.  May run in place (src == dst, C == 1).
+// q^n by binary exponentiation, fixed operation order (oracle/evo.py:_pow_int)
+__device__ __forceinline__ double pow_int(double q, int n) {
+  double result = 1.0, base = q;
+  int e = n;
+  while (e > 0) {
+    if (e & 1) result = __dmul_rn(result, base);
+    e >>= 1;
+    if (e) base = __dmul_rn(base, base);
+  }
+  return result;
+}
+
+// 1/k for k = 1..64 (IEEE division at compile time == oracle.evo.INV_TAB)
+__device__ __constant__ double kInvTab[65] = {
+    0.0,      1.0 / 1,  1.0 / 2,  1.0 / 3,  1.0 / 4,  1.0 / 5,  1.0 / 6,  1.0 / 7,  1.0 / 8,  1.0 / 9,  1.0 / 10,
+    1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
+    1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32,
+    1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41, 1.0 / 42, 1.0 / 43,
+    1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49, 1.0 / 50, 1.0 / 51, 1.0 / 52, 1.0 / 53, 1.0 / 54,
+    1.0 / 55, 1.0 / 56, 1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61, 1.0 / 62, 1.0 / 63, 1.0 / 64};
+
+// k ~ Binomial(n, p) by CDF inversion of u (oracle/evo.py:binomial_inverse), +,*,/ only, no FMA
+__device__ __forceinline__ int binomial_inverse(double u, int n, double p) {
+  if (n == 0 || !(p > 0.0)) return 0;
+  if (p >= 1.0) return n;
+  const bool flip = p > 0.5;
+  if (flip) p = __dsub_rn(1.0, p);
+  const double q = __dsub_rn(1.0, p);
+  double pmf = pow_int(q, n);
+  int k;
+  if (pmf == 0.0) {
+    k = (int)__dmul_rn((double)n, p);
+  } else {
+    const double r = __ddiv_rn(p, q);
+    double c = pmf;
+    k = 0;
+    while (u >= c && k < n) {
+      const double t = __dmul_rn(__dmul_rn(pmf, (double)(n - k)), r);
+      pmf = k + 1 <= 64 ? __dmul_rn(t, kInvTab[k + 1]) : __ddiv_rn(t, (double)(k + 1));
+      c = __dadd_rn(c, pmf);
+      ++k;
+    }
+  }
+  return flip ? n - k : k;
+}
+
+// position of the (i+1)-th set bit of a 64-bit mask (i < popcount), branch-light binary search
+__device__ __forceinline__ int nth_set_bit64(uint64_t m, int i) {
+  uint32_t x = (uint32_t)m;
+  int base = 0;
+  int c = __popc(x);
+  if (i >= c) {
+    i -= c;
+    x = (uint32_t)(m >> 32);
+    base = 32;
+  }
+  c = __popc(x & 0xFFFFu);
+  if (i >= c) { i -= c; x >>= 16; base += 16; }
+  c = __popc(x & 0xFFu);
+  if (i >= c) { i -= c; x >>= 8; base += 8; }
+  c = __popc(x & 0xFu);
+  if (i >= c) { i -= c; x >>= 4; base += 4; }
+  c = __popc(x & 0x3u);
+  if (i >= c) { i -= c; x >>= 2; base += 2; }
+  c = (int)(x & 1u);
+  if (i >= c) base += 1;
+  return base;
+}
+
+// position (0..H-1) of the idx-th set bit of the multi-word mask  m_w = cand_w(src) & ~fm_w
+__device__ __forceinline__ int nth_remaining(const uint64_t *src, const uint64_t *fm, int W64, int H, int cls, int idx) {
+  for (int w = 0; w < W64; ++w) {
+    const int nb = H - 64 * w;
+    const uint64_t valid = nb >= 64 ? ~0ull : ((1ull << nb) - 1);
+    const uint64_t m = (cls ? src[w] : (~src[w] & valid)) & ~fm[w];
+    const int c = __popcll(m);
+    if (idx < c) return (w << 6) + nth_set_bit64(m, idx);
+    idx -= c;
+  }
+  return 0;  // unreachable for idx < #remaining
+}
+
+// batch_sparseflip (evo.py:282-331): child j = parent j/C with every bit flipped independently with
+// probability p1 if the bit is set in the parent, p0 otherwise.  Sampled exactly as: number of flips
+// among the zero bits ~ Binomial(H-a, p0), among the one bits ~ Binomial(a, p1); positions = uniform
+// subset drawn without replacement (draw i = the t-th remaining candidate).  One LANE per child, one
+// Philox block for the two counts plus one per 4 flips, instead of H uniforms per child.
+// `fmask` (nchild x W64 words) collects the flips; dst = src ^ fmask, so src == dst (C == 1) is fine.
 __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int W64, int H, double sparsity,
-                                         double p_bf, const Stream &st0, const Stream &st1, uint64_t *thr,
-                                         uint8_t *flags, uint64_t *dst, int lane) {
+                                         double p_bf, const Stream &st0, const Stream &st1, uint64_t *fmask,
+                                         uint64_t *dst, int lane) {
   const double Hf = (double)H;
   const double crowd = __dmul_rn(sparsity, Hf);
-  for (int p = lane; p < P; p += 32) {
-    int a = 0;
-    for (int w = 0; w < W64; ++w) a += __popcll(src[p * W64 + w]);
-    double p0, p1;
-    sparseflip_probs((double)a, Hf, crowd, p_bf, p0, p1);
-    uint64_t T0, T1;
-    uint32_t a0, a1;
-    prob_to_fixed64(p0, T0, a0);
-    prob_to_fixed64(p1, T1, a1);
-    thr[2 * p] = T0;
-    thr[2 * p + 1] = T1;
-    flags[p] = (uint8_t)(a0 | (a1 << 1));
-  }
-  __syncwarp();
-  // tasks (child j, word w); descending so that in-place C==1 and out-of-place C>1 both read
-  // their source word before any task overwrites it (each task only touches word (j,w)).
-  const int ntask = P * C * W64;
-  for (int t0 = 0; t0 < ntask; t0 += 32) {
-    const int t = t0 + lane;
-    uint64_t out = 0;
-    if (t < ntask) {
-      const int j = t / W64, w = t % W64, p = j / C;
-      const uint64_t s = src[p * W64 + w];
-      const int nb = H - 64 * w;
-      const uint64_t valid = nb >= 64 ? ~0ull : ((1ull << nb) - 1);
-      const uint32_t slot = ((uint32_t)j << 8) | (uint32_t)w;
-      const uint8_t f = flags[p];
-      const uint64_t m0 = bernoulli_mask64(st0, slot, thr[2 * p], f & 1u, ~s & valid);
-      const uint64_t m1 = s ? bernoulli_mask64(st1, slot, thr[2 * p + 1], (f >> 1) & 1u, s) : 0ull;
-      out = s ^ (m0 | m1);
+  const int nchild = P * C;
+  for (int j0 = 0; j0 < nchild; j0 += 32) {
+    const int j = j0 + lane;
+    if (j < nchild) {
+      const uint64_t *par = src + (size_t)(j / C) * W64;
+      uint64_t *fm = fmask + (size_t)j * W64;
+      int a = 0;
+      for (int w = 0; w < W64; ++w) {
+        a += __popcll(par[w]);
+        fm[w] = 0;
+      }
+      double p0, p1;
+      sparseflip_probs((double)a, Hf, crowd, p_bf, p0, p1);
+#pragma unroll
+      for (int cls = 0; cls < 2; ++cls) {
+        const int n = cls ? a : H - a;
+        const double pc = cls ? p1 : p0;
+        if (n == 0 || !(pc > 0.0)) continue;
+        const Stream &st = cls ? st1 : st0;
+        const int k = binomial_inverse(unit_double(st.u64((uint32_t)j, 0)), n, pc);
+        if (k == 0) continue;
+        const bool complement = 2 * k > n;  // draw the smaller of {flipped, not flipped}
+        const int draws = k >= n ? 0 : (complement ? n - k : k);
+        uint4 r = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < draws; ++i) {
+          if ((i & 3) == 0) r = st.block((uint32_t)j, 1 + (i >> 2));
+          const uint32_t ri = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+          const int pos = nth_remaining(par, fm, W64, H, cls, (int)randint_u32(ri, (uint32_t)(n - i)));
+          fm[pos >> 6] |= 1ull << (pos & 63);
+        }
+        if (k >= n || complement) {  // flip every candidate of the class that was NOT drawn
+          for (int w = 0; w < W64; ++w) {
+            const int nb = H - 64 * w;
+            const uint64_t valid = nb >= 64 ? ~0ull : ((1ull << nb) - 1);
+            const uint64_t cand = cls ? par[w] : (~par[w] & valid);
+            fm[w] = (fm[w] & ~cand) | (cand & ~fm[w]);
+          }
+        }
+      }
+      for (int w = 0; w < W64; ++w) dst[(size_t)j * W64 + w] = par[w] ^ fm[w];
     }
     __syncwarp();
-    if (t < ntask) dst[t] = out;
   }
-  __syncwarp();
 }
 
 // batch_cross (evo.py:335-380): pairs in combinations(range(P),2) order, cut ~ U{1..H-1} from u32
@@ -291,7 +392,7 @@ __device__ inline void evo_generation(const WarpBuf<T> &wb, const uint64_t *cand
       mutate_randflip(wb.parents, ep.P, ep.C, W64, H, st, wb.iscr, children, lane);
       break;
     case TVO_MUT_SPARSEFLIP:
-      mutate_sparseflip(wb.parents, ep.P, ep.C, W64, H, sparsity, ep.p_bf, s0, s1, wb.thr, wb.flags, children, lane);
+      mutate_sparseflip(wb.parents, ep.P, ep.C, W64, H, sparsity, ep.p_bf, s0, s1, wb.fmask, children, lane);
       break;
     default: {
       st.tag = make_tag(ep.step, gen, PUR_CROSS);
@@ -306,7 +407,7 @@ __device__ inline void evo_generation(const WarpBuf<T> &wb, const uint64_t *cand
         }
         __syncwarp();
       } else if (ep.mut == TVO_MUT_CROSS_SPARSEFLIP) {
-        mutate_sparseflip(children, nc, 1, W64, H, sparsity, ep.p_bf, s0, s1, wb.thr, wb.flags, children, lane);
+        mutate_sparseflip(children, nc, 1, W64, H, sparsity, ep.p_bf, s0, s1, wb.fmask, children, lane);
       }
     }
   }
@@ -315,33 +416,75 @@ __device__ inline void evo_generation(const WarpBuf<T> &wb, const uint64_t *cand
 // ------------------------------------------------------------------------------------ dedup
 // set_redundant_lpj_to_low (_set_redundant_lpj_to_low_CPU.pyx:13-30): child c is redundant if it
 // equals a LATER child, else if it equals an old state.  Marks wb.lpj[S+c] = (float)-1e20.
+__device__ __forceinline__ bool same_state(const uint64_t *x, const uint64_t *y, int W64) {
+  bool eq = true;
+  for (int w = 0; w < W64; ++w) eq &= (x[w] == y[w]);
+  return eq;
+}
+
+// Child c is redundant if an old state (j < S) or a LATER child (j - S > c) has the same bits.
+// Pass 1 scans the 32-bit hashes of all M candidates (4 per shared load) for every child of the lane
+// and remembers the first hash match; pass 2 does ONE full compare per child.  Only a hash collision
+// (first match is not a true duplicate although further hash matches exist) takes the slow rescan.
 template <typename T>
 __device__ inline void mark_redundant(const WarpBuf<T> &wb, int S, int Snew, int W64, int lane) {
   const int M = S + Snew;
   for (int i = lane; i < M; i += 32)
     wb.hash[i] = hash_words(i < S ? wb.oldK + (size_t)i * W64 : wb.newK + (size_t)(i - S) * W64, W64);
   __syncwarp();
-  for (int c = lane; c < Snew; c += 32) {
-    const uint32_t hc = wb.hash[S + c];
-    const uint64_t *sc = wb.newK + (size_t)c * W64;
-    bool dup = false;
-    for (int j = c + 1; j < Snew && !dup; ++j) {
-      if (wb.hash[S + j] == hc) {
-        const uint64_t *sj = wb.newK + (size_t)j * W64;
-        bool eq = true;
-        for (int w = 0; w < W64; ++w) eq &= (sj[w] == sc[w]);
-        dup = eq;
+  constexpr int CPL = 4;  // children per lane handled per sweep
+  const int M4 = M & ~3;
+  for (int c0 = 0; c0 < Snew; c0 += 32 * CPL) {
+    uint32_t hc[CPL];
+    int first[CPL], nmatch[CPL];
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+      const int c = c0 + 32 * t + lane;
+      hc[t] = c < Snew ? wb.hash[S + c] : 0u;
+      first[t] = -1;
+      nmatch[t] = 0;
+    }
+    for (int j = 0; j < M; j += 4) {
+      uint4 h4;
+      if (j < M4) {
+        h4 = *reinterpret_cast<const uint4 *>(wb.hash + j);  // hash is 16-byte aligned
+      } else {
+        h4.x = wb.hash[j];
+        h4.y = j + 1 < M ? wb.hash[j + 1] : 0u;
+        h4.z = j + 2 < M ? wb.hash[j + 2] : 0u;
+        h4.w = 0u;
+      }
+#pragma unroll
+      for (int t = 0; t < CPL; ++t) {
+        const int c = c0 + 32 * t + lane;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t hj = u == 0 ? h4.x : u == 1 ? h4.y : u == 2 ? h4.z : h4.w;
+          const int jj = j + u;
+          const bool hit = hj == hc[t] && jj < M && c < Snew && (jj < S || jj - S > c);
+          if (hit) {
+            if (first[t] < 0) first[t] = jj;
+            ++nmatch[t];
+          }
+        }
       }
     }
-    for (int j = 0; j < S && !dup; ++j) {
-      if (wb.hash[j] == hc) {
-        const uint64_t *sj = wb.oldK + (size_t)j * W64;
-        bool eq = true;
-        for (int w = 0; w < W64; ++w) eq &= (sj[w] == sc[w]);
-        dup = eq;
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+      const int c = c0 + 32 * t + lane;
+      bool dup = false;
+      if (first[t] >= 0) {
+        const uint64_t *sc = wb.newK + (size_t)c * W64;
+        const int jj = first[t];
+        dup = same_state(jj < S ? wb.oldK + (size_t)jj * W64 : wb.newK + (size_t)(jj - S) * W64, sc, W64);
+        if (!dup && nmatch[t] > 1) {  // hash collision: rescan everything (practically never)
+          for (int j2 = jj + 1; j2 < M && !dup; ++j2)
+            if (wb.hash[j2] == hc[t] && (j2 < S || j2 - S > c))
+              dup = same_state(j2 < S ? wb.oldK + (size_t)j2 * W64 : wb.newK + (size_t)(j2 - S) * W64, sc, W64);
+        }
       }
+      if (dup) wb.lpj[S + c] = LowLpj<T>::v();
     }
-    if (dup) wb.lpj[S + c] = LowLpj<T>::v();
   }
   __syncwarp();
 }
@@ -350,6 +493,77 @@ __device__ inline void mark_redundant(const WarpBuf<T> &wb, int S, int Snew, int
 // update_states_for_batch (_utils.py:124-179): keep the S best of old+new, stored ascending (best
 // last); ties -> lower concatenated index ranks higher.  Writes the datapoint's K and lpj rows in
 // global memory and returns the number of selected children (warp-uniform).
+// "x ranks before y": larger key first, ties -> lower concatenated index first
+__device__ __forceinline__ bool ranks_before(uint64_t kx, int ix, uint64_t ky, int iy) {
+  return kx > ky || (kx == ky && ix < iy);
+}
+
+// Sort the M = S+Snew candidates best-first with a warp bitonic network (EPL elements per lane,
+// element e = lane*EPL + r; distances < EPL are register-local, larger ones use shuffles) and emit
+// the best S in ascending order.  iscr[pos] receives the source index of output position pos.
+template <typename T, int EPL>
+__device__ __forceinline__ int select_sorted(const WarpBuf<T> &wb, int S, int M, T *lpj_row, int lane) {
+  constexpr int MP = 32 * EPL;
+  uint64_t key[EPL];
+  int src[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    key[r] = e < M ? wb.keys[e] : 0ull;
+    src[r] = e < M ? e : 0x7fffffff;
+  }
+#pragma unroll
+  for (int k = 2; k <= MP; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j < EPL) {
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+          if ((r & j) == 0) {  // pair (r, r^j) inside the lane
+            const int e = lane * EPL + r;
+            const bool up = (e & k) == 0;  // best-first block
+            const bool swap = ranks_before(key[r ^ j], src[r ^ j], key[r], src[r]) == up;
+            if (swap) {
+              const uint64_t tk = key[r];
+              key[r] = key[r ^ j];
+              key[r ^ j] = tk;
+              const int ti = src[r];
+              src[r] = src[r ^ j];
+              src[r ^ j] = ti;
+            }
+          }
+        }
+      } else {
+        const int lm = j / EPL;
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+          const int e = lane * EPL + r;
+          const uint64_t ok = __shfl_xor_sync(FULL, key[r], lm);
+          const int oi = __shfl_xor_sync(FULL, src[r], lm);
+          const bool want_better = ((e & j) == 0) == ((e & k) == 0);
+          const bool other_better = ranks_before(ok, oi, key[r], src[r]);
+          if (other_better == want_better) {
+            key[r] = ok;
+            src[r] = oi;
+          }
+        }
+      }
+    }
+  }
+  int nsub = 0;
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    if (e < S) {
+      const int pos = S - 1 - e;
+      lpj_row[pos] = wb.lpj[src[r]];
+      wb.iscr[pos] = src[r];
+      nsub += (src[r] >= S) ? 1 : 0;
+    }
+  }
+  return nsub;
+}
+
 template <typename T>
 __device__ inline int select_topS(const WarpBuf<T> &wb, int S, int Snew, int W64, uint64_t *K_row, T *lpj_row,
                                   int lane) {
@@ -357,20 +571,26 @@ __device__ inline int select_topS(const WarpBuf<T> &wb, int S, int Snew, int W64
   for (int i = lane; i < M; i += 32) wb.keys[i] = sort_key((double)wb.lpj[i]);
   __syncwarp();
   int nsub = 0;
-  for (int i0 = 0; i0 < M; i0 += 32) {
-    const int i = i0 + lane;
-    const uint64_t ki = i < M ? wb.keys[i] : 0;
-    int rank = 0;
-    for (int j = 0; j < M; ++j) {
-      const uint64_t kj = wb.keys[j];
-      rank += (kj > ki || (kj == ki && j < i)) ? 1 : 0;
-    }
-    const bool sel = i < M && rank < S;
-    if (sel) {
-      const int pos = S - 1 - rank;
-      lpj_row[pos] = wb.lpj[i];
-      wb.iscr[pos] = i;  // source row of output position (iscr has >= S entries: Scmax >= S)
-      nsub += (i >= S) ? 1 : 0;
+  if (M <= 32) {
+    nsub = select_sorted<T, 1>(wb, S, M, lpj_row, lane);
+  } else if (M <= 64) {
+    nsub = select_sorted<T, 2>(wb, S, M, lpj_row, lane);
+  } else if (M <= 128) {
+    nsub = select_sorted<T, 4>(wb, S, M, lpj_row, lane);
+  } else if (M <= 256) {
+    nsub = select_sorted<T, 8>(wb, S, M, lpj_row, lane);
+  } else {
+    for (int i0 = 0; i0 < M; i0 += 32) {  // rank by counting
+      const int i = i0 + lane;
+      const uint64_t ki = i < M ? wb.keys[i] : 0;
+      int rank = 0;
+      for (int j = 0; j < M; ++j) rank += ranks_before(wb.keys[j], j, ki, i) ? 1 : 0;
+      if (i < M && rank < S) {
+        const int pos = S - 1 - rank;
+        lpj_row[pos] = wb.lpj[i];
+        wb.iscr[pos] = i;  // iscr has >= S entries: Scmax >= S
+        nsub += (i >= S) ? 1 : 0;
+      }
     }
   }
   __syncwarp();
