@@ -149,37 +149,52 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
   const double sparsity = sparsity_p ? *sparsity_p : 0.0;
   unsigned long long my_subs = 0;
 
-  for (int64_t b = (int64_t)blockIdx.x * wpb + wib; b < B; b += (int64_t)gridDim.x * wpb) {
-    const int64_t row = idx ? idx[b] : row0 + b;
+  // All warps of a CTA walk the phases of the E-step in lockstep (PHASE_SYNC): the fused program is
+  // ~100 KB of SASS, far beyond the instruction cache, and 24 independent warps at 24 different places
+  // thrash it (ncu: 35% of stalls were instruction fetch).  With the barriers the 8 warps of a CTA
+  // share the cache lines of the phase they are all in.
+#define PHASE_SYNC() __syncthreads()
+  for (int64_t b0 = (int64_t)blockIdx.x * wpb; b0 < B; b0 += (int64_t)gridDim.x * wpb) {
+    const int64_t b = b0 + wib;
+    const bool active = b < B;
+    const int64_t row = active ? (idx ? idx[b] : row0 + b) : 0;
     const uint32_t n_glob = ep.n_offset + (uint32_t)row;
     uint64_t *Krow = K + row * (int64_t)S * W64;
     T *lrow = lpj + row * (int64_t)S;
-    const T *y = Y + b * ldY;
-    __syncwarp();
+    const T *y = Y + (active ? b : 0) * ldY;
     double yy = 0.0;
     bool has_nan = false;
-    for (int d = lane; d < D; d += 32) {
-      const double v = (double)y[d];
-      has_nan |= (v != v);
-      yy += v * v;
+    if (active) {
+      for (int d = lane; d < D; d += 32) {
+        const double v = (double)y[d];
+        has_nan |= (v != v);
+        yy += v * v;
+      }
+      yy = warp_sum(yy);
+      has_nan = __any_sync(FULL, has_nan);
+      for (int h = lane; h < H; h += 32) a_sm[h] = A[b * (int64_t)H + h];
+      for (int t = lane; t < S * W64; t += 32) wb.oldK[t] = Krow[t];
+      __syncwarp();
     }
-    yy = warp_sum(yy);
-    has_nan = __any_sync(FULL, has_nan);
-    for (int h = lane; h < H; h += 32) a_sm[h] = A[b * (int64_t)H + h];
-    for (int t = lane; t < S * W64; t += 32) wb.oldK[t] = Krow[t];
-    __syncwarp();
-    score_states<T>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, lane);  // evo.py:95
+    PHASE_SYNC();
+    if (active) score_states<T>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, lane);  // evo.py:95
     for (int g = 0; g < ep.G; ++g) {
       const uint64_t *cand = g == 0 ? wb.oldK : wb.newK + (size_t)(g - 1) * Sgen * W64;
       const T *cand_lpj = g == 0 ? wb.lpj : wb.lpj + S + (g - 1) * Sgen;
       uint64_t *children = wb.newK + (size_t)g * Sgen * W64;
-      evo_generation<T>(wb, cand, cand_lpj, g == 0 ? S : Sgen, children, ep, g, n_glob, W64, H, sparsity, 0.0, 1.0,
-                        lane);
-      score_states<T>(children, Sgen, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj + S + g * Sgen, lane);
+      PHASE_SYNC();
+      if (active)
+        evo_generation<T>(wb, cand, cand_lpj, g == 0 ? S : Sgen, children, ep, g, n_glob, W64, H, sparsity, 0.0, 1.0,
+                          lane);
+      PHASE_SYNC();
+      if (active) score_states<T>(children, Sgen, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj + S + g * Sgen, lane);
     }
-    mark_redundant<T>(wb, S, Snew, W64, lane);
-    my_subs += (unsigned long long)select_topS<T>(wb, S, Snew, W64, Krow, lrow, lane);
+    PHASE_SYNC();
+    if (active) mark_redundant<T>(wb, S, Snew, W64, lane);
+    PHASE_SYNC();
+    if (active) my_subs += (unsigned long long)select_topS<T>(wb, S, Snew, W64, Krow, lrow, lane);
   }
+#undef PHASE_SYNC
   if (lane == 0 && my_subs) atomicAdd(nsubs, my_subs);
 }
 
@@ -352,6 +367,7 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   if (rc) return rc;
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
   const size_t wbytes = warp_buf_bytes<T>(dims) + align16((size_t)H * sizeof(T));
+  // 8 warps per CTA, 3 CTAs per SM (one 24-warp CTA per SM in lockstep measured the same)
   int wpb = 8;
   while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmemFast) wpb >>= 1;
   TVO_REQUIRE(wbytes * wpb <= (size_t)kMaxSmemFast, "estep_evo_bsc: per-datapoint working set %zu B exceeds shared memory",

@@ -305,7 +305,7 @@ __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int 
       }
       double p0, p1;
       sparseflip_probs((double)a, Hf, crowd, p_bf, p0, p1);
-#pragma unroll
+#pragma unroll 1
       for (int cls = 0; cls < 2; ++cls) {
         const int n = cls ? a : H - a;
         const double pc = cls ? p1 : p0;
@@ -416,7 +416,7 @@ __device__ inline void evo_generation(const WarpBuf<T> &wb, const uint64_t *cand
 // ------------------------------------------------------------------------------------ dedup
 // set_redundant_lpj_to_low (_set_redundant_lpj_to_low_CPU.pyx:13-30): child c is redundant if it
 // equals a LATER child, else if it equals an old state.  Marks wb.lpj[S+c] = (float)-1e20.
-__device__ __forceinline__ bool same_state(const uint64_t *x, const uint64_t *y, int W64) {
+static __device__ __noinline__ bool same_state(const uint64_t *x, const uint64_t *y, int W64) {
   bool eq = true;
   for (int w = 0; w < W64; ++w) eq &= (x[w] == y[w]);
   return eq;
@@ -512,39 +512,40 @@ __device__ __forceinline__ int select_sorted(const WarpBuf<T> &wb, int S, int M,
     key[r] = e < M ? wb.keys[e] : 0ull;
     src[r] = e < M ? e : 0x7fffffff;
   }
-#pragma unroll
+  // stage loops are kept rolled (code size: the unrolled network was 1.3k instructions per EPL)
+#pragma unroll 1
   for (int k = 2; k <= MP; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j >= EPL; j >>= 1) {  // partner in another lane
+      const int lm = j / EPL;
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j < EPL) {
+      for (int r = 0; r < EPL; ++r) {
+        const int e = lane * EPL + r;
+        const uint64_t ok = __shfl_xor_sync(FULL, key[r], lm);
+        const int oi = __shfl_xor_sync(FULL, src[r], lm);
+        const bool want_better = ((e & j) == 0) == ((e & k) == 0);
+        if (ranks_before(ok, oi, key[r], src[r]) == want_better) {
+          key[r] = ok;
+          src[r] = oi;
+        }
+      }
+    }
+#pragma unroll
+    for (int jj = EPL >> 1; jj > 0; jj >>= 1) {  // partner in the same lane (static register indices)
+      if (jj < k) {
 #pragma unroll
         for (int r = 0; r < EPL; ++r) {
-          if ((r & j) == 0) {  // pair (r, r^j) inside the lane
+          if ((r & jj) == 0) {
             const int e = lane * EPL + r;
             const bool up = (e & k) == 0;  // best-first block
-            const bool swap = ranks_before(key[r ^ j], src[r ^ j], key[r], src[r]) == up;
-            if (swap) {
+            if (ranks_before(key[r ^ jj], src[r ^ jj], key[r], src[r]) == up) {
               const uint64_t tk = key[r];
-              key[r] = key[r ^ j];
-              key[r ^ j] = tk;
+              key[r] = key[r ^ jj];
+              key[r ^ jj] = tk;
               const int ti = src[r];
-              src[r] = src[r ^ j];
-              src[r ^ j] = ti;
+              src[r] = src[r ^ jj];
+              src[r ^ jj] = ti;
             }
-          }
-        }
-      } else {
-        const int lm = j / EPL;
-#pragma unroll
-        for (int r = 0; r < EPL; ++r) {
-          const int e = lane * EPL + r;
-          const uint64_t ok = __shfl_xor_sync(FULL, key[r], lm);
-          const int oi = __shfl_xor_sync(FULL, src[r], lm);
-          const bool want_better = ((e & j) == 0) == ((e & k) == 0);
-          const bool other_better = ranks_before(ok, oi, key[r], src[r]);
-          if (other_better == want_better) {
-            key[r] = ok;
-            src[r] = oi;
           }
         }
       }
