@@ -210,6 +210,40 @@ int tvo_bsc_mstep_f32(const float *Y, int64_t ldY, const int64_t *idx, const uin
                       int64_t scratch_bytes, int64_t B, int32_t S, int32_t H, int32_t D, int32_t exact_residual,
                       void *stream);
 
+/* ---- NoisyOR (tvo/models/noisyor.py).  Y is uint8 (B, D), as the reference requires (noisyor.py:71).
+ *      theta digestion: W (D,H), pies (H) -> (1 - W)^T padded, log-odds prior, sum log(1-pi).
+ *      lpj: noisyor.py:67-106 incl. the all-zero-state rule (0 if y == 0 else -1e30).
+ *      fused EVO E-step: same contract as tvo_estep_evo_bsc (direct form; no scratch).
+ *      M-step: noisyor.py:108-138 into stats = [BtildeT (H*D) | CtildeT (H*D) | new_pi (H) | N | F]
+ *      (fp64, INCREMENTED; F = sum logsumexp(lpj) + sum_h log(1-pi_h)). ---- */
+int64_t tvo_noisyor_theta_ws_bytes(int32_t H, int32_t D, int32_t is_f64);
+int64_t tvo_noisyor_stats_len(int32_t H, int32_t D);
+int tvo_noisyor_prepare_f64(const double *W, const double *pies, int32_t H, int32_t D, void *theta_ws, void *stream);
+int tvo_noisyor_prepare_f32(const float *W, const float *pies, int32_t H, int32_t D, void *theta_ws, void *stream);
+int tvo_noisyor_lpj_f64(const uint8_t *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx,
+                        const void *theta_ws, double *lpj_out, int64_t lpj_stride_n, int64_t B, int32_t S, int32_t H,
+                        int32_t D, void *stream);
+int tvo_noisyor_lpj_f32(const uint8_t *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx,
+                        const void *theta_ws, float *lpj_out, int64_t lpj_stride_n, int64_t B, int32_t S, int32_t H,
+                        int32_t D, void *stream);
+int tvo_estep_evo_noisyor_f64(const uint8_t *Y, int64_t ldY, const int64_t *idx, uint64_t *K, double *lpj,
+                              const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity, int64_t B,
+                              int32_t S, int32_t H, int32_t D, int64_t *nsubs, void *stream);
+int tvo_estep_evo_noisyor_f32(const uint8_t *Y, int64_t ldY, const int64_t *idx, uint64_t *K, float *lpj,
+                              const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity, int64_t B,
+                              int32_t S, int32_t H, int32_t D, int64_t *nsubs, void *stream);
+int tvo_noisyor_mstep_f64(const uint8_t *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                          const double *lpj, int64_t lpj_stride_n, const void *theta_ws, double *stats, int64_t B,
+                          int32_t S, int32_t H, int32_t D, void *stream);
+int tvo_noisyor_mstep_f32(const uint8_t *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                          const float *lpj, int64_t lpj_stride_n, const void *theta_ws, double *stats, int64_t B,
+                          int32_t S, int32_t H, int32_t D, void *stream);
+/* *out (device double) += sum_b logsumexp_s lpj[b, s]  (model_protocols.py:191-193) */
+int tvo_logsumexp_sum_f64(const double *lpj, int64_t stride_n, const int64_t *idx, int64_t B, int32_t S, double *out,
+                          void *stream);
+int tvo_logsumexp_sum_f32(const float *lpj, int64_t stride_n, const int64_t *idx, int64_t B, int32_t S, double *out,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,182 @@
+"""GPU parity tests of the NoisyOR path (through the C ABI) against the oracle and the reference fixtures."""
+import math
+
+import numpy as np
+import pytest
+import torch as to
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+if to.cuda.is_available():
+    import tvo_b200
+    from tvo_b200.models import NoisyOR
+    from tvo_b200.trainer import Trainer
+    from tvo_b200.utils.data import TVODataLoader
+    from tvo_b200.variational import EVOVariationalStates, FullEM, RandomSampledVarStates
+
+from oracle import evo as oevo
+from oracle import models as om
+from oracle import states as ost
+
+DEV = "cuda:0"
+
+
+def dev(a, dtype=None):
+    t = to.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+@pytest.mark.parametrize("tag,dtype,tol", [("f64", to.float64, 1e-10), ("f32", to.float32, 1e-4)])
+def test_noisyor_golden(tag, dtype, tol):
+    g = load_golden(f"noisyor_{tag}.npz")
+    D, H = g["W"].shape
+    tvo_b200._set_device(to.device(DEV))
+    m = NoisyOR(H, D, dev(g["W"]), dev(g["pies"]), precision=dtype)
+    Y, K = dev(g["Y"]), dev(g["K"])
+    lpj = m.log_pseudo_joint(Y, K)
+    assert lpj.dtype == dtype
+    assert np.allclose(lpj.cpu().numpy(), g["lpj"], rtol=tol, atol=tol)
+    assert int((lpj == -1e30).sum()) == int((g["lpj"] == -1e30).sum()) > 0
+    N, S = g["K"].shape[:2]
+    st = EVOVariationalStates(N, H, S, dtype, "randparents", "randflip", 2, 1, 1, K_init=K)
+    st.lpj[:] = dev(g["lpj"], dtype)
+    assert math.isclose(m.free_energy(to.arange(N), Y, st), float(g["F"]), rel_tol=max(tol, 1e-12))
+    m.update_param_batch(to.arange(N), Y, st)
+    for name in ("new_pi", "Btilde", "Ctilde"):
+        assert np.allclose(getattr(m, name).cpu().numpy(), g[name], rtol=100 * tol, atol=100 * tol), name
+    assert int(m._train_datapoints.item()) == N
+    assert math.isclose(float(m._stats[-1]), float(g["F"]), rel_tol=max(tol, 1e-12))
+    m.update_param_epoch()
+    assert np.allclose(m.theta["W"].cpu().numpy(), g["W_new"], rtol=1000 * tol, atol=1000 * tol)
+    assert np.allclose(m.theta["pies"].cpu().numpy(), g["pies_new"], rtol=100 * tol)
+
+
+def test_noisyor_reference_closed_form():
+    # test/noisyor_test.py:17-67
+    tvo_b200._set_device(to.device(DEV))
+    N, D, H = 2, 1, 2
+    m = NoisyOR(H, D, to.full((D, H), 0.5), to.full((H,), 0.5), precision=to.float32)
+    st = FullEM(N, H, m.precision)
+    data = to.tensor([[0], [1]], dtype=to.uint8, device=DEV)
+    true_lpj = to.tensor([[0, np.log(1 / 2), np.log(1 / 2), np.log(1 / 4)], [-1e30, np.log(1 / 2), np.log(1 / 2), np.log(3 / 4)]],
+                         device=DEV, dtype=to.float32)
+    lpj = m.log_pseudo_joint(data, st.K)
+    assert to.allclose(lpj, true_lpj)
+    st.lpj[:] = lpj
+    F0 = m.free_energy(to.arange(N), data, st)
+    assert math.isclose(F0, -1.4020427180880297, rel_tol=1e-6)
+    m.init_epoch()
+    m.update_param_batch(to.arange(N), data, st)
+    m.update_param_epoch()
+    st.lpj[:] = m.log_pseudo_joint(data, st.K)
+    assert m.free_energy(to.arange(N), data, st) > F0
+
+
+@pytest.mark.parametrize("dtype,tol", [(to.float64, 1e-10), (to.float32, 2e-4)])
+@pytest.mark.parametrize("H,D,S", [(6, 7, 5), (64, 100, 16), (70, 33, 9), (130, 200, 4)])
+def test_noisyor_lpj_mstep_random_vs_oracle(dtype, tol, H, D, S):
+    rng = np.random.default_rng(H + D)
+    N = 21
+    npd = np.float64 if dtype == to.float64 else np.float32
+    W = rng.uniform(0.02, 0.98, (D, H)).astype(npd)
+    pies = rng.uniform(0.02, 0.4, H).astype(npd)
+    Y = (rng.random((N, D)) < 0.3).astype(np.uint8)
+    Y[2] = 0
+    K = (rng.random((N, S, H)) < min(0.3, 4.0 / H)).astype(np.uint8)
+    K[:, 0] = 0
+    tvo_b200._set_device(to.device(DEV))
+    m = NoisyOR(H, D, dev(W), dev(pies), precision=dtype)
+    o = om.NoisyOR(H, D, W, pies, precision=npd)
+    want = o.log_pseudo_joint(Y, K)
+    lpj = m.log_pseudo_joint(dev(Y), dev(K)).cpu().numpy()
+    ok = want > -1e29
+    assert np.array_equal(lpj[~ok], want[~ok])
+    assert np.allclose(lpj[ok], want[ok], rtol=tol, atol=tol * np.abs(want[ok]).max())
+    st = EVOVariationalStates(N, H, S, dtype, "randparents", "randflip", 2, 1, 1, K_init=dev(K))
+    st.lpj[:] = dev(want)
+    od = om.NoisyOR(H, D, W.astype(np.float64), pies.astype(np.float64))
+    od.update_param_batch(Y, K, want.astype(np.float64))
+    m.update_param_batch(to.arange(N), dev(Y), st)
+    mt = 50 * tol
+    assert np.allclose(m.new_pi.cpu().numpy(), od.new_pi, rtol=mt, atol=mt)
+    assert np.allclose(m.Btilde.cpu().numpy(), od.Btilde, rtol=mt, atol=mt * np.abs(od.Btilde).max())
+    assert np.allclose(m.Ctilde.cpu().numpy(), od.Ctilde, rtol=mt, atol=mt * np.abs(od.Ctilde).max())
+
+
+@pytest.mark.parametrize("sel,mut,P,Cn,G,cross", [
+    ("fitparents_fixed", "randflip", 4, None, 1, True),      # BASELINE config 4 operators (cross_randflip)
+    ("batch_fitparents", "randflip", 4, None, 1, True),      # reference-compatible fitness -> unfused kernels
+    ("randparents", "sparseflip", 3, 2, 2, False),
+])
+def test_noisyor_estep_bit_exact(sel, mut, P, Cn, G, cross):
+    rng = np.random.default_rng(5)
+    N, H, D, S = 20, 64, 100, 12
+    W = rng.uniform(0.05, 0.95, (D, H))
+    pies = np.full(H, 2.0 / H)
+    Y = (rng.random((N, D)) < 0.25).astype(np.uint8)
+    K = np.zeros((N, S, H), np.uint8)
+    for n in range(N):
+        seen = {}
+        while len(seen) < S:
+            s = (rng.random(H) < 3.0 / H).astype(np.uint8)
+            seen.setdefault(s.tobytes(), s)
+        K[n] = list(seen.values())
+    tvo_b200._set_device(to.device(DEV))
+    m = NoisyOR(H, D, dev(W), dev(pies), precision=to.float64)
+    st = EVOVariationalStates(N, H, S, to.float64, sel, mut, P, G, n_children=Cn, crossover=cross,
+                              bitflip_frequency=1.5 / H, seed=17, K_init=dev(K))
+    o = om.NoisyOR(H, D, W, pies)
+    Kw = K
+    for step in range(2):
+        nsubs = st.update(to.arange(N, device=DEV), dev(Y), m)
+        lpj = o.log_pseudo_joint(Y, Kw)
+        Cn_eff = P - 1 if cross else Cn
+        new_s, new_l = oevo.evolve_states(lpj, Kw, lambda s: o.log_pseudo_joint(Y, s), P, Cn_eff, G,
+                                          "batch_fitparents" if "fitparents" in sel else sel, st.config["mutation"],
+                                          float(m._tvo_sparsity().item()), 1.5 / H, np.arange(N), 17, step,
+                                          fit_corrected=(sel == "fitparents_fixed"))
+        Kw = Kw.copy()
+        nw = ost.update_states_for_batch(new_s, new_l, np.arange(N), Kw, lpj)
+        assert np.array_equal(st.K.unpack().cpu().numpy(), Kw), step
+        assert nsubs == nw
+        assert np.allclose(st.lpj.cpu().numpy(), lpj, rtol=1e-10, atol=1e-10)
+
+
+def test_noisyor_trainer_reference_flow():
+    # test/trainer_test.py:19-82: NoisyOR + RandomSampledVarStates, F increases over two em_steps; valid split
+    to.manual_seed(0)
+    np.random.seed(0)
+    tvo_b200._set_device(to.device(DEV))
+    N, D, S, H, S_new = 10, 16, 8, 8, 10
+    model = NoisyOR(H, D, precision=to.float32)
+    td = to.randint(2, size=(N, D), dtype=to.uint8, device=DEV)
+    vd = to.randint(2, size=(N, D), dtype=to.uint8, device=DEV)
+    tr = Trainer(model, TVODataLoader(td, batch_size=N), RandomSampledVarStates(N, H, S, to.float32, S_new, seed=1),
+                 TVODataLoader(vd, batch_size=N), RandomSampledVarStates(N, H, S, to.float32, S_new, seed=2))
+    d1 = tr.em_step()
+    d2 = tr.em_step()
+    assert set(d1) == {"train_F", "train_subs", "test_F", "test_subs"}
+    assert d1["train_F"] < d2["train_F"] and d1["test_F"] < d2["test_F"]
+    e1 = tr.e_step()
+    e2 = tr.e_step()
+    assert e1["test_F"] <= e2["test_F"] + 1e-6
+
+
+def test_noisyor_rollback_with_fullem():
+    # test/trainer_test.py:85-111
+    to.manual_seed(123)
+    tvo_b200._set_device(to.device(DEV))
+    eps = 1e-6
+    N, H, D = 10, 4, 32
+    data = (to.rand(N, D, device=DEV) < 0.8).byte()
+    dl = TVODataLoader(data, batch_size=N)
+    m1 = NoisyOR(H, D, precision=to.float64)
+    m2 = NoisyOR(H, D, precision=m1.precision, W_init=m1.theta["W"], pi_init=m1.theta["pies"])
+    st = FullEM(N, H, m1.precision)
+    F = [Trainer(m1, dl, st).em_step()["train_F"] for _ in range(1)]
+    tr = Trainer(m2, dl, st, rollback_if_F_decreases=["W"])
+    F = [tr.em_step()["train_F"] for _ in range(30)]
+    assert np.all(np.isfinite(F))
+    assert np.all(np.diff(F) >= -eps)

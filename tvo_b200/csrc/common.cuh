@@ -119,6 +119,7 @@ __device__ __forceinline__ uint64_t bernoulli_mask64(const Stream &st, uint32_t 
 // order-preserving map of an lpj value to u64 (larger lpj -> larger key; NaN above +inf, as torch.topk)
 __device__ __forceinline__ uint64_t sort_key(double x) {
   if (x != x) return ~0ull;
+  if (x == 0.0) x = 0.0;  // -0.0 and +0.0 compare equal in torch.topk: one key
   const uint64_t b = (uint64_t)__double_as_longlong(x);
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }

@@ -1,0 +1,409 @@
+// tvo_b200 — NoisyOR kernels (tvo/models/noisyor.py:67-162).
+//
+// lpj (noisyor.py:67-106):  P_d = clamp(prod_{h in s}(1 - W_dh), eps, 1-eps),
+//     lpj = sum_{h in s} log(pi_h/(1-pi_h)) + sum_d [ y_d log(1/P_d - 1) + log P_d ],
+//     all-zero state: 0 if y is all zero, else -1e30.
+// The product only runs over the SET bits of the packed state (1 - W*0 == 1 exactly), lanes over d.
+// M-step (noisyor.py:108-138): Btilde / Ctilde only receive contributions from active h, so the
+// (N,S,D,H) temporaries of the reference never exist; one CTA owns private [h][d] accumulators in
+// shared memory (threads over d, no atomics) and flushes them once at the end.
+#include "estep_fused.cuh"
+
+namespace tvo {
+
+constexpr double kNorEps = 1e-7;  // NoisyOR.eps (noisyor.py:17)
+
+struct NorThetaHdr {
+  double prior_sum;  // sum_h log(1 - pi_h)   (noisyor.py:162)
+  double pad[7];
+};
+__host__ __device__ inline int nor_dpad(int D) { return pad32(D); }
+template <typename T>
+__host__ __device__ inline size_t nor_w_off(int H) {
+  return sizeof(NorThetaHdr) + align16((size_t)H * sizeof(T));
+}
+template <typename T>
+__host__ __device__ inline size_t nor_ws_bytes(int H, int D) {
+  return nor_w_off<T>(H) + (size_t)H * nor_dpad(D) * sizeof(T);
+}
+template <typename T>
+struct NorTheta {
+  const NorThetaHdr *hdr;
+  const T *prior;  // H
+  const T *W1mT;   // H x Dpad: 1 - W_dh, padded with 1
+  int Dpad;
+};
+template <typename T>
+__host__ __device__ inline NorTheta<T> nor_theta_view(const void *ws, int H, int D) {
+  NorTheta<T> t;
+  const unsigned char *p = (const unsigned char *)ws;
+  t.hdr = (const NorThetaHdr *)p;
+  t.prior = (const T *)(p + sizeof(NorThetaHdr));
+  t.W1mT = (const T *)(p + nor_w_off<T>(H));
+  t.Dpad = nor_dpad(D);
+  return t;
+}
+
+template <typename T>
+__global__ void nor_prepare_kernel(const T *__restrict__ W, const T *__restrict__ pies, int H, int D, void *ws) {
+  unsigned char *p = (unsigned char *)ws;
+  NorThetaHdr *hdr = (NorThetaHdr *)p;
+  T *prior = (T *)(p + sizeof(NorThetaHdr));
+  T *W1mT = (T *)(p + nor_w_off<T>(H));
+  const int Dpad = nor_dpad(D);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)H * Dpad; i += (size_t)gridDim.x * blockDim.x) {
+    const int h = (int)(i / Dpad), d = (int)(i % Dpad);
+    W1mT[i] = d < D ? T(1) - W[(size_t)d * H + h] : T(1);
+  }
+  for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
+    const T pi = pies[h];
+    prior[h] = log(pi / (T(1) - pi));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    double s = 0.0;
+    for (int h = threadIdx.x; h < H; h += 32) s += (double)log(T(1) - pies[h]);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) hdr->prior_sum = s;
+  }
+}
+
+// lpj of ONE state, warp-cooperative (lanes over d).  ybits: bit i of lane l = y[l + 32 i] != 0.
+template <typename T>
+__device__ inline T nor_state_lpj(const uint64_t *st, int W64, const NorTheta<T> &th, const uint32_t *ybits, bool any_y,
+                                  int D, int lane) {
+  uint64_t any = 0;
+  for (int w = 0; w < W64; ++w) any |= st[w];
+  if (!any) return any_y ? T(-1e30) : T(0);  // noisyor.py:83-86,102
+  const T lo = (T)kNorEps, hi = T(1) - (T)kNorEps;
+  T acc = T(0), pr = T(0);
+  for (int c = 0, ci = 0; c < th.Dpad; c += 32, ++ci) {
+    T P = T(1);
+    for (int w = 0; w < W64; ++w) {
+      uint64_t word = st[w];
+      while (word) {
+        const int h = (w << 6) + __ffsll((long long)word) - 1;
+        word &= word - 1;
+        P *= __ldg(th.W1mT + (size_t)h * th.Dpad + c + lane);
+        if (c == 0) pr += __ldg(th.prior + h);
+      }
+    }
+    if (c + lane < D) {
+      P = P < lo ? lo : (P > hi ? hi : P);  // to.clamp (noisyor.py:89)
+      const bool yd = (ybits[ci >> 5] >> (ci & 31)) & 1u;
+      // y log(1/P - 1) + log P  ==  y ? log(1 - P) : log P   (noisyor.py:91-97)
+      acc += yd ? log(T(1) - P) : log(P);
+    }
+  }
+  return pr + warp_sum(acc);
+}
+
+// model adapter for the generic fused E-step kernel
+template <typename T>
+struct NorModel {
+  struct Params {
+    const uint8_t *Y;
+    int64_t ldY;
+    const void *ws;
+    int H, D;
+  };
+  static size_t smem_bytes(const Params &) { return 0; }
+  struct Ctx {
+    uint32_t ybits[2];  // D <= 2048
+    bool any_y;
+    __device__ void load(const Params &p, int64_t b, unsigned char *, int lane) {
+      const uint8_t *y = p.Y + b * p.ldY;
+      ybits[0] = ybits[1] = 0;
+      for (int d = lane, i = 0; d < p.D; d += 32, ++i)
+        if (y[d]) ybits[i >> 5] |= 1u << (i & 31);
+      any_y = __any_sync(FULL, (ybits[0] | ybits[1]) != 0);
+    }
+    __device__ void score(const Params &p, const uint64_t *states, int count, int W64, T *out, int lane) {
+      const NorTheta<T> th = nor_theta_view<T>(p.ws, p.H, p.D);
+      for (int s = 0; s < count; ++s) {
+        const T v = nor_state_lpj<T>(states + (size_t)s * W64, W64, th, ybits, any_y, p.D, lane);
+        if (lane == 0) out[s] = v;
+      }
+      __syncwarp();
+    }
+  };
+};
+
+// log_pseudo_joint for explicit state sets; work item = (datapoint, chunk of CH states)
+template <typename T>
+__global__ void __launch_bounds__(256)
+nor_lpj_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const uint64_t *__restrict__ K, int64_t k_stride_n,
+               const int64_t *__restrict__ idx, const void *ws, T *__restrict__ lpj_out, int64_t lpj_stride_n, int64_t B,
+               int S, int H, int D, int CH) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int W64 = n_words(H);
+  const int nchunk = (S + CH - 1) / CH;
+  typename NorModel<T>::Params p{Y, ldY, ws, H, D};
+  typename NorModel<T>::Ctx ctx;
+  for (int64_t task = (int64_t)blockIdx.x * wpb + wib; task < B * nchunk; task += (int64_t)gridDim.x * wpb) {
+    const int64_t b = task / nchunk;
+    const int c = (int)(task % nchunk);
+    const int64_t row = idx ? idx[b] : b;
+    ctx.load(p, b, nullptr, lane);
+    const int s0 = c * CH, n = min(S, s0 + CH) - s0;
+    ctx.score(p, K + row * k_stride_n + (size_t)s0 * W64, n, W64, lpj_out + row * lpj_stride_n + s0, lane);
+  }
+}
+
+// F_out += sum_b logsumexp_s lpj[b, s]   (model_protocols.py:191-193; the model constant is added by the caller)
+template <typename T>
+__global__ void __launch_bounds__(256)
+logsumexp_sum_kernel(const T *__restrict__ lpj, int64_t stride_n, const int64_t *__restrict__ idx, int64_t B, int S,
+                     double *out) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  double acc = 0.0;
+  for (int64_t b = (int64_t)blockIdx.x * wpb + wib; b < B; b += (int64_t)gridDim.x * wpb) {
+    const T *l = lpj + (idx ? idx[b] : b) * stride_n;
+    double mx = -INFINITY;
+    for (int s = lane; s < S; s += 32) mx = fmax(mx, (double)l[s]);
+    mx = warp_max(mx);
+    if (!(mx > -INFINITY && mx < INFINITY)) mx = mx != mx ? mx : 0.0;
+    double se = 0.0;
+    for (int s = lane; s < S; s += 32) se += exp((double)l[s] - mx);
+    acc += mx + log(warp_sum(se));
+  }
+  __shared__ double part[8];
+  if (lane == 0) part[wib] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < wpb; ++w) s += part[w];
+    atomicAdd(out, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------ M-step
+// stats: [BtT (H*D) | CtT (H*D) | new_pi (H) | N | F]; the CTA accumulates the h-tile [h0, h0+Ht).
+template <typename T>
+__global__ void __launch_bounds__(256)
+nor_mstep_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx,
+                 const uint64_t *__restrict__ K, int64_t k_stride_n, const T *__restrict__ lpj, int64_t lpj_stride_n,
+                 const void *ws, double *__restrict__ stats, int64_t B, int S, int H, int D, int Ht) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const NorTheta<T> th = nor_theta_view<T>(ws, H, D);
+  const int W64 = n_words(H), Dpad = th.Dpad;
+  const int h0 = blockIdx.y * Ht, h1 = min(H, h0 + Ht);
+  double *Bt = (double *)smem_raw;              // Ht x Dpad
+  double *Ct = Bt + (size_t)Ht * Dpad;          // Ht x Dpad
+  double *pi_acc = Ct + (size_t)Ht * Dpad;      // Ht
+  double *q = pi_acc + Ht;                      // S
+  uint64_t *Ksm = (uint64_t *)(q + S);          // S x W64
+  __shared__ double red[2];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  for (int i = tid; i < 2 * Ht * Dpad + Ht; i += nt) Bt[i] = 0.0;
+  double accF = 0.0, accN = 0.0;
+  const T eps = (T)kNorEps;
+  __syncthreads();
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const int64_t row = idx ? idx[b] : b;
+    const T *l = lpj + row * lpj_stride_n;
+    for (int t = tid; t < S * W64; t += nt) Ksm[t] = K[row * k_stride_n + t];
+    if (tid < 32) {  // softmax weights by warp 0 (lpj2pjc, _utils.py:182-191)
+      double mx = -INFINITY;
+      for (int s = lane; s < S; s += 32) mx = fmax(mx, (double)l[s]);
+      mx = warp_max(mx);
+      double se = 0.0;
+      for (int s = lane; s < S; s += 32) {
+        const double e = exp((double)l[s] - mx);
+        q[s] = e;
+        se += e;
+      }
+      se = warp_sum(se);
+      if (lane == 0) {
+        red[0] = se;
+        red[1] = mx + log(se);
+      }
+    }
+    __syncthreads();
+    const double se = red[0];
+    if (tid == 0 && blockIdx.y == 0) {
+      accF += red[1] + th.hdr->prior_sum;
+      accN += 1.0;
+    }
+    // threads over d: Btilde, Ctilde (noisyor.py:121-132)
+    for (int d = tid; d < D; d += nt) {
+      const T ym1 = (T)Y[b * ldY + d] - T(1);
+      for (int s = 0; s < S; ++s) {
+        const double qs = q[s] / se;
+        const uint64_t *st = Ksm + (size_t)s * W64;
+        T Q = T(1);
+        for (int w = 0; w < W64; ++w) {
+          uint64_t word = st[w];
+          while (word) {
+            const int h = (w << 6) + __ffsll((long long)word) - 1;
+            word &= word - 1;
+            Q *= __ldg(th.W1mT + (size_t)h * Dpad + d);
+          }
+        }
+        for (int w = 0; w < W64; ++w) {
+          uint64_t word = st[w];
+          while (word) {
+            const int h = (w << 6) + __ffsll((long long)word) - 1;
+            word &= word - 1;
+            if (h < h0 || h >= h1) continue;
+            const T Ws = __ldg(th.W1mT + (size_t)h * Dpad + d);
+            const T Bv = T(1) / (Ws * (T(1) - Q) + eps);  // K / (Ws (1 - prod) + eps)
+            const T Cv = Bv * Q / Ws;
+            Bt[(size_t)(h - h0) * Dpad + d] += qs * (double)(Bv * ym1);
+            Ct[(size_t)(h - h0) * Dpad + d] += qs * (double)Cv;
+          }
+        }
+      }
+    }
+    // threads over h: new_pi += <s_h>  (noisyor.py:117)
+    for (int h = h0 + tid; h < h1; h += nt) {
+      double e = 0.0;
+      for (int s = 0; s < S; ++s)
+        if ((Ksm[(size_t)s * W64 + (h >> 6)] >> (h & 63)) & 1ull) e += q[s] / se;
+      pi_acc[h - h0] += e;
+    }
+    __syncthreads();
+  }
+  const size_t HD = (size_t)H * D;
+  for (int i = tid; i < (h1 - h0) * D; i += nt) {
+    const int hh = i / D, d = i % D;
+    const double bv = Bt[(size_t)hh * Dpad + d], cv = Ct[(size_t)hh * Dpad + d];
+    if (bv != 0.0) atomicAdd(stats + (size_t)(h0 + hh) * D + d, bv);
+    if (cv != 0.0) atomicAdd(stats + HD + (size_t)(h0 + hh) * D + d, cv);
+  }
+  for (int h = h0 + tid; h < h1; h += nt)
+    if (pi_acc[h - h0] != 0.0) atomicAdd(stats + 2 * HD + h, pi_acc[h - h0]);
+  if (tid == 0 && accN != 0.0) {
+    atomicAdd(stats + 2 * HD + H, accN);
+    atomicAdd(stats + 2 * HD + H + 1, accF);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+template <typename T>
+int nor_prepare(const T *W, const T *pies, int H, int D, void *ws, void *stream) {
+  TVO_REQUIRE(W && pies && ws, "noisyor_prepare: null pointer");
+  TVO_REQUIRE(H > 0 && D > 0 && D <= 2048, "noisyor_prepare: need H > 0 and 0 < D <= 2048 (got H=%d D=%d)", H, D);
+  const size_t total = (size_t)H * nor_dpad(D);
+  nor_prepare_kernel<T><<<(int)max((size_t)1, min((size_t)4 * sm_count(), (total + 255) / 256)), 256, 0,
+                          (cudaStream_t)stream>>>(W, pies, H, D, ws);
+  TVO_AFTER_LAUNCH("noisyor_prepare");
+  return TVO_OK;
+}
+
+template <typename T>
+int nor_lpj(const uint8_t *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx, const void *ws,
+            T *lpj_out, int64_t lpj_stride_n, int64_t B, int S, int H, int D, void *stream) {
+  TVO_REQUIRE(Y && K && ws && lpj_out, "noisyor_lpj: null pointer");
+  TVO_REQUIRE(B >= 0 && S > 0 && H > 0 && D > 0 && D <= 2048, "noisyor_lpj: bad sizes");
+  if (B == 0) return TVO_OK;
+  const int CH = S <= 64 ? S : 64;
+  const int64_t ntask = B * ((S + CH - 1) / CH);
+  const int grid = (int)max((int64_t)1, min((ntask + 7) / 8, (int64_t)sm_count() * 8));
+  nor_lpj_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(Y, ldY, K, k_stride_n, idx, ws, lpj_out, lpj_stride_n, B, S, H,
+                                                            D, CH);
+  TVO_AFTER_LAUNCH("noisyor_lpj");
+  return TVO_OK;
+}
+
+template <typename T>
+int nor_estep(const uint8_t *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj, const void *ws,
+              const tvo_evo_config *cfg, const double *sparsity, int64_t B, int S, int H, int D, int64_t *nsubs,
+              void *stream) {
+  TVO_REQUIRE(Y && K && lpj && ws && cfg && nsubs, "estep_evo_noisyor: null pointer");
+  TVO_REQUIRE(B >= 0 && D > 0 && D <= 2048, "estep_evo_noisyor: need 0 < D <= 2048");
+  typename NorModel<T>::Params mp{Y, ldY, ws, H, D};
+  return launch_estep_evo_fused<T, NorModel<T>>(mp, idx, 0, K, lpj, cfg, sparsity, B, S, H, nsubs, (cudaStream_t)stream,
+                                                "estep_evo_noisyor");
+}
+
+template <typename T>
+int nor_mstep(const uint8_t *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n, const T *lpj,
+              int64_t lpj_stride_n, const void *ws, double *stats, int64_t B, int S, int H, int D, void *stream) {
+  TVO_REQUIRE(Y && K && lpj && ws && stats, "noisyor_mstep: null pointer");
+  TVO_REQUIRE(B >= 0 && S > 0 && H > 0 && D > 0, "noisyor_mstep: bad sizes");
+  if (B == 0) return TVO_OK;
+  const int Dpad = nor_dpad(D), W64 = n_words(H);
+  const size_t fixed = (size_t)S * 8 + (size_t)S * W64 * 8 + 64;
+  const size_t budget = 200 * 1024;
+  TVO_REQUIRE(fixed + (size_t)(2 * Dpad + 1) * 8 <= budget, "noisyor_mstep: S/D too large for shared memory");
+  int Ht = (int)min((size_t)H, (budget - fixed) / ((size_t)(2 * Dpad + 1) * 8));
+  const int ntile = (H + Ht - 1) / Ht;
+  Ht = (H + ntile - 1) / ntile;
+  const size_t smem = (size_t)(2 * Ht * Dpad + Ht) * 8 + fixed;
+  auto kern = nor_mstep_kernel<T>;
+  TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = min(256, max(64, Dpad));
+  int occ = 1;
+  TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+  const int gx = (int)max((int64_t)1, min(B, (int64_t)sm_count() * max(occ, 1)));
+  kern<<<dim3(gx, ntile), threads, smem, (cudaStream_t)stream>>>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, ws, stats, B,
+                                                                 S, H, D, Ht);
+  TVO_AFTER_LAUNCH("noisyor_mstep");
+  return TVO_OK;
+}
+
+template <typename T>
+int logsumexp_sum(const T *lpj, int64_t stride_n, const int64_t *idx, int64_t B, int S, double *out, void *stream) {
+  TVO_REQUIRE(lpj && out, "logsumexp_sum: null pointer");
+  TVO_REQUIRE(B >= 0 && S > 0, "logsumexp_sum: bad sizes");
+  if (B == 0) return TVO_OK;
+  const int grid = (int)max((int64_t)1, min((B + 7) / 8, (int64_t)sm_count() * 8));
+  logsumexp_sum_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(lpj, stride_n, idx, B, S, out);
+  TVO_AFTER_LAUNCH("logsumexp_sum");
+  return TVO_OK;
+}
+
+}  // namespace tvo
+
+using namespace tvo;
+
+extern "C" {
+int64_t tvo_noisyor_theta_ws_bytes(int32_t H, int32_t D, int32_t is_f64) {
+  return (int64_t)(is_f64 ? nor_ws_bytes<double>(H, D) : nor_ws_bytes<float>(H, D));
+}
+int64_t tvo_noisyor_stats_len(int32_t H, int32_t D) { return 2 * (int64_t)H * D + H + 2; }
+int tvo_noisyor_prepare_f64(const double *W, const double *pies, int32_t H, int32_t D, void *ws, void *stream) {
+  return nor_prepare<double>(W, pies, H, D, ws, stream);
+}
+int tvo_noisyor_prepare_f32(const float *W, const float *pies, int32_t H, int32_t D, void *ws, void *stream) {
+  return nor_prepare<float>(W, pies, H, D, ws, stream);
+}
+int tvo_noisyor_lpj_f64(const uint8_t *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx,
+                        const void *ws, double *lpj_out, int64_t lpj_stride_n, int64_t B, int32_t S, int32_t H, int32_t D,
+                        void *stream) {
+  return nor_lpj<double>(Y, ldY, K, k_stride_n, idx, ws, lpj_out, lpj_stride_n, B, S, H, D, stream);
+}
+int tvo_noisyor_lpj_f32(const uint8_t *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx,
+                        const void *ws, float *lpj_out, int64_t lpj_stride_n, int64_t B, int32_t S, int32_t H, int32_t D,
+                        void *stream) {
+  return nor_lpj<float>(Y, ldY, K, k_stride_n, idx, ws, lpj_out, lpj_stride_n, B, S, H, D, stream);
+}
+int tvo_estep_evo_noisyor_f64(const uint8_t *Y, int64_t ldY, const int64_t *idx, uint64_t *K, double *lpj, const void *ws,
+                              const tvo_evo_config *cfg, const double *sparsity, int64_t B, int32_t S, int32_t H,
+                              int32_t D, int64_t *nsubs, void *stream) {
+  return nor_estep<double>(Y, ldY, idx, K, lpj, ws, cfg, sparsity, B, S, H, D, nsubs, stream);
+}
+int tvo_estep_evo_noisyor_f32(const uint8_t *Y, int64_t ldY, const int64_t *idx, uint64_t *K, float *lpj, const void *ws,
+                              const tvo_evo_config *cfg, const double *sparsity, int64_t B, int32_t S, int32_t H,
+                              int32_t D, int64_t *nsubs, void *stream) {
+  return nor_estep<float>(Y, ldY, idx, K, lpj, ws, cfg, sparsity, B, S, H, D, nsubs, stream);
+}
+int tvo_noisyor_mstep_f64(const uint8_t *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                          const double *lpj, int64_t lpj_stride_n, const void *ws, double *stats, int64_t B, int32_t S,
+                          int32_t H, int32_t D, void *stream) {
+  return nor_mstep<double>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, ws, stats, B, S, H, D, stream);
+}
+int tvo_noisyor_mstep_f32(const uint8_t *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                          const float *lpj, int64_t lpj_stride_n, const void *ws, double *stats, int64_t B, int32_t S,
+                          int32_t H, int32_t D, void *stream) {
+  return nor_mstep<float>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, ws, stats, B, S, H, D, stream);
+}
+int tvo_logsumexp_sum_f64(const double *lpj, int64_t stride_n, const int64_t *idx, int64_t B, int32_t S, double *out,
+                          void *stream) {
+  return logsumexp_sum<double>(lpj, stride_n, idx, B, S, out, stream);
+}
+int tvo_logsumexp_sum_f32(const float *lpj, int64_t stride_n, const int64_t *idx, int64_t B, int32_t S, double *out,
+                          void *stream) {
+  return logsumexp_sum<float>(lpj, stride_n, idx, B, S, out, stream);
+}
+}

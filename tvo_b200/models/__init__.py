@@ -1,3 +1,4 @@
 from .bsc import BSC
+from .noisyor import NoisyOR
 
-__all__ = ["BSC"]
+__all__ = ["BSC", "NoisyOR"]
