@@ -244,6 +244,45 @@ int tvo_logsumexp_sum_f64(const double *lpj, int64_t stride_n, const int64_t *id
 int tvo_logsumexp_sum_f32(const float *lpj, int64_t stride_n, const int64_t *idx, int64_t B, int32_t S, double *out,
                           void *stream);
 
+/* ---- SSSC (tvo/models/sssc.py).  theta: W (D,H), sigma2 (1), mus (H), Psi (H,H), pies (H).
+ *      lpj: the reformulated form (sssc.py:266-337) evaluated per state by Cholesky factorisations of
+ *      the a x a active sub-blocks (a = popcount; at most 32, fewer if shared memory is short) — see
+ *      csrc/sssc.cu.  States with more active units get lpj = finfo.min and set *overflow (device int)
+ *      so that the host can fail loudly.  `scratch` (tvo_sssc_scratch_bytes) holds a = W^T y (and, for
+ *      the M-step, <kappa>_q and <s>_q) for one chunk of datapoints; GEMMs on it are cuBLAS.
+ *      M-step (sssc.py:366-452) stats layout (fp64, INCREMENTED):
+ *      [y_szT^T (H*D) | sz_szT (H*H) | szszT (H*H) | ssT (H*H, upper triangle) | ssz (H*H) | s (H) | sz (H)
+ *       | diag_yyT (D) | N | F]. ---- */
+int64_t tvo_sssc_theta_ws_bytes(int32_t H, int32_t D, int32_t is_f64);
+int64_t tvo_sssc_stats_len(int32_t H, int32_t D);
+int64_t tvo_sssc_scratch_bytes(int64_t B, int32_t H, int32_t D, int32_t is_f64);
+int tvo_sssc_prepare_f64(const double *W, const double *sigma2, const double *mus, const double *Psi, const double *pies,
+                         int32_t H, int32_t D, void *theta_ws, void *stream);
+int tvo_sssc_prepare_f32(const float *W, const float *sigma2, const float *mus, const float *Psi, const float *pies,
+                         int32_t H, int32_t D, void *theta_ws, void *stream);
+int tvo_sssc_lpj_f64(const double *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx,
+                     const void *theta_ws, double *lpj_out, int64_t lpj_stride_n, void *scratch, int64_t scratch_bytes,
+                     int32_t *overflow, int64_t B, int32_t S, int32_t H, int32_t D, void *stream);
+int tvo_sssc_lpj_f32(const float *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx,
+                     const void *theta_ws, float *lpj_out, int64_t lpj_stride_n, void *scratch, int64_t scratch_bytes,
+                     int32_t *overflow, int64_t B, int32_t S, int32_t H, int32_t D, void *stream);
+int tvo_estep_evo_sssc_f64(const double *Y, int64_t ldY, const int64_t *idx, uint64_t *K, double *lpj,
+                           const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity, void *scratch,
+                           int64_t scratch_bytes, int32_t *overflow, int64_t B, int32_t S, int32_t H, int32_t D,
+                           int64_t *nsubs, void *stream);
+int tvo_estep_evo_sssc_f32(const float *Y, int64_t ldY, const int64_t *idx, uint64_t *K, float *lpj,
+                           const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity, void *scratch,
+                           int64_t scratch_bytes, int32_t *overflow, int64_t B, int32_t S, int32_t H, int32_t D,
+                           int64_t *nsubs, void *stream);
+int tvo_sssc_mstep_f64(const double *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                       const double *lpj, int64_t lpj_stride_n, const void *theta_ws, double *stats, void *scratch,
+                       int64_t scratch_bytes, int32_t *overflow, int64_t B, int32_t S, int32_t H, int32_t D,
+                       int32_t with_ssz, void *stream);
+int tvo_sssc_mstep_f32(const float *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                       const float *lpj, int64_t lpj_stride_n, const void *theta_ws, double *stats, void *scratch,
+                       int64_t scratch_bytes, int32_t *overflow, int64_t B, int32_t S, int32_t H, int32_t D,
+                       int32_t with_ssz, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

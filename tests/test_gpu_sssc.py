@@ -1,0 +1,159 @@
+"""GPU parity tests of the SSSC path (through the C ABI) against the oracle and the reference fixtures."""
+import math
+
+import numpy as np
+import pytest
+import torch as to
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+if to.cuda.is_available():
+    import tvo_b200
+    from tvo_b200.models import SSSC
+    from tvo_b200.trainer import Trainer
+    from tvo_b200.utils.data import TVODataLoader
+    from tvo_b200.variational import EVOVariationalStates, FullEM
+
+from oracle import evo as oevo
+from oracle import models as om
+from oracle import states as ost
+
+DEV = "cuda:0"
+
+
+def dev(a, dtype=None):
+    t = to.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def make(g, dtype=to.float64, reform=False):
+    D, H = g["W"].shape
+    return SSSC(H, D, dev(g["W"]), dev(g["sigma2"]), dev(g["mus"]), dev(g["Psi"]), dev(g["pies"]),
+                reformulated_psi_update=reform, precision=dtype)
+
+
+@pytest.mark.parametrize("tag,reform", [("f64", False), ("f64_psi", True)])
+def test_sssc_golden(tag, reform):
+    g = load_golden(f"sssc_{tag}.npz")
+    D, H = g["W"].shape
+    tvo_b200._set_device(to.device(DEV))
+    m = make(g, reform=reform)
+    Y, K = dev(g["Y"]), dev(g["K"])
+    lpj = m.log_pseudo_joint(Y, K)
+    assert np.allclose(lpj.cpu().numpy(), g["lpj"], rtol=1e-10, atol=1e-10)
+    assert np.allclose(m.log_joint(Y, K, lpj).cpu().numpy(), g["log_joint"], rtol=1e-10, atol=1e-10)
+    N, S = g["K"].shape[:2]
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "randflip", 2, 1, 1, K_init=K)
+    st.lpj[:] = dev(g["lpj"])
+    assert math.isclose(m.free_energy(to.arange(N), Y, st), float(g["F"]), rel_tol=1e-10)
+    m.update_param_batch(to.arange(N), Y, st)
+    names = {"sum_y_szT": "_my_sum_y_szT", "sum_xpt_sz_xpt_szT": "_my_sum_xpt_sz_xpt_szT", "sum_xpt_szszT": "_my_sum_xpt_szszT",
+             "sum_xpt_s": "_my_sum_xpt_s", "sum_xpt_sz": "_my_sum_xpt_sz", "sum_xpt_ssT": "_my_sum_xpt_ssT",
+             "sum_diag_yyT": "_my_sum_diag_yyT"}
+    if reform:
+        names["sum_xpt_ssz"] = "_my_sum_xpt_ssz"
+    for gname, attr in names.items():
+        assert np.allclose(getattr(m, attr).cpu().numpy(), g[gname], rtol=1e-9, atol=1e-9), gname
+    assert math.isclose(float(m._stats[-1]), float(g["F"]), rel_tol=1e-10)
+    N2 = g["K2"].shape[0]
+    st2 = EVOVariationalStates(N2, H, S, to.float64, "randparents", "randflip", 2, 1, 1, K_init=dev(g["K2"]))
+    st2.lpj[:] = dev(g["lpj2"])
+    m.update_param_batch(to.arange(N2), dev(g["Y2"]), st2)
+    m.update_param_epoch()
+    for k in ("W", "pies", "mus", "Psi", "sigma2"):
+        assert np.allclose(m.theta[k].cpu().numpy(), g[k + "_new"], rtol=1e-7, atol=1e-7), k
+
+
+def test_sssc_appendix_a():
+    W = np.array([[1.0, -0.5, 0.25, 2.0], [0.5, 1.5, -1.0, 0.0], [-0.25, 0.75, 0.5, -1.5]])
+    Y = np.array([[1.0, 0.5, -0.25], [0.0, 2.0, 1.25]])
+    K = np.array([[[0, 0, 0, 0], [1, 0, 0, 0], [1, 0, 1, 1]], [[0, 1, 0, 0], [0, 1, 1, 0], [1, 1, 1, 1]]], np.uint8)
+    Psi = np.array([[1, 0.25, 0, 0], [0.25, 2, 0, 0.5], [0, 0, 0.5, 0], [0, 0.5, 0, 1.5]], float)
+    tvo_b200._set_device(to.device(DEV))
+    m = SSSC(4, 3, dev(W), dev(np.array([0.5])), dev(np.array([0.5, -0.25, 1.0, 0.0])), dev(Psi),
+             dev(np.array([0.125, 0.25, 0.5, 0.375])), precision=to.float64)
+    lpj = m.log_pseudo_joint(dev(Y), dev(K)).cpu().numpy()
+    want = np.array([[-1.3125, -2.680354534587943, -5.344007104422202], [-3.435717196959697, -4.09862850737411, -7.485431308356349]])
+    assert np.allclose(lpj, want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("dtype,tol", [(to.float64, 1e-9), (to.float32, 2e-4)])
+def test_sssc_lpj_random_nan_and_zero_states(dtype, tol):
+    rng = np.random.default_rng(4)
+    N, D, H, S = 12, 20, 40, 9
+    npd = np.float64 if dtype == to.float64 else np.float32
+    W = rng.standard_normal((D, H))
+    A = rng.standard_normal((H, H)) * 0.2
+    Psi = A @ A.T + np.eye(H)
+    mus = rng.standard_normal(H) * 0.5
+    pies = rng.uniform(0.005, 0.3, H)  # includes values below the 0.01 clamp
+    Y = rng.standard_normal((N, D)) * 2
+    Y[3, 2] = np.nan
+    Y[7, 5:9] = np.nan
+    K = (rng.random((N, S, H)) < 0.1).astype(np.uint8)
+    K[:, 0] = 0
+    tvo_b200._set_device(to.device(DEV))
+    m = SSSC(H, D, dev(W), dev(np.array([0.3])), dev(mus), dev(Psi), dev(pies), precision=dtype)
+    o = om.SSSC(H, D, W.astype(npd), np.array([0.3], npd), mus.astype(npd), Psi.astype(npd), pies.astype(npd), precision=npd)
+    want = o.log_pseudo_joint(Y.astype(npd), K)
+    got = m.log_pseudo_joint(dev(Y, dtype), dev(K)).cpu().numpy()
+    assert np.allclose(got, want, rtol=tol, atol=tol * np.abs(want).max())
+    lj = m.log_joint(dev(Y, dtype), dev(K)).cpu().numpy()
+    assert np.allclose(lj, o.log_joint(Y.astype(npd), K, want), rtol=tol, atol=tol * np.abs(want).max())
+
+
+def test_sssc_estep_bit_exact_and_training():
+    rng = np.random.default_rng(8)
+    np.random.seed(8)
+    N, D, H, S, P, Cn, G = 40, 16, 24, 8, 3, 2, 2
+    Wg = rng.standard_normal((D, H))
+    Psi = np.eye(H)
+    mus = np.zeros(H) + 1.0
+    pies = np.full(H, 3.0 / H)
+    s = rng.random((N, H)) < pies
+    Y = (s * (mus + rng.standard_normal((N, H)))) @ Wg.T + 0.3 * rng.standard_normal((N, D))
+    K = np.zeros((N, S, H), np.uint8)
+    for n in range(N):
+        seen = {}
+        while len(seen) < S:
+            v = (rng.random(H) < 3.0 / H).astype(np.uint8)
+            seen.setdefault(v.tobytes(), v)
+        K[n] = list(seen.values())
+    tvo_b200._set_device(to.device(DEV))
+    m = SSSC(H, D, dev(Wg + 0.3 * rng.standard_normal((D, H))), dev(np.array([0.5])), dev(mus), dev(Psi), dev(pies),
+             precision=to.float64)
+    o = om.SSSC(H, D, m.theta["W"].cpu().numpy(), [0.5], mus, Psi, pies)
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", P, G, Cn, bitflip_frequency=1.0 / H, seed=21,
+                              K_init=dev(K))
+    nsubs = st.update(to.arange(N, device=DEV), dev(Y), m)
+    lpj = o.log_pseudo_joint(Y, K)
+    new_s, new_l = oevo.evolve_states(lpj, K, lambda x: o.log_pseudo_joint(Y, x), P, Cn, G, "randparents", "sparseflip",
+                                      float(m._tvo_sparsity().item()), 1.0 / H, np.arange(N), 21, 0)
+    Kw = K.copy()
+    nw = ost.update_states_for_batch(new_s, new_l, np.arange(N), Kw, lpj)
+    assert np.array_equal(st.K.unpack().cpu().numpy(), Kw)
+    assert nsubs == nw
+    assert np.allclose(st.lpj.cpu().numpy(), lpj, rtol=1e-9, atol=1e-9)
+    # a few EM iterations through the Trainer: F must increase (test/sssc_test.py:146-159)
+    tr = Trainer(m, TVODataLoader(dev(Y), batch_size=16), st)
+    Fs = [tr.em_step()["train_F"] for _ in range(4)]
+    assert np.all(np.isfinite(Fs)) and Fs[-1] > Fs[0]
+
+
+def test_sssc_fullem_train_increases_F():
+    # test/sssc_test.py:146-159 (FullEM, default-initialised model)
+    to.manual_seed(0)
+    tvo_b200._set_device(to.device(DEV))
+    N, D, H = 5, 4, 2
+    for prec in (to.float32, to.float64):
+        m = SSSC(H=H, D=D, precision=prec)
+        data = to.rand((N, D), dtype=prec, device=DEV)
+        st = FullEM(N, H, prec)
+        st.lpj[:] = m.log_pseudo_joint(data, st.K)
+        F0 = m.free_energy(to.arange(N), data, st)
+        m.update_param_batch(to.arange(N), data, st)
+        m.update_param_epoch()
+        st.lpj[:] = m.log_pseudo_joint(data, st.K)
+        assert m.free_energy(to.arange(N), data, st) > F0

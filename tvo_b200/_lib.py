@@ -53,6 +53,9 @@ _PROTOS = {
     "tvo_random_states": [_P, _P, _I64, _I32, _I32, _F64, _U64, _U32, _U32, _P],
     "tvo_noisyor_theta_ws_bytes": [_I32, _I32, _I32],
     "tvo_noisyor_stats_len": [_I32, _I32],
+    "tvo_sssc_theta_ws_bytes": [_I32, _I32, _I32],
+    "tvo_sssc_stats_len": [_I32, _I32],
+    "tvo_sssc_scratch_bytes": [_I64, _I32, _I32, _I32],
 }
 for _sfx in ("f64", "f32"):
     _PROTOS.update({
@@ -74,6 +77,12 @@ for _sfx in ("f64", "f32"):
                                           _P],
         f"tvo_noisyor_mstep_{_sfx}": [_P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _P],
         f"tvo_logsumexp_sum_{_sfx}": [_P, _I64, _P, _I64, _I32, _P, _P],
+        f"tvo_sssc_prepare_{_sfx}": [_P, _P, _P, _P, _P, _I32, _I32, _P, _P],
+        f"tvo_sssc_lpj_{_sfx}": [_P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P],
+        f"tvo_estep_evo_sssc_{_sfx}": [_P, _I64, _P, _P, _P, _P, C.POINTER(EvoConfig), _P, _P, _I64, _P, _I64, _I32, _I32,
+                                       _I32, _P, _P],
+        f"tvo_sssc_mstep_{_sfx}": [_P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32,
+                                   _P],
         f"tvo_bsc_mstep_{_sfx}": [_P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P],
     })
 _RESTYPES = {
@@ -86,6 +95,9 @@ _RESTYPES = {
     "tvo_bsc_mstep_scratch_bytes": _I64,
     "tvo_noisyor_theta_ws_bytes": _I64,
     "tvo_noisyor_stats_len": _I64,
+    "tvo_sssc_theta_ws_bytes": _I64,
+    "tvo_sssc_stats_len": _I64,
+    "tvo_sssc_scratch_bytes": _I64,
 }
 
 _lib = None

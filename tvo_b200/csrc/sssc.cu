@@ -1,0 +1,706 @@
+// tvo_b200 — Spike-and-Slab Sparse Coding kernels (tvo/models/sssc.py:175-540).
+//
+// For a state s with active set A (|A| = a) the reference (sssc.py:216-337) forms
+//   Lambda^-1 = W_A^T W_A / s2 + Psi_A^-1,   C_s^-1 = I/s2 - W_A Lambda W_A^T / s2^2,
+//   lpj = sum_A log(pi/(1-pi)) - 1/2 [ logdet(Lambda^-1) + logdet(Psi_A) + r^T C_s^-1 r ],  r = y - W_A mu_A
+// with explicit a x a inverses in a python loop per (n, s).  Here, per state and warp-cooperatively in
+// shared memory, with G = W^T W, a = W^T y (one GEMM per chunk) and Psi_A = R R^T (Cholesky):
+//   M = I + R^T G_AA R / s2 = C C^T            (SPD; det M = det(Lambda^-1) det(Psi_A))
+//   b = a_A - G_AA mu_A = W_A^T r,  ||r||^2 = yy - 2 mu_A.a_A + mu_A^T G_AA mu_A
+//   r^T C_s^-1 r = ||r||^2/s2 - ||C^-1 R^T b||^2 / s2^2,   logdet terms = 2 sum log C_ii
+//   Lambda = U U^T with U = R C^-T,  kappa = mu_A + Lambda b / s2              (M-step, sssc.py:418-423)
+// No explicit inverse is formed.  Rows of y with NaN take a slow path with G_AA, a_A restricted to the
+// observed dimensions (sssc.py:283,298).  All arithmetic is fp64; lpj is stored in the model precision.
+#include <cublas_v2.h>
+
+#include "estep_fused.cuh"
+
+namespace tvo {
+
+struct SsscThetaHdr {
+  double sigma2;
+  double prior_sum;  // sum_h log(1 - clamp(pi_h))        (sssc.py:356-359)
+  double log_2pi_sigma2;  // log(2 pi) + log(sigma2)      (sssc.py:360)
+  double pad[5];
+};
+__host__ __device__ inline int sssc_dpad(int D) { return pad32(D); }
+// workspace: hdr | prior (H dbl) | mus (H dbl) | Psi (H*H dbl) | G (H*H dbl) | Wt (H*Dpad, T)
+__host__ __device__ inline size_t sssc_off_prior() { return sizeof(SsscThetaHdr); }
+__host__ __device__ inline size_t sssc_off_mus(int H) { return sssc_off_prior() + (size_t)H * 8; }
+__host__ __device__ inline size_t sssc_off_psi(int H) { return sssc_off_mus(H) + (size_t)H * 8; }
+__host__ __device__ inline size_t sssc_off_g(int H) { return sssc_off_psi(H) + (size_t)H * H * 8; }
+__host__ __device__ inline size_t sssc_off_wt(int H) { return align16(sssc_off_g(H) + (size_t)H * H * 8); }
+template <typename T>
+__host__ __device__ inline size_t sssc_ws_bytes(int H, int D) {
+  return sssc_off_wt(H) + (size_t)H * sssc_dpad(D) * sizeof(T);
+}
+template <typename T>
+struct SsscTheta {
+  const SsscThetaHdr *hdr;
+  const double *prior, *mus, *Psi, *G;
+  const T *Wt;
+  int Dpad;
+};
+template <typename T>
+__host__ __device__ inline SsscTheta<T> sssc_theta_view(const void *ws, int H, int D) {
+  const unsigned char *p = (const unsigned char *)ws;
+  SsscTheta<T> t;
+  t.hdr = (const SsscThetaHdr *)p;
+  t.prior = (const double *)(p + sssc_off_prior());
+  t.mus = (const double *)(p + sssc_off_mus(H));
+  t.Psi = (const double *)(p + sssc_off_psi(H));
+  t.G = (const double *)(p + sssc_off_g(H));
+  t.Wt = (const T *)(p + sssc_off_wt(H));
+  t.Dpad = sssc_dpad(D);
+  return t;
+}
+
+template <typename T>
+__global__ void sssc_prepare_kernel(const T *__restrict__ W, const T *__restrict__ sigma2, const T *__restrict__ mus,
+                                    const T *__restrict__ Psi, const T *__restrict__ pies, int H, int D, void *ws) {
+  unsigned char *p = (unsigned char *)ws;
+  SsscThetaHdr *hdr = (SsscThetaHdr *)p;
+  double *prior = (double *)(p + sssc_off_prior());
+  double *mu = (double *)(p + sssc_off_mus(H));
+  double *Ps = (double *)(p + sssc_off_psi(H));
+  double *G = (double *)(p + sssc_off_g(H));
+  T *Wt = (T *)(p + sssc_off_wt(H));
+  const int Dpad = sssc_dpad(D);
+  const size_t gt = (size_t)gridDim.x * blockDim.x, g0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = g0; i < (size_t)H * Dpad; i += gt) {
+    const int h = (int)(i / Dpad), d = (int)(i % Dpad);
+    Wt[i] = d < D ? W[(size_t)d * H + h] : T(0);
+  }
+  for (size_t i = g0; i < (size_t)H * H; i += gt) {
+    Ps[i] = (double)Psi[i];
+    const int h1 = (int)(i / H), h2 = (int)(i % H);
+    double acc = 0.0;
+    for (int d = 0; d < D; ++d) acc += (double)W[(size_t)d * H + h1] * (double)W[(size_t)d * H + h2];
+    G[i] = acc;
+  }
+  for (size_t h = g0; h < (size_t)H; h += gt) {
+    T pi = pies[h];
+    pi = pi < T(1e-2) ? T(1e-2) : (pi > T(1.0 - 1e-2) ? T(1.0 - 1e-2) : pi);  // clamp (sssc.py:276)
+    prior[h] = (double)log(pi / (T(1) - pi));
+    mu[h] = (double)mus[h];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    double s = 0.0;
+    for (int h = threadIdx.x; h < H; h += 32) {
+      T pi = pies[h];
+      pi = pi < T(1e-2) ? T(1e-2) : (pi > T(1.0 - 1e-2) ? T(1.0 - 1e-2) : pi);
+      s += (double)log(T(1) - pi);
+    }
+    s = warp_sum(s);
+    if (threadIdx.x == 0) {
+      hdr->sigma2 = (double)sigma2[0];
+      hdr->prior_sum = s;
+      hdr->log_2pi_sigma2 = log(2.0 * 3.14159265358979323846) + (double)log(sigma2[0]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ per-state solve
+// Per-warp scratch for one state with up to `amax` active units.
+struct SsscScratch {
+  double *R;    // amax*amax : Psi_A -> Cholesky factor R (lower)
+  double *Gm;   // amax*amax : G_AA  -> M -> Cholesky factor C (lower)
+  double *X;    // amax*amax : G R, then C^-1, then U = R C^-T; finally Lambda + kappa kappa^T (M-step)
+  double *vec;  // 6*amax    : mu_A | a_A | b | v / z | kappa | tmp
+  int *act;     // amax
+};
+__host__ __device__ inline size_t sssc_scratch_bytes(int amax) {
+  return (size_t)3 * amax * amax * 8 + (size_t)6 * amax * 8 + align16((size_t)amax * 4);
+}
+__device__ inline SsscScratch sssc_carve(unsigned char *p, int amax) {
+  SsscScratch s;
+  s.R = (double *)p;
+  s.Gm = s.R + (size_t)amax * amax;
+  s.X = s.Gm + (size_t)amax * amax;
+  s.vec = s.X + (size_t)amax * amax;
+  s.act = (int *)(s.vec + 6 * amax);
+  return s;
+}
+
+// in-place Cholesky (lower) of the a x a SPD matrix A (row stride ld); returns false on a bad pivot
+__device__ inline bool chol_lower(double *A, int a, int ld, int lane) {
+  bool ok = true;
+  for (int j = 0; j < a; ++j) {
+    __syncwarp();
+    double djj = A[j * ld + j];
+    for (int k = 0; k < j; ++k) djj -= A[j * ld + k] * A[j * ld + k];
+    ok = ok && (djj > 0.0);
+    const double ljj = sqrt(djj);
+    for (int i = j + 1 + lane; i < a; i += 32) {
+      double v = A[i * ld + j];
+      for (int k = 0; k < j; ++k) v -= A[i * ld + k] * A[j * ld + k];
+      A[i * ld + j] = v / ljj;
+    }
+    __syncwarp();
+    if (lane == 0) A[j * ld + j] = ljj;
+  }
+  __syncwarp();
+  return ok;
+}
+
+// lpj of one state (warp-cooperative).  a_vec: shared (H) = W^T y; yy = ||y||^2.  If want_moments,
+// sc.vec[4*amax ..] receives kappa (a) and sc.X receives Lambda + kappa kappa^T (a x a).
+// y_nan_row != nullptr selects the restricted (NaN-aware) path.  Returns lpj (double; NaN if the state
+// cannot be evaluated) and the number of active units through n_act (-1: more than amax).
+template <typename T>
+__device__ inline double sssc_state(const uint64_t *st, int W64, int H, int D, const SsscTheta<T> &th,
+                                    const double *a_vec, double yy, const T *y_nan_row, const SsscScratch &sc, int amax,
+                                    bool want_moments, int &n_act, int lane) {
+  const double s2 = th.hdr->sigma2;
+  // active set
+  int a = 0;
+  for (int w = 0; w < W64; ++w) a += __popcll(st[w]);
+  n_act = a;
+  if (a > amax) {
+    n_act = -1;
+    return __longlong_as_double(0x7ff8000000000000ll);  // NaN -> finfo.min at the caller (sssc.py:343-345)
+  }
+  if (lane == 0) {
+    int k = 0;
+    for (int w = 0; w < W64; ++w) {
+      uint64_t m = st[w];
+      while (m) {
+        sc.act[k++] = (w << 6) + __ffsll((long long)m) - 1;
+        m &= m - 1;
+      }
+    }
+  }
+  __syncwarp();
+  double *mu = sc.vec, *aA = sc.vec + amax, *bv = sc.vec + 2 * amax, *vz = sc.vec + 3 * amax, *kap = sc.vec + 4 * amax;
+  double prior = 0.0;
+  for (int i = 0; i < a; ++i) prior += th.prior[sc.act[i]];
+  if (a == 0) {
+    double yyn = yy;
+    if (y_nan_row) {
+      double t = 0.0;
+      for (int d = lane; d < D; d += 32) {
+        const double v = (double)y_nan_row[d];
+        if (v == v) t += v * v;
+      }
+      yyn = warp_sum(t);
+    }
+    return -0.5 * (yyn / s2);
+  }
+  const int ld = amax;
+  // Psi_A, G_AA, mu_A, a_A
+  for (int t = lane; t < a * a; t += 32) {
+    const int i = t / a, j = t % a;
+    sc.R[i * ld + j] = th.Psi[(size_t)sc.act[i] * H + sc.act[j]];
+    if (!y_nan_row) sc.Gm[i * ld + j] = th.G[(size_t)sc.act[i] * H + sc.act[j]];
+  }
+  for (int i = lane; i < a; i += 32) {
+    mu[i] = th.mus[sc.act[i]];
+    if (!y_nan_row) aA[i] = a_vec[sc.act[i]];
+  }
+  if (y_nan_row) {  // restricted to the observed dimensions (sssc.py:283-298)
+    for (int t = lane; t < a * a + a; t += 32) {
+      const int i = t < a * a ? t / a : t - a * a, j = t < a * a ? t % a : -1;
+      const T *wi = th.Wt + (size_t)sc.act[i] * th.Dpad;
+      const T *wj = j >= 0 ? th.Wt + (size_t)sc.act[j] * th.Dpad : nullptr;
+      double acc = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double yv = (double)y_nan_row[d];
+        if (yv == yv) acc += (double)wi[d] * (j >= 0 ? (double)wj[d] : yv);
+      }
+      if (j >= 0) sc.Gm[i * ld + j] = acc; else aA[i] = acc;
+    }
+    double t = 0.0;
+    for (int d = lane; d < D; d += 32) {
+      const double v = (double)y_nan_row[d];
+      if (v == v) t += v * v;
+    }
+    yy = warp_sum(t);
+  }
+  __syncwarp();
+  // b = a_A - G mu,  rr = yy - 2 mu.a_A + mu^T G mu
+  for (int i = lane; i < a; i += 32) {
+    double gm = 0.0;
+    for (int k = 0; k < a; ++k) gm += sc.Gm[i * ld + k] * mu[k];
+    bv[i] = aA[i] - gm;
+    vz[i] = mu[i] * (gm - 2.0 * aA[i]);
+  }
+  __syncwarp();
+  double rr = yy;
+  for (int i = 0; i < a; ++i) rr += vz[i];
+  // Psi_A = R R^T
+  bool ok = chol_lower(sc.R, a, ld, lane);
+  // X = G R  (R lower: k >= j)
+  for (int t = lane; t < a * a; t += 32) {
+    const int i = t / a, j = t % a;
+    double acc = 0.0;
+    for (int k = j; k < a; ++k) acc += sc.Gm[i * ld + k] * sc.R[k * ld + j];
+    sc.X[i * ld + j] = acc;
+  }
+  __syncwarp();
+  // M = I + R^T X / s2  (into Gm)
+  for (int t = lane; t < a * a; t += 32) {
+    const int i = t / a, j = t % a;
+    double acc = 0.0;
+    for (int k = i; k < a; ++k) acc += sc.R[k * ld + i] * sc.X[k * ld + j];
+    sc.Gm[i * ld + j] = acc / s2 + (i == j ? 1.0 : 0.0);
+  }
+  __syncwarp();
+  ok = chol_lower(sc.Gm, a, ld, lane) && ok;  // M = C C^T
+  double logdet = 0.0;
+  for (int i = 0; i < a; ++i) logdet += log(sc.Gm[i * ld + i]);
+  logdet *= 2.0;
+  // v = R^T b ; z = C^-1 v (forward substitution)
+  for (int i = lane; i < a; i += 32) {
+    double acc = 0.0;
+    for (int k = i; k < a; ++k) acc += sc.R[k * ld + i] * bv[k];
+    vz[i] = acc;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    for (int i = 0; i < a; ++i) {
+      double v = vz[i];
+      for (int k = 0; k < i; ++k) v -= sc.Gm[i * ld + k] * vz[k];
+      vz[i] = v / sc.Gm[i * ld + i];
+    }
+  }
+  __syncwarp();
+  double zz = 0.0;
+  for (int i = 0; i < a; ++i) zz += vz[i] * vz[i];
+  const double quad = rr / s2 - zz / (s2 * s2);
+  double lpj = prior - 0.5 * (logdet + quad);
+  if (!ok) lpj = __longlong_as_double(0x7ff8000000000000ll);
+  if (want_moments) {
+    // Cinv = C^-1 (lower) column by column into X ; U = R Cinv^T ; Lambda = U U^T
+    for (int j = lane; j < a; j += 32) {
+      for (int i = 0; i < a; ++i) {
+        double v = (i == j) ? 1.0 : 0.0;
+        for (int k = j; k < i; ++k) v -= sc.Gm[i * ld + k] * sc.X[k * ld + j];
+        sc.X[i * ld + j] = i < j ? 0.0 : v / sc.Gm[i * ld + i];
+      }
+    }
+    __syncwarp();
+    // t = C^-T z  -> kappa = mu + R t / s2 ;  U = R Cinv^T written over Gm (C no longer needed)
+    for (int i = lane; i < a; i += 32) {
+      double acc = 0.0;
+      for (int k = i; k < a; ++k) acc += sc.X[k * ld + i] * vz[k];
+      kap[i] = acc;  // t_i
+    }
+    __syncwarp();
+    for (int t = lane; t < a * a; t += 32) {
+      const int i = t / a, j = t % a;
+      double acc = 0.0;
+      for (int k = 0; k <= i; ++k) acc += sc.R[i * ld + k] * sc.X[j * ld + k];  // Cinv^T[k][j] = Cinv[j][k]
+      sc.Gm[i * ld + j] = acc;  // U
+    }
+    for (int i = lane; i < a; i += 32) {
+      double acc = 0.0;
+      for (int k = 0; k <= i; ++k) acc += sc.R[i * ld + k] * kap[k];
+      bv[i] = mu[i] + acc / s2;  // kappa_i (bv reused; b no longer needed)
+    }
+    __syncwarp();
+    for (int i = lane; i < a; i += 32) kap[i] = bv[i];
+    for (int t = lane; t < a * a; t += 32) {
+      const int i = t / a, j = t % a;
+      double acc = 0.0;
+      for (int k = 0; k < a; ++k) acc += sc.Gm[i * ld + k] * sc.Gm[j * ld + k];
+      sc.X[i * ld + j] = acc + bv[i] * bv[j];  // Lambda + kappa kappa^T  (sssc.py:421-423)
+    }
+    __syncwarp();
+  }
+  return lpj;
+}
+
+template <typename T>
+__device__ __forceinline__ T sssc_finish(double lpj) {
+  // lpj[isnan] = lpj[isinf] = finfo.min  (sssc.py:343-345)
+  const double mn = sizeof(T) == 8 ? -1.7976931348623157e308 : -3.4028234663852886e38;
+  if (lpj != lpj || lpj == INFINITY || lpj == -INFINITY) return (T)mn;
+  if (sizeof(T) == 4 && (lpj < mn)) return (T)mn;
+  return (T)lpj;
+}
+
+template <typename T>
+struct SsscModel {
+  struct Params {
+    const T *Y;
+    int64_t ldY;
+    const T *A;  // B x H : W^T y per datapoint of this launch
+    const void *ws;
+    int H, D, amax;
+    int *overflow;  // set when a state has more than amax active units
+  };
+  __host__ __device__ static size_t smem_bytes(const Params &p) { return (size_t)p.H * 8 + sssc_scratch_bytes(p.amax); }
+  struct Ctx {
+    double yy;
+    bool has_nan;
+    const T *y;
+    double *a_sm;
+    SsscScratch sc;
+    __device__ void load(const Params &p, int64_t b, unsigned char *smem, int lane) {
+      y = p.Y + b * p.ldY;
+      a_sm = (double *)smem;
+      sc = sssc_carve(smem + (size_t)p.H * 8, p.amax);
+      double t = 0.0;
+      bool nan = false;
+      for (int d = lane; d < p.D; d += 32) {
+        const double v = (double)y[d];
+        nan |= (v != v);
+        t += v * v;
+      }
+      yy = warp_sum(t);
+      has_nan = __any_sync(FULL, nan);
+      for (int h = lane; h < p.H; h += 32) a_sm[h] = (double)p.A[b * (int64_t)p.H + h];
+    }
+    __device__ void score(const Params &p, const uint64_t *states, int count, int W64, T *out, int lane) {
+      const SsscTheta<T> th = sssc_theta_view<T>(p.ws, p.H, p.D);
+      for (int s = 0; s < count; ++s) {
+        int na;
+        const double v = sssc_state<T>(states + (size_t)s * W64, W64, p.H, p.D, th, a_sm, yy, has_nan ? y : nullptr, sc,
+                                       p.amax, false, na, lane);
+        if (lane == 0) {
+          out[s] = sssc_finish<T>(v);
+          if (na < 0) *p.overflow = 1;
+        }
+        __syncwarp();
+      }
+    }
+  };
+};
+
+// log_pseudo_joint for explicit state sets: one warp per (datapoint, chunk of states)
+template <typename T>
+__global__ void __launch_bounds__(256)
+sssc_lpj_kernel(typename SsscModel<T>::Params p, const uint64_t *__restrict__ K, int64_t k_stride_n,
+                const int64_t *__restrict__ idx, T *__restrict__ lpj_out, int64_t lpj_stride_n, int64_t B, int S, int CH,
+                size_t msm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int W64 = n_words(p.H);
+  const int nchunk = (S + CH - 1) / CH;
+  typename SsscModel<T>::Ctx ctx;
+  for (int64_t task = (int64_t)blockIdx.x * wpb + wib; task < B * nchunk; task += (int64_t)gridDim.x * wpb) {
+    const int64_t b = task / nchunk;
+    const int c = (int)(task % nchunk);
+    const int64_t row = idx ? idx[b] : b;
+    __syncwarp();
+    ctx.load(p, b, smem_raw + (size_t)wib * msm, lane);
+    __syncwarp();
+    const int s0 = c * CH, n = min(S, s0 + CH) - s0;
+    ctx.score(p, K + row * k_stride_n + (size_t)s0 * W64, n, W64, lpj_out + row * lpj_stride_n + s0, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------ M-step
+// stats: [y_szT^T (H*D) | sz_szT (H*H) | szszT (H*H) | ssT (H*H, UPPER) | ssz (H*H) | s (H) | sz (H) |
+//         diag_yyT (D) | N | F]
+// The kernel accumulates szszT, ssT, s, sz, diag_yyT, N, F and writes X = <kappa>_q (B x H) and
+// E = <s>_q (B x H); the three outer-product sums are GEMMs on X, E, Y done by the host wrapper.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sssc_mstep_kernel(typename SsscModel<T>::Params p, const int64_t *__restrict__ idx, int64_t row0,
+                  const uint64_t *__restrict__ K, int64_t k_stride_n, const T *__restrict__ lpj, int64_t lpj_stride_n,
+                  double *__restrict__ stats, double *__restrict__ X_out, double *__restrict__ E_out,
+                  double *__restrict__ Yd_out, int64_t B, int S, size_t wbytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int H = p.H, D = p.D, W64 = n_words(H), amax = p.amax;
+  const SsscTheta<T> th = sssc_theta_view<T>(p.ws, H, D);
+  unsigned char *base = smem_raw + (size_t)wib * wbytes;
+  typename SsscModel<T>::Ctx ctx;
+  double *xk = (double *)(base + SsscModel<T>::smem_bytes(p));  // <kappa> (H)
+  double *xe = xk + H;                                           // <s> (H)
+  double *q = xe + H;                                            // S
+  uint64_t *Ksm = (uint64_t *)(q + S);                           // S*W64
+  const size_t HD = (size_t)H * D, HH = (size_t)H * H;
+  double *szszT = stats + HD + HH, *ssT = szszT + HH, *s_acc = ssT + 2 * HH, *sz_acc = s_acc + H;
+  double *yy_acc = sz_acc + H, *Ncnt = yy_acc + D, *Facc = Ncnt + 1;
+  double accF = 0.0, accN = 0.0;
+  for (int64_t b = (int64_t)blockIdx.x * wpb + wib; b < B; b += (int64_t)gridDim.x * wpb) {
+    const int64_t row = idx ? idx[b] : row0 + b;
+    const T *l = lpj + row * lpj_stride_n;
+    __syncwarp();
+    ctx.load(p, b, base, lane);
+    for (int t = lane; t < S * W64; t += 32) Ksm[t] = K[row * k_stride_n + t];
+    for (int h = lane; h < H; h += 32) {
+      xk[h] = 0.0;
+      xe[h] = 0.0;
+    }
+    double mx = -INFINITY;
+    for (int s = lane; s < S; s += 32) mx = fmax(mx, (double)l[s]);
+    mx = warp_max(mx);
+    double se = 0.0;
+    for (int s = lane; s < S; s += 32) {
+      const double e = exp((double)l[s] - mx);
+      q[s] = e;
+      se += e;
+    }
+    se = warp_sum(se);
+    int dn = 0;
+    for (int d = lane; d < D; d += 32) {
+      const double v = (double)ctx.y[d];
+      dn += (v == v) ? 1 : 0;
+      atomicAdd(yy_acc + d, v * v);  // sum_n y^2 (sssc.py:445)
+      if (Yd_out) Yd_out[b * (int64_t)D + d] = v;
+    }
+    dn = warp_sum(dn);
+    accF += mx + log(se) + th.hdr->prior_sum - 0.5 * (double)dn * th.hdr->log_2pi_sigma2;
+    accN += 1.0;
+    __syncwarp();
+    for (int s = 0; s < S; ++s) {
+      const double qs = q[s] / se;
+      int na;
+      sssc_state<T>(Ksm + (size_t)s * W64, W64, H, D, th, ctx.a_sm, ctx.yy, nullptr, ctx.sc, amax, true, na, lane);
+      if (na < 0 && lane == 0) *p.overflow = 1;
+      if (na <= 0 || qs == 0.0) {
+        __syncwarp();
+        continue;
+      }
+      const double *kap = ctx.sc.vec + 4 * amax;
+      for (int i = lane; i < na; i += 32) {
+        const int h = ctx.sc.act[i];
+        xe[h] += qs;
+        xk[h] += qs * kap[i];
+      }
+      for (int t = lane; t < na * na; t += 32) {
+        const int i = t / na, j = t % na;
+        const int hi = ctx.sc.act[i], hj = ctx.sc.act[j];
+        atomicAdd(szszT + (size_t)hi * H + hj, qs * ctx.sc.X[i * amax + j]);  // <Lambda + kappa kappa^T>
+        if (j >= i) atomicAdd(ssT + (size_t)hi * H + hj, qs);                 // <s s^T>, upper triangle
+      }
+      __syncwarp();
+    }
+    for (int h = lane; h < H; h += 32) {
+      const double e = xe[h], k = xk[h];
+      X_out[b * (int64_t)H + h] = k;
+      E_out[b * (int64_t)H + h] = e;
+      if (e != 0.0) {
+        atomicAdd(s_acc + h, e);
+        atomicAdd(sz_acc + h, k);
+      }
+    }
+  }
+  if (lane == 0 && accN != 0.0) {
+    atomicAdd(Ncnt, accN);
+    atomicAdd(Facc, accF);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+static cublasHandle_t g_sssc_handles[64];
+static int sssc_cublas(cudaStream_t st, cublasHandle_t &h) {
+  int dev = 0;
+  TVO_CUDA(cudaGetDevice(&dev));
+  TVO_REQUIRE(dev >= 0 && dev < 64, "cublas: device index %d out of range", dev);
+  if (!g_sssc_handles[dev] && cublasCreate(&g_sssc_handles[dev]) != CUBLAS_STATUS_SUCCESS)
+    return set_error(TVO_ECUDA, "cublasCreate failed");
+  h = g_sssc_handles[dev];
+  if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) return set_error(TVO_ECUDA, "cublasSetStream failed");
+  return TVO_OK;
+}
+#define TVO_CUBLAS(expr)                                                                     \
+  do {                                                                                       \
+    cublasStatus_t s_ = (expr);                                                              \
+    if (s_ != CUBLAS_STATUS_SUCCESS) return set_error(TVO_ECUDA, "%s failed (%d)", #expr, (int)s_); \
+    count_launch();                                                                          \
+  } while (0)
+
+static int sssc_gemm_A(cublasHandle_t h, const double *Wt, int Dpad, const double *Y, int64_t ldY, double *A, int Bc, int H, int D) {
+  const double one = 1.0, zero = 0.0;
+  TVO_CUBLAS(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, H, Bc, D, &one, Wt, Dpad, Y, (int)ldY, &zero, A, H));
+  return TVO_OK;
+}
+static int sssc_gemm_A(cublasHandle_t h, const float *Wt, int Dpad, const float *Y, int64_t ldY, float *A, int Bc, int H, int D) {
+  const float one = 1.f, zero = 0.f;
+  TVO_CUBLAS(cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, H, Bc, D, &one, Wt, Dpad, Y, (int)ldY, &zero, A, H));
+  return TVO_OK;
+}
+
+static int sssc_pick_amax(int H, size_t other_bytes, int min_wpb) {
+  const int cands[4] = {32, 24, 16, 8};
+  for (int c : cands) {
+    const int amax = H < c ? H : c;
+    if ((other_bytes + (size_t)H * 8 + sssc_scratch_bytes(amax)) * min_wpb <= (size_t)227 * 1024) return amax;
+  }
+  return 0;
+}
+
+template <typename T>
+int sssc_prepare(const T *W, const T *sigma2, const T *mus, const T *Psi, const T *pies, int H, int D, void *ws,
+                 void *stream) {
+  TVO_REQUIRE(W && sigma2 && mus && Psi && pies && ws, "sssc_prepare: null pointer");
+  TVO_REQUIRE(H > 0 && D > 0, "sssc_prepare: bad sizes");
+  const size_t total = (size_t)H * max(sssc_dpad(D), H);
+  sssc_prepare_kernel<T><<<(int)max((size_t)1, min((size_t)4 * sm_count(), (total + 255) / 256)), 256, 0,
+                           (cudaStream_t)stream>>>(W, sigma2, mus, Psi, pies, H, D, ws);
+  TVO_AFTER_LAUNCH("sssc_prepare");
+  return TVO_OK;
+}
+
+// scratch: A (cap x H, T) for lpj / E-step; X, E (cap x H dbl each) [+ Yd cap x D dbl for f32] for the M-step
+template <typename T>
+int sssc_lpj(const T *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx, const void *ws,
+             T *lpj_out, int64_t lpj_stride_n, void *scratch, int64_t scratch_bytes, int *overflow, int64_t B, int S, int H,
+             int D, void *stream) {
+  TVO_REQUIRE(Y && K && ws && lpj_out && scratch && overflow, "sssc_lpj: null pointer");
+  TVO_REQUIRE(B >= 0 && S > 0 && H > 0 && D > 0 && ldY < (1ll << 31), "sssc_lpj: bad sizes");
+  const int64_t cap = scratch_bytes / ((int64_t)H * sizeof(T));
+  TVO_REQUIRE(cap >= 1, "sssc_lpj: scratch too small");
+  if (B == 0) return TVO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cublasHandle_t hb;
+  int rc = sssc_cublas(st, hb);
+  if (rc) return rc;
+  const SsscTheta<T> th = sssc_theta_view<T>(ws, H, D);
+  const int amax = sssc_pick_amax(H, 0, 4);
+  TVO_REQUIRE(amax > 0, "sssc_lpj: H=%d too large for shared memory", H);
+  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, amax, overflow};
+  const size_t msm = align16(SsscModel<T>::smem_bytes(p));
+  int wpb = 8;
+  while (wpb > 1 && msm * wpb > (size_t)227 * 1024) wpb >>= 1;
+  auto kern = sssc_lpj_kernel<T>;
+  TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(msm * wpb)));
+  const int CH = S <= 32 ? S : 32;
+  for (int64_t c0 = 0; c0 < B; c0 += cap) {
+    const int Bc = (int)min(cap, B - c0);
+    rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, (T *)scratch, Bc, H, D);
+    if (rc) return rc;
+    p.Y = Y + c0 * ldY;
+    const int64_t ntask = (int64_t)Bc * ((S + CH - 1) / CH);
+    const int grid = (int)max((int64_t)1, min((ntask + wpb - 1) / wpb, (int64_t)sm_count() * 4));
+    // rows of K / lpj are addressed through idx (or consecutively from c0)
+    kern<<<grid, wpb * 32, msm * wpb, st>>>(p, idx ? K : K + c0 * k_stride_n, k_stride_n, idx ? idx + c0 : nullptr,
+                                            idx ? lpj_out : lpj_out + c0 * lpj_stride_n, lpj_stride_n, Bc, S, CH, msm);
+    TVO_AFTER_LAUNCH("sssc_lpj");
+  }
+  return TVO_OK;
+}
+
+template <typename T>
+int sssc_estep(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj, const void *ws, const tvo_evo_config *cfg,
+               const double *sparsity, void *scratch, int64_t scratch_bytes, int *overflow, int64_t B, int S, int H, int D,
+               int64_t *nsubs, void *stream) {
+  TVO_REQUIRE(Y && K && lpj && ws && cfg && nsubs && scratch && overflow, "estep_evo_sssc: null pointer");
+  TVO_REQUIRE(B >= 0 && H > 0 && D > 0 && ldY < (1ll << 31), "estep_evo_sssc: bad sizes");
+  const int64_t cap = scratch_bytes / ((int64_t)H * sizeof(T));
+  TVO_REQUIRE(cap >= 1, "estep_evo_sssc: scratch too small");
+  if (B == 0) return TVO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cublasHandle_t hb;
+  int rc = sssc_cublas(st, hb);
+  if (rc) return rc;
+  EvoParams ep;
+  EstepDims dims;
+  rc = evo_params_from_cfg(cfg, S, H, ep, dims, "estep_evo_sssc");
+  if (rc) return rc;
+  const SsscTheta<T> th = sssc_theta_view<T>(ws, H, D);
+  const int amax = sssc_pick_amax(H, warp_buf_bytes<T>(dims), 2);
+  TVO_REQUIRE(amax > 0, "estep_evo_sssc: working set too large for shared memory");
+  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, amax, overflow};
+  for (int64_t c0 = 0; c0 < B; c0 += cap) {
+    const int Bc = (int)min(cap, B - c0);
+    rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, (T *)scratch, Bc, H, D);
+    if (rc) return rc;
+    p.Y = Y + c0 * ldY;
+    rc = launch_estep_evo_fused<T, SsscModel<T>>(p, idx ? idx + c0 : nullptr, c0, K, lpj, cfg, sparsity, Bc, S, H, nsubs, st,
+                                                 "estep_evo_sssc");
+    if (rc) return rc;
+  }
+  return TVO_OK;
+}
+
+template <typename T>
+int sssc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n, const T *lpj,
+               int64_t lpj_stride_n, const void *ws, double *stats, void *scratch, int64_t scratch_bytes, int *overflow,
+               int64_t B, int S, int H, int D, int with_ssz, void *stream) {
+  TVO_REQUIRE(Y && K && lpj && ws && stats && scratch && overflow, "sssc_mstep: null pointer");
+  TVO_REQUIRE(B >= 0 && S > 0 && H > 0 && D > 0 && ldY < (1ll << 31), "sssc_mstep: bad sizes");
+  const bool f64 = sizeof(T) == 8;
+  const int64_t per = (int64_t)H * sizeof(T) + 2 * (int64_t)H * 8 + (f64 ? 0 : (int64_t)D * 8);
+  const int64_t cap = scratch_bytes / per;
+  TVO_REQUIRE(cap >= 1, "sssc_mstep: scratch too small (need %lld B per datapoint)", (long long)per);
+  if (B == 0) return TVO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cublasHandle_t hb;
+  int rc = sssc_cublas(st, hb);
+  if (rc) return rc;
+  const SsscTheta<T> th = sssc_theta_view<T>(ws, H, D);
+  const int W64 = n_words(H);
+  const size_t extra = (size_t)2 * H * 8 + (size_t)S * 8 + (size_t)S * W64 * 8;
+  const int amax = sssc_pick_amax(H, extra, 2);
+  TVO_REQUIRE(amax > 0, "sssc_mstep: working set too large for shared memory");
+  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, amax, overflow};
+  const size_t wbytes = align16(SsscModel<T>::smem_bytes(p) + extra);
+  int wpb = 8;
+  while (wpb > 1 && wbytes * wpb > (size_t)227 * 1024) wpb >>= 1;
+  auto kern = sssc_mstep_kernel<T>;
+  TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wbytes * wpb)));
+  int occ = 1;
+  TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, wbytes * wpb));
+  const size_t HD = (size_t)H * D, HH = (size_t)H * H;
+  const double one = 1.0;
+  for (int64_t c0 = 0; c0 < B; c0 += cap) {
+    const int Bc = (int)min(cap, B - c0);
+    T *A = (T *)scratch;
+    double *X = (double *)((unsigned char *)scratch + align16((size_t)cap * H * sizeof(T)));
+    double *E = X + (size_t)cap * H;
+    double *Yd = f64 ? nullptr : E + (size_t)cap * H;
+    rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, A, Bc, H, D);
+    if (rc) return rc;
+    p.Y = Y + c0 * ldY;
+    const int grid = (int)max((int64_t)1, min((int64_t)(Bc + wpb - 1) / wpb, (int64_t)sm_count() * max(occ, 1)));
+    kern<<<grid, wpb * 32, wbytes * wpb, st>>>(p, idx ? idx + c0 : nullptr, c0, K, k_stride_n, lpj, lpj_stride_n, stats, X, E,
+                                              Yd, Bc, S, wbytes);
+    TVO_AFTER_LAUNCH("sssc_mstep");
+    const double *Yp = f64 ? (const double *)(Y + c0 * ldY) : Yd;
+    const int ldy = f64 ? (int)ldY : D;
+    // y_szT^T (H x D row-major) += X^T Y                     (sssc.py:446)
+    TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, D, H, Bc, &one, Yp, ldy, X, H, &one, stats, D));
+    // sz_szT (H x H) += X^T X                                 (sssc.py:443)
+    TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, H, H, Bc, &one, X, H, X, H, &one, stats + HD, H));
+    // ssz (H x H row-major, [h_s][h_kappa]) += E^T X         (sssc.py:448-450); col-major view: ssz^T = X^T E
+    if (with_ssz)
+      TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, H, H, Bc, &one, X, H, E, H, &one, stats + HD + 3 * HH, H));
+  }
+  return TVO_OK;
+}
+
+}  // namespace tvo
+
+using namespace tvo;
+
+extern "C" {
+int64_t tvo_sssc_theta_ws_bytes(int32_t H, int32_t D, int32_t is_f64) {
+  return (int64_t)(is_f64 ? sssc_ws_bytes<double>(H, D) : sssc_ws_bytes<float>(H, D));
+}
+int64_t tvo_sssc_stats_len(int32_t H, int32_t D) { return (int64_t)H * D + 4 * (int64_t)H * H + 2 * H + D + 2; }
+int64_t tvo_sssc_scratch_bytes(int64_t B, int32_t H, int32_t D, int32_t is_f64) {
+  return 16 + B * ((int64_t)H * (is_f64 ? 8 : 4) + 2 * (int64_t)H * 8 + (is_f64 ? 0 : (int64_t)D * 8));
+}
+#define TVO_SSSC_WRAP(sfx, T)                                                                                              \
+  int tvo_sssc_prepare_##sfx(const T *W, const T *sigma2, const T *mus, const T *Psi, const T *pies, int32_t H, int32_t D, \
+                             void *ws, void *stream) {                                                                     \
+    return sssc_prepare<T>(W, sigma2, mus, Psi, pies, H, D, ws, stream);                                                   \
+  }                                                                                                                        \
+  int tvo_sssc_lpj_##sfx(const T *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, const int64_t *idx,               \
+                         const void *ws, T *lpj_out, int64_t lpj_stride_n, void *scratch, int64_t scratch_bytes,           \
+                         int32_t *overflow, int64_t B, int32_t S, int32_t H, int32_t D, void *stream) {                    \
+    return sssc_lpj<T>(Y, ldY, K, k_stride_n, idx, ws, lpj_out, lpj_stride_n, scratch, scratch_bytes, overflow, B, S, H,   \
+                       D, stream);                                                                                         \
+  }                                                                                                                        \
+  int tvo_estep_evo_sssc_##sfx(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj, const void *ws,           \
+                               const tvo_evo_config *cfg, const double *sparsity, void *scratch, int64_t scratch_bytes,    \
+                               int32_t *overflow, int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs,              \
+                               void *stream) {                                                                             \
+    return sssc_estep<T>(Y, ldY, idx, K, lpj, ws, cfg, sparsity, scratch, scratch_bytes, overflow, B, S, H, D, nsubs,      \
+                         stream);                                                                                          \
+  }                                                                                                                        \
+  int tvo_sssc_mstep_##sfx(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,             \
+                           const T *lpj, int64_t lpj_stride_n, const void *ws, double *stats, void *scratch,               \
+                           int64_t scratch_bytes, int32_t *overflow, int64_t B, int32_t S, int32_t H, int32_t D,           \
+                           int32_t with_ssz, void *stream) {                                                               \
+    return sssc_mstep<T>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, ws, stats, scratch, scratch_bytes, overflow, B, S, \
+                         H, D, with_ssz, stream);                                                                          \
+  }
+TVO_SSSC_WRAP(f64, double)
+TVO_SSSC_WRAP(f32, float)
+}
