@@ -175,6 +175,7 @@ def run_gpu(args):
     from tvo_b200.variational import EVOVariationalStates
 
     if world > 1:
+        os.environ.pop("NCCL_DEBUG", None)  # the box exports NCCL_DEBUG=VERSION, which prints to stdout
         parallel.init_processes()
     else:
         to.cuda.set_device(local_rank)
