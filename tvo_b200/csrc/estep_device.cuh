@@ -45,7 +45,7 @@ __host__ __device__ inline size_t warp_buf_bytes(const EstepDims &d) {
   }
   b += align16(d.need_fit ? (size_t)d.Scmax * 8 : 0);
   b += align16((size_t)(d.S + d.Snew) * sizeof(T));
-  b += align16((size_t)(d.S + d.Snew) * 4);
+  b += align16((size_t)(((d.S + 3) & ~3) + ((d.Snew + 3) & ~3)) * 4);  // hash_len(S, Snew)
   const int isz = d.Scmax > 2 * d.Sgen ? d.Scmax : 2 * d.Sgen;
   b += align16((size_t)isz * 4);
   return b;
@@ -71,7 +71,7 @@ __device__ inline WarpBuf<T> carve_warp_buf(unsigned char *p, const EstepDims &d
   w.lpj = (T *)p;
   p += align16((size_t)(d.S + d.Snew) * sizeof(T));
   w.hash = (uint32_t *)p;
-  p += align16((size_t)(d.S + d.Snew) * 4);
+  p += align16((size_t)(((d.S + 3) & ~3) + ((d.Snew + 3) & ~3)) * 4);
   w.iscr = (int32_t *)p;
   return w;
 }
@@ -422,70 +422,105 @@ static __device__ __noinline__ bool same_state(const uint64_t *x, const uint64_t
   return eq;
 }
 
-// Child c is redundant if an old state (j < S) or a LATER child (j - S > c) has the same bits.
-// Pass 1 scans the 32-bit hashes of all M candidates (4 per shared load) for every child of the lane
-// and remembers the first hash match; pass 2 does ONE full compare per child.  Only a hash collision
-// (first match is not a true duplicate although further hash matches exist) takes the slow rescan.
-template <typename T>
-__device__ inline void mark_redundant(const WarpBuf<T> &wb, int S, int Snew, int W64, int lane) {
-  const int M = S + Snew;
-  for (int i = lane; i < M; i += 32)
-    wb.hash[i] = hash_words(i < S ? wb.oldK + (size_t)i * W64 : wb.newK + (size_t)(i - S) * W64, W64);
-  __syncwarp();
-  constexpr int CPL = 4;  // children per lane handled per sweep
-  const int M4 = M & ~3;
+// Child c is redundant if an old state or a LATER child has the same bits.
+//
+// Hash scan with one deferred full compare.  The 32-bit hashes (forced odd, so the zero padding never
+// matches) live in two 16-byte-aligned runs: S old hashes padded to a multiple of 4, then Snew child
+// hashes padded likewise.  Each lane owns CPL children (c = c0 + 32 t + lane) and remembers ANY
+// matching candidate:
+//   * old states: broadcast LDS.128 of 4 hashes, 2 instructions per (hash, child) pair;
+//   * later children of a LATER 32-group: same scan, no index condition needed;
+//   * later children of the SAME 32-group: one __match_any_sync on the hash register.
+// One full state compare per child confirms the match; only a genuine hash collision takes the
+// exhaustive rescan.
+__host__ __device__ inline int hash_old_pad(int S) { return (S + 3) & ~3; }
+__host__ __device__ inline int hash_len(int S, int Snew) { return hash_old_pad(S) + ((Snew + 3) & ~3); }
+
+#define TVO_CMP4(h4, base)                      \
+  _Pragma("unroll") for (int t = 0; t < CPL; ++t) { \
+    if ((h4).x == hc[t]) hit[t] = (base);       \
+    if ((h4).y == hc[t]) hit[t] = (base) + 1;   \
+    if ((h4).z == hc[t]) hit[t] = (base) + 2;   \
+    if ((h4).w == hc[t]) hit[t] = (base) + 3;   \
+  }
+
+template <typename T, int CPL>
+__device__ __forceinline__ void mark_redundant_cpl(const WarpBuf<T> &wb, int S, int Snew, int W64, int lane) {
+  const int Sp = hash_old_pad(S), Snp = (Snew + 3) & ~3;
+  const uint32_t *ho = wb.hash, *hn = wb.hash + Sp;
+#pragma unroll 1
   for (int c0 = 0; c0 < Snew; c0 += 32 * CPL) {
     uint32_t hc[CPL];
-    int first[CPL], nmatch[CPL];
+    int hit[CPL];  // concatenated index (old: j, child: S + j) of a candidate with the same hash
 #pragma unroll
     for (int t = 0; t < CPL; ++t) {
       const int c = c0 + 32 * t + lane;
-      hc[t] = c < Snew ? wb.hash[S + c] : 0u;
-      first[t] = -1;
-      nmatch[t] = 0;
+      hc[t] = c < Snew ? hn[c] : 0u;
+      hit[t] = -1;
     }
-    for (int j = 0; j < M; j += 4) {
-      uint4 h4;
-      if (j < M4) {
-        h4 = *reinterpret_cast<const uint4 *>(wb.hash + j);  // hash is 16-byte aligned
-      } else {
-        h4.x = wb.hash[j];
-        h4.y = j + 1 < M ? wb.hash[j + 1] : 0u;
-        h4.z = j + 2 < M ? wb.hash[j + 2] : 0u;
-        h4.w = 0u;
-      }
+#pragma unroll 2
+    for (int j = 0; j < Sp; j += 4) {
+      const uint4 h4 = *reinterpret_cast<const uint4 *>(ho + j);
+      TVO_CMP4(h4, j)
+    }
 #pragma unroll
-      for (int t = 0; t < CPL; ++t) {
-        const int c = c0 + 32 * t + lane;
+    for (int g = 1; g < CPL; ++g) {  // children of later 32-groups of this sweep
+      const int jb = c0 + 32 * g, je = min(jb + 32, Snp);
+      for (int j = jb; j < je; j += 4) {
+        const uint4 h4 = *reinterpret_cast<const uint4 *>(hn + j);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t hj = u == 0 ? h4.x : u == 1 ? h4.y : u == 2 ? h4.z : h4.w;
-          const int jj = j + u;
-          const bool hit = hj == hc[t] && jj < M && c < Snew && (jj < S || jj - S > c);
-          if (hit) {
-            if (first[t] < 0) first[t] = jj;
-            ++nmatch[t];
+        for (int t = 0; t < CPL; ++t) {
+          if (t < g) {
+            if (h4.x == hc[t]) hit[t] = S + j;
+            if (h4.y == hc[t]) hit[t] = S + j + 1;
+            if (h4.z == hc[t]) hit[t] = S + j + 2;
+            if (h4.w == hc[t]) hit[t] = S + j + 3;
           }
         }
       }
     }
+    for (int j = c0 + 32 * CPL; j < Snp; j += 4) {  // children of later sweeps (Snew > 32*CPL only)
+      const uint4 h4 = *reinterpret_cast<const uint4 *>(hn + j);
+      TVO_CMP4(h4, S + j)
+    }
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {  // later children of the same 32-group
+      const unsigned later = __match_any_sync(FULL, hc[t]) & ~((2u << lane) - 1u);
+      if (later && hc[t]) hit[t] = S + c0 + 32 * t + __ffs(later) - 1;
+    }
 #pragma unroll
     for (int t = 0; t < CPL; ++t) {
       const int c = c0 + 32 * t + lane;
-      bool dup = false;
-      if (first[t] >= 0) {
+      if (c < Snew && hit[t] >= 0) {
         const uint64_t *sc = wb.newK + (size_t)c * W64;
-        const int jj = first[t];
-        dup = same_state(jj < S ? wb.oldK + (size_t)jj * W64 : wb.newK + (size_t)(jj - S) * W64, sc, W64);
-        if (!dup && nmatch[t] > 1) {  // hash collision: rescan everything (practically never)
-          for (int j2 = jj + 1; j2 < M && !dup; ++j2)
-            if (wb.hash[j2] == hc[t] && (j2 < S || j2 - S > c))
-              dup = same_state(j2 < S ? wb.oldK + (size_t)j2 * W64 : wb.newK + (size_t)(j2 - S) * W64, sc, W64);
+        const int jj = hit[t];
+        bool dup = same_state(jj < S ? wb.oldK + (size_t)jj * W64 : wb.newK + (size_t)(jj - S) * W64, sc, W64);
+        if (!dup) {  // hash collision: exhaustive rescan (practically never)
+          for (int j2 = 0; j2 < S && !dup; ++j2)
+            if (ho[j2] == hc[t]) dup = same_state(wb.oldK + (size_t)j2 * W64, sc, W64);
+          for (int j2 = c + 1; j2 < Snew && !dup; ++j2)
+            if (hn[j2] == hc[t]) dup = same_state(wb.newK + (size_t)j2 * W64, sc, W64);
         }
+        if (dup) wb.lpj[S + c] = LowLpj<T>::v();
       }
-      if (dup) wb.lpj[S + c] = LowLpj<T>::v();
     }
   }
+}
+#undef TVO_CMP4
+
+template <typename T>
+__device__ inline void mark_redundant(const WarpBuf<T> &wb, int S, int Snew, int W64, int lane) {
+  const int Sp = hash_old_pad(S), Snp = (Snew + 3) & ~3;
+  for (int i = lane; i < Sp; i += 32) wb.hash[i] = i < S ? (hash_words(wb.oldK + (size_t)i * W64, W64) | 1u) : 0u;
+  for (int i = lane; i < Snp; i += 32)
+    wb.hash[Sp + i] = i < Snew ? (hash_words(wb.newK + (size_t)i * W64, W64) | 1u) : 0u;
+  __syncwarp();
+  if (Snew <= 32)
+    mark_redundant_cpl<T, 1>(wb, S, Snew, W64, lane);
+  else if (Snew <= 64)
+    mark_redundant_cpl<T, 2>(wb, S, Snew, W64, lane);
+  else
+    mark_redundant_cpl<T, 4>(wb, S, Snew, W64, lane);
   __syncwarp();
 }
 
