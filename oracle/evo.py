@@ -3,7 +3,7 @@
 Restates tvo/variational/evo.py with the reference's sampling semantics but a counter-based
 stream (oracle/philox.py) in place of torch's / numpy's global generators:
 
-  batch_randparents      evo.py:436-451   P distinct candidates = first P of a random permutation
+  batch_randparents      evo.py:436-451   P distinct candidates in random order (P smallest random keys)
   batch_fitparents       evo.py:397-433   fitness-proportional, with replacement, batch-global
                                           normalisation and the S-1-count index (quirk Q3)
   batch_randflip         evo.py:248-279   C distinct bit positions per parent, one flip per child
@@ -33,19 +33,18 @@ def get_n_new_states(mutation, n_parents, n_children, n_gen):
 
 # ----------------------------------------------------------------------------- selection
 def randparents_idx(n_glob, S_c, P, seed, step, gen):
-    """(N,P) indices: partial Fisher-Yates = first P entries of a uniform random permutation."""
+    """(N,P) indices of P distinct candidates in random order (evo.py:436-451: first P of a randperm).
+
+    Candidate i gets the key (r_i with its low `bits` bits replaced by i), r_i = u32 stream element i
+    of sub-stream 0, bits = bit_length(S_c - 1); the parents are the candidates with the P smallest
+    keys in ascending key order.  Keys are unique, so no tie rule is needed."""
     n_glob = np.asarray(n_glob, dtype=np.uint32)
-    N = len(n_glob)
     tag = px.make_tag(step, gen, px.PUR_SELECT)
-    perm = np.tile(np.arange(S_c, dtype=np.int64), (N, 1))
-    rows = np.arange(N)
-    for i in range(P):
-        r = px.stream_u32(seed, n_glob, np.uint32(0), tag, np.uint32(i))
-        k = i + px.randint_u32(r, S_c - i)
-        tmp = perm[rows, i].copy()
-        perm[rows, i] = perm[rows, k]
-        perm[rows, k] = tmp
-    return perm[:, :P]
+    bits = int(S_c - 1).bit_length()
+    i = np.arange(S_c, dtype=np.uint32)[None, :]
+    r = px.stream_u32(seed, n_glob[:, None], np.uint32(0), tag, i).astype(np.uint64)
+    key = ((r >> np.uint64(bits)) << np.uint64(bits)) | i.astype(np.uint64)
+    return np.argsort(key, axis=1, kind="stable")[:, :P].astype(np.int64)
 
 
 def fit_norm(lpj):

@@ -180,7 +180,9 @@ def test_reference_kats_dedup_merge():
 
 
 @pytest.mark.parametrize("dtype", [to.float64, to.float32])
-@pytest.mark.parametrize("H,S,Snew", [(4, 6, 9), (70, 5, 40), (256, 64, 64), (300, 33, 17)])
+@pytest.mark.parametrize("H,S,Snew", [(4, 6, 9), (70, 5, 40), (256, 64, 64), (300, 33, 17),
+                                      # many duplicates across the 32-groups / sweeps of the hash scan
+                                      (5, 7, 33), (6, 10, 100), (7, 9, 129), (6, 3, 300), (256, 64, 130)])
 def test_dedup_merge_random_vs_oracle(dtype, H, S, Snew):
     rng = np.random.default_rng(S * Snew)
     N, Ntot = 50, 80

@@ -11,6 +11,7 @@
 // per chunk so that  WpT += E^T Y  is one DGEMM (the union of active bits per datapoint is ~100 of 256,
 // so the outer product is effectively dense).
 #include <cublas_v2.h>
+#include <stdlib.h>
 
 #include "bsc_device.cuh"
 
@@ -60,9 +61,10 @@ static int gemm_A(cublasHandle_t h, const float *Wt, int Dpad, const float *Y, i
 
 // ------------------------------------------------------------------------------------ Gram lpj
 // lpj of ONE state, evaluated by ONE lane.  a: shared memory (H), G: global (H x H), prior: global.
+// Bit-walk form: used when the state has more active units than the lane's position list holds.
 template <typename T>
-__device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, const T *a, const double *__restrict__ G,
-                                          const T *__restrict__ prior, double yy, double coef) {
+__device__ __noinline__ T bsc_gram_lpj_walk(const uint64_t *st, int W64, int H, const T *a, const double *__restrict__ G,
+                                            const T *__restrict__ prior, double yy, double coef) {
   double f = 0.0, pr = 0.0;
   for (int w1 = 0; w1 < W64; ++w1) {
     uint64_t m1 = st[w1];
@@ -86,6 +88,43 @@ __device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, co
       }
       f += 2.0 * g2;
     }
+  }
+  return (T)((yy + f) * coef + pr);
+}
+
+// Same sums in the same order, but the active positions are first written to a lane-strided list in
+// shared memory (plist[j * 32], the lane's base already applied), so the |s|(|s|-1)/2 pair loop is
+// LDS + address + LDG + DADD instead of a 64-bit find-first-set / clear-lowest-bit walk per pair.
+template <typename T>
+__device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, const T *a, const double *__restrict__ G,
+                                          const T *__restrict__ prior, double yy, double coef, uint16_t *plist, int cap) {
+  int n = 0;
+  for (int w = 0; w < W64; ++w) {
+    const uint64_t m = st[w];
+    uint32_t x = (uint32_t)m;
+    int base = w << 6;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      while (x) {
+        const int pos = base + __ffs((int)x) - 1;
+        x &= x - 1;
+        if (n < cap) plist[n * 32] = (uint16_t)pos;
+        ++n;
+      }
+      x = (uint32_t)(m >> 32);
+      base += 32;
+    }
+  }
+  if (n > cap) return bsc_gram_lpj_walk<T>(st, W64, H, a, G, prior, yy, coef);
+  double f = 0.0, pr = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const int h1 = plist[i * 32];
+    const double *Grow = G + (size_t)h1 * H;
+    f += __ldg(Grow + h1) - 2.0 * (double)a[h1];
+    pr += (double)__ldg(prior + h1);
+    double g2 = 0.0;
+    for (int j = i + 1; j < n; ++j) g2 += __ldg(Grow + plist[j * 32]);
+    f += 2.0 * g2;
   }
   return (T)((yy + f) * coef + pr);
 }
@@ -117,10 +156,10 @@ __device__ inline T bsc_direct_lpj_slow(const uint64_t *st, int W64, const BscTh
 template <typename T>
 __device__ __forceinline__ void score_states(const uint64_t *states, int count, int W64, int H, int D, const BscTheta<T> &th,
                                              const T *a_sm, const T *__restrict__ y, double yy, bool has_nan, T *out,
-                                             int lane) {
+                                             uint16_t *plist, int pcap, int lane) {
   if (!has_nan) {
     for (int s = lane; s < count; s += 32)
-      out[s] = bsc_gram_lpj<T>(states + (size_t)s * W64, W64, H, a_sm, th.G, th.prior, yy, th.hdr->coef);
+      out[s] = bsc_gram_lpj<T>(states + (size_t)s * W64, W64, H, a_sm, th.G, th.prior, yy, th.hdr->coef, plist + lane, pcap);
   } else {
     for (int s = 0; s < count; ++s) {
       const T v = bsc_direct_lpj_slow<T>(states + (size_t)s * W64, W64, th, y, D, lane, (T)th.hdr->coef);
@@ -132,7 +171,7 @@ __device__ __forceinline__ void score_states(const uint64_t *states, int count, 
 
 // EVOVariationalStates.update (evo.py:80-115) for BSC, Gram form.  Same structure and same random
 // stream as estep_evo_bsc_kernel (bsc.cu); `A` holds a = W^T y for the B datapoints of this launch.
-template <typename T>
+template <typename T, bool LOCKSTEP>
 __global__ void __launch_bounds__(256, 3)
 estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                           int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
@@ -148,12 +187,18 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
   const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64;
   const double sparsity = sparsity_p ? *sparsity_p : 0.0;
   unsigned long long my_subs = 0;
+  // position lists of the Gram scorer live in the keys/fmask region (free while states are scored)
+  uint16_t *plist = (uint16_t *)wb.keys;
+  const int pcap = H <= 65536 ? (int)(keys_region_bytes(dims) / 64) : 0;
 
   // All warps of a CTA walk the phases of the E-step in lockstep (PHASE_SYNC): the fused program is
   // ~100 KB of SASS, far beyond the instruction cache, and 24 independent warps at 24 different places
   // thrash it (ncu: 35% of stalls were instruction fetch).  With the barriers the 8 warps of a CTA
   // share the cache lines of the phase they are all in.
-#define PHASE_SYNC() __syncthreads()
+#define PHASE_SYNC()                \
+  do {                              \
+    if (LOCKSTEP) __syncthreads();  \
+  } while (0)
   for (int64_t b0 = (int64_t)blockIdx.x * wpb; b0 < B; b0 += (int64_t)gridDim.x * wpb) {
     const int64_t b = b0 + wib;
     const bool active = b < B;
@@ -177,7 +222,7 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
       __syncwarp();
     }
     PHASE_SYNC();
-    if (active) score_states<T>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, lane);  // evo.py:95
+    if (active) score_states<T>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, plist, pcap, lane);  // evo.py:95
     for (int g = 0; g < ep.G; ++g) {
       const uint64_t *cand = g == 0 ? wb.oldK : wb.newK + (size_t)(g - 1) * Sgen * W64;
       const T *cand_lpj = g == 0 ? wb.lpj : wb.lpj + S + (g - 1) * Sgen;
@@ -187,7 +232,8 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
         evo_generation<T>(wb, cand, cand_lpj, g == 0 ? S : Sgen, children, ep, g, n_glob, W64, H, sparsity, 0.0, 1.0,
                           lane);
       PHASE_SYNC();
-      if (active) score_states<T>(children, Sgen, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj + S + g * Sgen, lane);
+      if (active) score_states<T>(children, Sgen, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj + S + g * Sgen, plist, pcap,
+                                  lane);
     }
     PHASE_SYNC();
     if (active) mark_redundant<T>(wb, S, Snew, W64, lane);
@@ -347,7 +393,12 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
                   int S, int H, int D, int64_t *nsubs, void *stream) {
   TVO_REQUIRE(Y && K && lpj && ws && cfg && nsubs, "estep_evo_bsc: null pointer");
   const int64_t per = estep_scratch_per_dp<T>(H);
-  int64_t cap = scratch ? scratch_bytes / per : 0;
+  // scratch layout: [sparseflip table (flip_table_bytes(H), only when it fits)] [a = W^T y rows]
+  const bool sparse = cfg->mutation == TVO_MUT_SPARSEFLIP || cfg->mutation == TVO_MUT_CROSS_SPARSEFLIP;
+  const int64_t tab_bytes = sparse && scratch && sparsity ? (int64_t)flip_table_bytes(H) : 0;
+  const bool use_tab = tab_bytes > 0 && scratch_bytes >= tab_bytes + per * min((int64_t)1024, B);
+  unsigned char *scratch_a = (unsigned char *)scratch + (use_tab ? tab_bytes : 0);
+  int64_t cap = scratch ? (scratch_bytes - (use_tab ? tab_bytes : 0)) / per : 0;
   if (cap < 1024 && cap < B)  // no (useful) scratch: direct column-walk form
     return estep_evo_bsc_direct<T>(Y, ldY, idx, K, lpj, ws, cfg, sparsity, B, S, H, D, nsubs, stream);
   EvoParams ep;
@@ -368,17 +419,24 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
   const size_t wbytes = warp_buf_bytes<T>(dims) + align16((size_t)H * sizeof(T));
   // 8 warps per CTA, 3 CTAs per SM (one 24-warp CTA per SM in lockstep measured the same)
-  int wpb = 8;
+  int wpb = getenv("TVO_B200_WPB") ? atoi(getenv("TVO_B200_WPB")) : 8;
   while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmemFast) wpb >>= 1;
   TVO_REQUIRE(wbytes * wpb <= (size_t)kMaxSmemFast, "estep_evo_bsc: per-datapoint working set %zu B exceeds shared memory",
               wbytes);
   const size_t smem = wbytes * wpb;
-  auto kern = estep_evo_bsc_gram_kernel<T>;
+  static const bool lockstep = !getenv("TVO_B200_NO_LOCKSTEP");
+  auto kern = lockstep ? estep_evo_bsc_gram_kernel<T, true> : estep_evo_bsc_gram_kernel<T, false>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
   occ = max(occ, 1);
-  T *A = (T *)scratch;
+  T *A = (T *)scratch_a;
+  if (use_tab) {
+    FlipEntry *tab = (FlipEntry *)scratch;
+    flip_table_kernel<<<(H + 1 + 127) / 128, 128, 0, st>>>(tab, sparsity, H, ep.p_bf);
+    TVO_AFTER_LAUNCH("flip_table");
+    ep.flip_tab = tab;
+  }
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
     const int Bc = (int)min(cap, B - c0);
     rc = gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, A, Bc, H, D);
@@ -439,7 +497,9 @@ using namespace tvo;
 
 extern "C" {
 int64_t tvo_bsc_stats_len(int32_t H, int32_t D) { return (int64_t)H * D + (int64_t)H * H + H + 3; }
-int64_t tvo_bsc_estep_scratch_bytes(int64_t B, int32_t H, int32_t is_f64) { return B * (int64_t)H * (is_f64 ? 8 : 4); }
+int64_t tvo_bsc_estep_scratch_bytes(int64_t B, int32_t H, int32_t is_f64) {
+  return B * (int64_t)H * (is_f64 ? 8 : 4) + (int64_t)flip_table_bytes(H);
+}
 int64_t tvo_bsc_mstep_scratch_bytes(int64_t B, int32_t H, int32_t D, int32_t is_f64) {
   return B * ((int64_t)H * 8 + (is_f64 ? 0 : (int64_t)D * 8));
 }

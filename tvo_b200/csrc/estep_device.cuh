@@ -35,14 +35,17 @@ struct WarpBuf {
   int32_t *iscr;      // max(Scmax, 2*Sgen)
 };
 
+// keys (select) and fmask (mutation) are never live at the same time: one region
+__host__ __device__ inline size_t keys_region_bytes(const EstepDims &d) {
+  const size_t k = (size_t)(d.S + d.Snew) * 8, f = (size_t)d.Sgen * d.W64 * 8;
+  return align16(k > f ? k : f);
+}
+
 template <typename T>
 __host__ __device__ inline size_t warp_buf_bytes(const EstepDims &d) {
   size_t b = 0;
   b += align16((size_t)d.S * d.W64 * 8) + align16((size_t)d.Snew * d.W64 * 8) + align16((size_t)d.P * d.W64 * 8);
-  {  // keys (select) and fmask (mutation) are never live at the same time: one region
-    const size_t k = (size_t)(d.S + d.Snew) * 8, f = (size_t)d.Sgen * d.W64 * 8;
-    b += align16(k > f ? k : f);
-  }
+  b += keys_region_bytes(d);
   b += align16(d.need_fit ? (size_t)d.Scmax * 8 : 0);
   b += align16((size_t)(d.S + d.Snew) * sizeof(T));
   b += align16((size_t)(((d.S + 3) & ~3) + ((d.Snew + 3) & ~3)) * 4);  // hash_len(S, Snew)
@@ -62,10 +65,7 @@ __device__ inline WarpBuf<T> carve_warp_buf(unsigned char *p, const EstepDims &d
   p += align16((size_t)d.P * d.W64 * 8);
   w.keys = (uint64_t *)p;
   w.fmask = (uint64_t *)p;
-  {
-    const size_t k = (size_t)(d.S + d.Snew) * 8, f = (size_t)d.Sgen * d.W64 * 8;
-    p += align16(k > f ? k : f);
-  }
+  p += keys_region_bytes(d);
   w.dscr = (double *)p;
   p += align16(d.need_fit ? (size_t)d.Scmax * 8 : 0);
   w.lpj = (T *)p;
@@ -77,33 +77,109 @@ __device__ inline WarpBuf<T> carve_warp_buf(unsigned char *p, const EstepDims &d
 }
 
 // ------------------------------------------------------------------------------------ selection
-// batch_randparents (evo.py:436-451): first P entries of a uniform random permutation of the S_c
-// candidates, by a partial Fisher-Yates shuffle driven by u32 stream elements 0..P-1.
-__device__ inline void select_randparents(const uint64_t *cand, int S_c, int P, int W64, const Stream &st,
-                                          int32_t *perm, uint64_t *parents, int lane) {
-  // the P u32 draws come from ceil(P/4) Philox blocks: lanes compute them in parallel (32 blocks per
-  // round), lane 0 then runs the P dependent swaps reading the draws by shuffle
-  for (int i = lane; i < S_c; i += 32) perm[i] = i;
-  __syncwarp();
-  for (int i0 = 0; i0 < P; i0 += 128) {
-    const int nblk = (min(P - i0, 128) + 3) >> 2;
+// batch_randparents (evo.py:436-451): P distinct candidates in random order.  Candidate i gets the key
+// (r_i with its low `bits` bits replaced by i), r_i = u32 stream element i, bits = bit_length(S_c-1);
+// the parents are the candidates with the P smallest keys, in ascending key order (keys are unique, so
+// this is a uniform random P-permutation up to 2^-(32-bits) ties in the random part).  One register
+// per candidate, sorted by a warp bitonic network — no serial Fisher-Yates chain on one lane.
+__host__ __device__ inline int index_bits(int S_c) {
+  int b = 0;
+  while ((1 << b) < S_c) ++b;
+  return b;
+}
+
+template <int EPL>
+__device__ __forceinline__ void randparents_sort(int S_c, int P, int bits, const Stream &st, int32_t *chosen, int lane) {
+  constexpr int MP = 32 * EPL;
+  uint32_t key[EPL];
+  const uint32_t himask = ~((1u << bits) - 1u);
+  if (EPL >= 4) {
+#pragma unroll
+    for (int q = 0; q < EPL / 4; ++q) {
+      const int e0 = lane * EPL + 4 * q;
+      uint4 r = make_uint4(0, 0, 0, 0);
+      if (e0 < S_c) r = st.block(0, (uint32_t)(e0 >> 2));
+      key[4 * q + 0] = r.x;
+      if (EPL > 1) key[(4 * q + 1) % EPL] = r.y;
+      if (EPL > 2) key[(4 * q + 2) % EPL] = r.z;
+      if (EPL > 3) key[(4 * q + 3) % EPL] = r.w;
+    }
+  } else {
+    const int e0 = lane * EPL;
     uint4 r = make_uint4(0, 0, 0, 0);
-    if (lane < nblk) r = st.block(0, (uint32_t)((i0 >> 2) + lane));
-    const int iend = min(P, i0 + 128);
-    for (int i = i0; i < iend; ++i) {
-      const int src = (i - i0) >> 2, q = i & 3;
-      const uint32_t pick = q == 0 ? r.x : q == 1 ? r.y : q == 2 ? r.z : r.w;
-      const uint32_t ri = __shfl_sync(FULL, pick, src);
-      if (lane == 0) {
-        const int k = i + (int)randint_u32(ri, (uint32_t)(S_c - i));
-        const int32_t t = perm[i];
-        perm[i] = perm[k];
-        perm[k] = t;
+    if (e0 < S_c) r = st.block(0, (uint32_t)(e0 >> 2));
+    const int o = e0 & 3;  // EPL 1: any of 0..3; EPL 2: 0 or 2
+    key[0] = o == 0 ? r.x : o == 1 ? r.y : o == 2 ? r.z : r.w;
+    if (EPL == 2) key[EPL - 1] = o == 0 ? r.y : r.w;
+  }
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    key[r] = e < S_c ? ((key[r] & himask) | (uint32_t)e) : 0xFFFFFFFFu;
+  }
+#pragma unroll 1
+  for (int k = 2; k <= MP; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j >= EPL; j >>= 1) {  // partner in another lane
+      const int lm = j / EPL;
+#pragma unroll
+      for (int r = 0; r < EPL; ++r) {
+        const int e = lane * EPL + r;
+        const uint32_t o = __shfl_xor_sync(FULL, key[r], lm);
+        const bool take_min = ((e & j) == 0) == ((e & k) == 0);
+        key[r] = take_min ? min(key[r], o) : max(key[r], o);
+      }
+    }
+#pragma unroll
+    for (int jj = EPL >> 1; jj > 0; jj >>= 1) {  // partner in the same lane
+      if (jj < k) {
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+          if ((r & jj) == 0) {
+            const int e = lane * EPL + r;
+            const bool asc = (e & k) == 0;
+            const uint32_t lo = min(key[r], key[r ^ jj]), hi = max(key[r], key[r ^ jj]);
+            key[r] = asc ? lo : hi;
+            key[r ^ jj] = asc ? hi : lo;
+          }
+        }
       }
     }
   }
-  __syncwarp();
-  for (int t = lane; t < P * W64; t += 32) parents[t] = cand[perm[t / W64] * W64 + t % W64];
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    if (e < P) chosen[e] = (int32_t)(key[r] & ~himask);
+  }
+}
+
+__device__ inline void select_randparents(const uint64_t *cand, int S_c, int P, int W64, const Stream &st,
+                                          int32_t *scr, uint64_t *parents, int lane) {
+  const int bits = index_bits(S_c);
+  if (S_c <= 256) {
+    if (S_c <= 32)
+      randparents_sort<1>(S_c, P, bits, st, scr, lane);
+    else if (S_c <= 64)
+      randparents_sort<2>(S_c, P, bits, st, scr, lane);
+    else if (S_c <= 128)
+      randparents_sort<4>(S_c, P, bits, st, scr, lane);
+    else
+      randparents_sort<8>(S_c, P, bits, st, scr, lane);
+    __syncwarp();
+    for (int t = lane; t < P * W64; t += 32) parents[t] = cand[scr[t / W64] * W64 + t % W64];
+  } else {  // large candidate sets: rank every key by counting (same result, O(S_c^2 / 32) per datapoint)
+    const uint32_t himask = ~((1u << bits) - 1u);
+    for (int i = lane; i < S_c; i += 32) scr[i] = (int32_t)((st.u32(0, (uint32_t)i) & himask) | (uint32_t)i);
+    __syncwarp();
+    for (int i0 = 0; i0 < S_c; i0 += 32) {
+      const int i = i0 + lane;
+      const uint32_t ki = i < S_c ? (uint32_t)scr[i] : 0xFFFFFFFFu;
+      int rank = 0;
+      for (int j = 0; j < S_c; ++j) rank += ((uint32_t)scr[j] < ki) ? 1 : 0;
+      if (i < S_c && rank < P)
+        for (int w = 0; w < W64; ++w) parents[rank * W64 + w] = cand[i * W64 + w];
+    }
+  }
   __syncwarp();
 }
 
@@ -220,29 +296,64 @@ __device__ __constant__ double kInvTab[65] = {
     1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49, 1.0 / 50, 1.0 / 51, 1.0 / 52, 1.0 / 53, 1.0 / 54,
     1.0 / 55, 1.0 / 56, 1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61, 1.0 / 62, 1.0 / 63, 1.0 / 64};
 
-// k ~ Binomial(n, p) by CDF inversion of u (oracle/evo.py:binomial_inverse), +,*,/ only, no FMA
-__device__ __forceinline__ int binomial_inverse(double u, int n, double p) {
-  if (n == 0 || !(p > 0.0)) return 0;
-  if (p >= 1.0) return n;
+// k ~ Binomial(n, p) by CDF inversion of u (oracle/evo.py:binomial_inverse), +,*,/ only, no FMA.
+// Split into the part that depends on (n, p) only — FlipClass: pmf(0) = q^n, r = p/q and the special
+// cases — and the short CDF walk that consumes u.  For sparseflip (n, p) are functions of the parent's
+// popcount a alone, so the fused E-step reads FlipClass from a table built once per launch
+// (flip_table_kernel) instead of redoing 2 divisions and a ~log2(H)-step power per child and class.
+struct FlipClass {
+  double pmf0, r;
+  int32_t kconst;  // >= 0: the result regardless of u;  -1: walk the CDF
+  int32_t flip;    // p > 1/2: sampled as n - Binomial(n, 1-p)
+};
+struct FlipEntry {
+  FlipClass c[2];  // [0]: the H-a zero bits with p0, [1]: the a one bits with p1
+};
+
+__device__ __forceinline__ FlipClass flip_class_make(int n, double p) {
+  FlipClass e;
+  e.pmf0 = 0.0;
+  e.r = 0.0;
+  e.flip = 0;
+  e.kconst = -1;
+  if (n == 0 || !(p > 0.0)) {
+    e.kconst = 0;
+    return e;
+  }
+  if (p >= 1.0) {
+    e.kconst = n;
+    return e;
+  }
   const bool flip = p > 0.5;
   if (flip) p = __dsub_rn(1.0, p);
   const double q = __dsub_rn(1.0, p);
-  double pmf = pow_int(q, n);
-  int k;
+  const double pmf = pow_int(q, n);
   if (pmf == 0.0) {
-    k = (int)__dmul_rn((double)n, p);
-  } else {
-    const double r = __ddiv_rn(p, q);
-    double c = pmf;
-    k = 0;
-    while (u >= c && k < n) {
-      const double t = __dmul_rn(__dmul_rn(pmf, (double)(n - k)), r);
-      pmf = k + 1 <= 64 ? __dmul_rn(t, kInvTab[k + 1]) : __ddiv_rn(t, (double)(k + 1));
-      c = __dadd_rn(c, pmf);
-      ++k;
-    }
+    const int k = (int)__dmul_rn((double)n, p);
+    e.kconst = flip ? n - k : k;
+    return e;
   }
-  return flip ? n - k : k;
+  e.pmf0 = pmf;
+  e.r = __ddiv_rn(p, q);
+  e.flip = flip ? 1 : 0;
+  return e;
+}
+
+__device__ __forceinline__ int flip_class_sample(const FlipClass &e, double u, int n) {
+  if (e.kconst >= 0) return e.kconst;
+  double pmf = e.pmf0, c = pmf;
+  int k = 0;
+  while (u >= c && k < n) {
+    const double t = __dmul_rn(__dmul_rn(pmf, (double)(n - k)), e.r);
+    pmf = k + 1 <= 64 ? __dmul_rn(t, kInvTab[k + 1]) : __ddiv_rn(t, (double)(k + 1));
+    c = __dadd_rn(c, pmf);
+    ++k;
+  }
+  return e.flip ? n - k : k;
+}
+
+__device__ __forceinline__ int binomial_inverse(double u, int n, double p) {
+  return flip_class_sample(flip_class_make(n, p), u, n);
 }
 
 // position of the (i+1)-th set bit of a 64-bit mask (i < popcount), branch-light binary search
@@ -289,7 +400,7 @@ __device__ __forceinline__ int nth_remaining(const uint64_t *src, const uint64_t
 // `fmask` (nchild x W64 words) collects the flips; dst = src ^ fmask, so src == dst (C == 1) is fine.
 __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int W64, int H, double sparsity,
                                          double p_bf, const Stream &st0, const Stream &st1, uint64_t *fmask,
-                                         uint64_t *dst, int lane) {
+                                         uint64_t *dst, int lane, const FlipEntry *__restrict__ tab = nullptr) {
   const double Hf = (double)H;
   const double crowd = __dmul_rn(sparsity, Hf);
   const int nchild = P * C;
@@ -303,15 +414,23 @@ __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int 
         a += __popcll(par[w]);
         fm[w] = 0;
       }
-      double p0, p1;
-      sparseflip_probs((double)a, Hf, crowd, p_bf, p0, p1);
+      double p0 = 0.0, p1 = 0.0;
+      if (!tab) sparseflip_probs((double)a, Hf, crowd, p_bf, p0, p1);
 #pragma unroll 1
       for (int cls = 0; cls < 2; ++cls) {
         const int n = cls ? a : H - a;
-        const double pc = cls ? p1 : p0;
-        if (n == 0 || !(pc > 0.0)) continue;
+        FlipClass fc;
+        if (tab) {
+          const FlipClass *tp = &tab[a].c[cls];
+          fc.pmf0 = __ldg(&tp->pmf0);
+          fc.r = __ldg(&tp->r);
+          fc.kconst = __ldg(&tp->kconst);
+          fc.flip = __ldg(&tp->flip);
+        } else {
+          fc = flip_class_make(n, cls ? p1 : p0);
+        }
         const Stream &st = cls ? st1 : st0;
-        const int k = binomial_inverse(unit_double(st.u64((uint32_t)j, 0)), n, pc);
+        const int k = fc.kconst >= 0 ? fc.kconst : flip_class_sample(fc, unit_double(st.u64((uint32_t)j, 0)), n);
         if (k == 0) continue;
         const bool complement = 2 * k > n;  // draw the smaller of {flipped, not flipped}
         const int draws = k >= n ? 0 : (complement ? n - k : k);
@@ -365,7 +484,20 @@ struct EvoParams {
   double p_bf;
   uint2 key;
   uint32_t step, n_offset;
+  const FlipEntry *flip_tab;  // sparseflip: per-popcount table (flip_table_kernel) or nullptr = compute inline
 };
+
+// tab[a], a = 0..H: the two FlipClass entries of a parent with a active units
+static __global__ void flip_table_kernel(FlipEntry *tab, const double *__restrict__ sparsity_p, int H, double p_bf) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a > H) return;
+  const double Hf = (double)H;
+  double p0, p1;
+  sparseflip_probs((double)a, Hf, __dmul_rn(*sparsity_p, Hf), p_bf, p0, p1);
+  tab[a].c[0] = flip_class_make(H - a, p0);
+  tab[a].c[1] = flip_class_make(a, p1);
+}
+__host__ inline size_t flip_table_bytes(int H) { return (((size_t)(H + 1) * sizeof(FlipEntry)) + 255) & ~size_t(255); }
 
 __host__ inline int children_per_gen(int mut, int P, int C) { return mut >= TVO_MUT_CROSS ? P * (P - 1) : P * C; }
 
@@ -392,7 +524,7 @@ __device__ inline void evo_generation(const WarpBuf<T> &wb, const uint64_t *cand
       mutate_randflip(wb.parents, ep.P, ep.C, W64, H, st, wb.iscr, children, lane);
       break;
     case TVO_MUT_SPARSEFLIP:
-      mutate_sparseflip(wb.parents, ep.P, ep.C, W64, H, sparsity, ep.p_bf, s0, s1, wb.fmask, children, lane);
+      mutate_sparseflip(wb.parents, ep.P, ep.C, W64, H, sparsity, ep.p_bf, s0, s1, wb.fmask, children, lane, ep.flip_tab);
       break;
     default: {
       st.tag = make_tag(ep.step, gen, PUR_CROSS);
@@ -407,7 +539,7 @@ __device__ inline void evo_generation(const WarpBuf<T> &wb, const uint64_t *cand
         }
         __syncwarp();
       } else if (ep.mut == TVO_MUT_CROSS_SPARSEFLIP) {
-        mutate_sparseflip(children, nc, 1, W64, H, sparsity, ep.p_bf, s0, s1, wb.fmask, children, lane);
+        mutate_sparseflip(children, nc, 1, W64, H, sparsity, ep.p_bf, s0, s1, wb.fmask, children, lane, ep.flip_tab);
       }
     }
   }
