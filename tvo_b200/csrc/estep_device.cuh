@@ -665,23 +665,16 @@ __device__ __forceinline__ bool ranks_before(uint64_t kx, int ix, uint64_t ky, i
   return kx > ky || (kx == ky && ix < iy);
 }
 
-// Sort the M = S+Snew candidates best-first with a warp bitonic network (EPL elements per lane,
-// element e = lane*EPL + r; distances < EPL are register-local, larger ones use shuffles) and emit
-// the best S in ascending order.  iscr[pos] receives the source index of output position pos.
-template <typename T, int EPL>
-__device__ __forceinline__ int select_sorted(const WarpBuf<T> &wb, int S, int M, T *lpj_row, int lane) {
+// Warp bitonic network over (key, src) pairs, best-first; EPL elements per lane, element e =
+// lane*EPL + r; distances < EPL are register-local, larger ones use shuffles.  Runs the stages
+// k = k_first, 2 k_first, ..., 32*EPL:  k_first = 2 is a full sort, k_first = 32*EPL only merges a
+// bitonic sequence.  Stage loops are kept rolled (code size: the unrolled network is 1.3k instructions
+// per EPL and the fused kernels live or die by the instruction cache).
+template <int EPL>
+__device__ __forceinline__ void bitonic_network(uint64_t (&key)[EPL], int (&src)[EPL], int lane, int k_first) {
   constexpr int MP = 32 * EPL;
-  uint64_t key[EPL];
-  int src[EPL];
-#pragma unroll
-  for (int r = 0; r < EPL; ++r) {
-    const int e = lane * EPL + r;
-    key[r] = e < M ? wb.keys[e] : 0ull;
-    src[r] = e < M ? e : 0x7fffffff;
-  }
-  // stage loops are kept rolled (code size: the unrolled network was 1.3k instructions per EPL)
 #pragma unroll 1
-  for (int k = 2; k <= MP; k <<= 1) {
+  for (int k = k_first; k <= MP; k <<= 1) {
 #pragma unroll 1
     for (int j = k >> 1; j >= EPL; j >>= 1) {  // partner in another lane
       const int lm = j / EPL;
@@ -718,7 +711,90 @@ __device__ __forceinline__ int select_sorted(const WarpBuf<T> &wb, int S, int M,
       }
     }
   }
-  int nsub = 0;
+}
+
+constexpr int kPadSrc = 0x7fffffff;  // padding element: key 0 (below every real key), ranks last
+
+// Sort the ns surviving children (indices in `slist`, keys in wb.keys) best-first, in place.
+template <typename T, int EPL>
+__device__ __forceinline__ void sort_survivors(const WarpBuf<T> &wb, int32_t *slist, int ns, int lane) {
+  uint64_t key[EPL];
+  int src[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    src[r] = e < ns ? slist[e] : kPadSrc;
+    key[r] = e < ns ? wb.keys[src[r]] : 0ull;
+  }
+  __syncwarp();
+  bitonic_network<EPL>(key, src, lane, 2);
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    if (e < ns) slist[e] = src[r];
+  }
+  __syncwarp();
+}
+
+// Top-S of old + new, best-first in registers, written out ascending.  Three cheaper pieces instead of
+// one sort of all M = S + Snew candidates:
+//   1. sort the S old states (network of 32*EPL >= S elements);
+//   2. only children that beat the worst old state can enter the top S: compact them by ballot (late
+//      in training that is a handful of the Snew children) and sort them;
+//   3. C[e] = better(old[e], survivor[MP-1-e]) is bitonic and holds the top MP: one merge stage.
+// Returns false (nothing written) when more than 256 children survive: the caller ranks by counting.
+template <typename T, int EPL>
+__device__ __forceinline__ bool select_merge(const WarpBuf<T> &wb, int S, int Snew, T *lpj_row, int lane, int &nsub) {
+  constexpr int MP = 32 * EPL;
+  uint64_t key[EPL];
+  int src[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    key[r] = e < S ? wb.keys[e] : 0ull;
+    src[r] = e < S ? e : kPadSrc;
+  }
+  bitonic_network<EPL>(key, src, lane, 2);
+  uint64_t wkey = 0;
+#pragma unroll
+  for (int r = 0; r < EPL; ++r)
+    if (((S - 1) % EPL) == r) wkey = key[r];
+  wkey = __shfl_sync(FULL, wkey, (S - 1) / EPL);
+  int32_t *slist = (int32_t *)wb.hash;  // free after mark_redundant; holds >= S + Snew ints
+  int ns = 0;
+  for (int c0 = 0; c0 < Snew; c0 += 32) {
+    const int c = c0 + lane;
+    const bool keep = c < Snew && wb.keys[S + c] > wkey;  // ties go to the old state (lower index)
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) slist[ns + __popc(m & ((1u << lane) - 1u))] = S + c;
+    ns += __popc(m);
+  }
+  __syncwarp();
+  if (ns > 256) return false;
+  if (ns > 0) {
+    if (ns <= 32)
+      sort_survivors<T, 1>(wb, slist, ns, lane);
+    else if (ns <= 64)
+      sort_survivors<T, 2>(wb, slist, ns, lane);
+    else if (ns <= 128)
+      sort_survivors<T, 4>(wb, slist, ns, lane);
+    else
+      sort_survivors<T, 8>(wb, slist, ns, lane);
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) {
+      const int bi = MP - 1 - (lane * EPL + r);
+      if (bi < ns) {
+        const int bs = slist[bi];
+        const uint64_t bk = wb.keys[bs];
+        if (ranks_before(bk, bs, key[r], src[r])) {
+          key[r] = bk;
+          src[r] = bs;
+        }
+      }
+    }
+    bitonic_network<EPL>(key, src, lane, MP);
+  }
+  nsub = 0;
 #pragma unroll
   for (int r = 0; r < EPL; ++r) {
     const int e = lane * EPL + r;
@@ -729,7 +805,7 @@ __device__ __forceinline__ int select_sorted(const WarpBuf<T> &wb, int S, int M,
       nsub += (src[r] >= S) ? 1 : 0;
     }
   }
-  return nsub;
+  return true;
 }
 
 template <typename T>
@@ -739,15 +815,16 @@ __device__ inline int select_topS(const WarpBuf<T> &wb, int S, int Snew, int W64
   for (int i = lane; i < M; i += 32) wb.keys[i] = sort_key((double)wb.lpj[i]);
   __syncwarp();
   int nsub = 0;
-  if (M <= 32) {
-    nsub = select_sorted<T, 1>(wb, S, M, lpj_row, lane);
-  } else if (M <= 64) {
-    nsub = select_sorted<T, 2>(wb, S, M, lpj_row, lane);
-  } else if (M <= 128) {
-    nsub = select_sorted<T, 4>(wb, S, M, lpj_row, lane);
-  } else if (M <= 256) {
-    nsub = select_sorted<T, 8>(wb, S, M, lpj_row, lane);
-  } else {
+  bool done = false;
+  if (S <= 32)
+    done = select_merge<T, 1>(wb, S, Snew, lpj_row, lane, nsub);
+  else if (S <= 64)
+    done = select_merge<T, 2>(wb, S, Snew, lpj_row, lane, nsub);
+  else if (S <= 128)
+    done = select_merge<T, 4>(wb, S, Snew, lpj_row, lane, nsub);
+  else if (S <= 256)
+    done = select_merge<T, 8>(wb, S, Snew, lpj_row, lane, nsub);
+  if (!done) {
     for (int i0 = 0; i0 < M; i0 += 32) {  // rank by counting
       const int i = i0 + lane;
       const uint64_t ki = i < M ? wb.keys[i] : 0;
