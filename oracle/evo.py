@@ -178,22 +178,41 @@ def binomial_inverse(u, n, p):
 INV_TAB = [0.0] + [1.0 / k for k in range(1, 65)]  # 1/(k+1) factors of the pmf recurrence
 
 
-def _choose_positions(k, n, seed, n_glob, slot, tag):
-    """Indices (into the ascending candidate list) of k of n candidates, uniform without replacement:
-    draw i picks the t-th REMAINING candidate, t = randint(n - i) from u32 stream element 4 + i.
-    For k > n/2 the n-k candidates that are NOT flipped are drawn instead."""
+def _choose_positions(k, cand, H, seed, n_glob, slot, tag):
+    """Absolute positions of k of the candidates ``cand`` (ascending), uniform without replacement.
+    For k > n/2 the n-k candidates that are NOT flipped are drawn instead.  u32 stream elements
+    4, 5, ... of the sub-stream are consumed one per attempt:
+
+      dense class (2 n >= H): rejection — pos = randint(H) is accepted when it is a candidate that
+          has not been drawn yet (after 64 + 64*draws attempts the sparse rule finishes the job);
+      sparse class: draw picks the t-th REMAINING candidate, t = randint(#remaining)."""
+    n = len(cand)
     if k <= 0:
         return []
     if k >= n:
-        return list(range(n))
+        return list(cand)
     complement = 2 * k > n
     draws = n - k if complement else k
-    remaining = list(range(n))
+    remaining = list(cand)
     picked = []
-    for i in range(draws):
-        r = int(px.stream_u32(seed, np.uint32(n_glob), np.uint32(slot), tag, np.uint32(4 + i)))
-        picked.append(remaining.pop((r * (n - i)) >> 32))
-    return sorted(set(range(n)) - set(picked)) if complement else picked
+    t = 0
+
+    def u32():
+        nonlocal t
+        r = int(px.stream_u32(seed, np.uint32(n_glob), np.uint32(slot), tag, np.uint32(4 + t)))
+        t += 1
+        return r
+
+    if 2 * n >= H:
+        cap = 64 + 64 * draws
+        while len(picked) < draws and t < cap:
+            pos = (u32() * H) >> 32
+            if pos in remaining:
+                remaining.remove(pos)
+                picked.append(pos)
+    while len(picked) < draws:
+        picked.append(remaining.pop((u32() * len(remaining)) >> 32))
+    return sorted(remaining) if complement else picked
 
 
 def sparseflip(parents, C, sparsity, p_bf, n_glob, seed, step, gen):
@@ -217,8 +236,8 @@ def sparseflip(parents, C, sparsity, p_bf, n_glob, seed, step, gen):
             for cls, tag, cand, prob in ((0, tag0, zeros, p0[n, p]), (1, tag1, ones, p1[n, p])):
                 u = float(px.u64_to_unit_double(px.stream_u64(seed, np.uint32(n_glob[n]), np.uint32(j), tag, np.uint32(0))))
                 k = binomial_inverse(u, len(cand), prob)
-                for i in _choose_positions(k, len(cand), seed, n_glob[n], j, tag):
-                    children[n, j, cand[i]] ^= 1
+                for h in _choose_positions(k, cand, H, seed, n_glob[n], j, tag):
+                    children[n, j, h] ^= 1
     return children
 
 

@@ -395,8 +395,9 @@ __device__ __forceinline__ int nth_remaining(const uint64_t *src, const uint64_t
 // batch_sparseflip (evo.py:282-331): child j = parent j/C with every bit flipped independently with
 // probability p1 if the bit is set in the parent, p0 otherwise.  Sampled exactly as: number of flips
 // among the zero bits ~ Binomial(H-a, p0), among the one bits ~ Binomial(a, p1); positions = uniform
-// subset drawn without replacement (draw i = the t-th remaining candidate).  One LANE per child, one
-// Philox block for the two counts plus one per 4 flips, instead of H uniforms per child.
+// subset drawn without replacement (dense class, 2n >= H: rejection over all H positions; sparse class:
+// draw = the t-th remaining candidate; one u32 per attempt).  One LANE per child, one Philox block for
+// each count plus one per 4 attempts, instead of H uniforms per child.
 // `fmask` (nchild x W64 words) collects the flips; dst = src ^ fmask, so src == dst (C == 1) is fine.
 __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int W64, int H, double sparsity,
                                          double p_bf, const Stream &st0, const Stream &st1, uint64_t *fmask,
@@ -435,10 +436,28 @@ __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int 
         const bool complement = 2 * k > n;  // draw the smaller of {flipped, not flipped}
         const int draws = k >= n ? 0 : (complement ? n - k : k);
         uint4 r = make_uint4(0, 0, 0, 0);
-        for (int i = 0; i < draws; ++i) {
-          if ((i & 3) == 0) r = st.block((uint32_t)j, 1 + (i >> 2));
-          const uint32_t ri = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-          const int pos = nth_remaining(par, fm, W64, H, cls, (int)randint_u32(ri, (uint32_t)(n - i)));
+        int got = 0;
+        uint32_t t = 0;  // u32 stream elements 4 + t, one per attempt
+        if (2 * n >= H) {  // dense class: rejection sampling over all H positions
+          const uint32_t cap = 64u + 64u * (uint32_t)draws;
+          while (got < draws && t < cap) {
+            if ((t & 3) == 0) r = st.block((uint32_t)j, 1 + (t >> 2));
+            const uint32_t ri = (t & 3) == 0 ? r.x : (t & 3) == 1 ? r.y : (t & 3) == 2 ? r.z : r.w;
+            ++t;
+            const int pos = (int)randint_u32(ri, (uint32_t)H);
+            const uint64_t bit = 1ull << (pos & 63);
+            const uint64_t pw = par[pos >> 6], fw = fm[pos >> 6];
+            if (((pw & bit) != 0) == (cls != 0) && !(fw & bit)) {
+              fm[pos >> 6] = fw | bit;
+              ++got;
+            }
+          }
+        }
+        for (; got < draws; ++got) {  // sparse class: the idx-th remaining candidate
+          if ((t & 3) == 0) r = st.block((uint32_t)j, 1 + (t >> 2));
+          const uint32_t ri = (t & 3) == 0 ? r.x : (t & 3) == 1 ? r.y : (t & 3) == 2 ? r.z : r.w;
+          ++t;
+          const int pos = nth_remaining(par, fm, W64, H, cls, (int)randint_u32(ri, (uint32_t)(n - got)));
           fm[pos >> 6] |= 1ull << (pos & 63);
         }
         if (k >= n || complement) {  // flip every candidate of the class that was NOT drawn
@@ -662,7 +681,18 @@ __device__ inline void mark_redundant(const WarpBuf<T> &wb, int S, int Snew, int
 // global memory and returns the number of selected children (warp-uniform).
 // "x ranks before y": larger key first, ties -> lower concatenated index first
 __device__ __forceinline__ bool ranks_before(uint64_t kx, int ix, uint64_t ky, int iy) {
-  return kx > ky || (kx == ky && ix < iy);
+  // (kx, ~ix) > (ky, ~iy) as one 96-bit unsigned compare: Y - X borrows.  The low word ~iy - ~ix equals
+  // ix - iy and borrows iff ix < iy, so the indices enter the chain un-negated (both are >= 0).
+  uint32_t b;
+  asm("{\n\t.reg .u32 t;\n\t"
+      "sub.cc.u32 t, %1, %2;\n\t"
+      "subc.cc.u32 t, %3, %4;\n\t"
+      "subc.cc.u32 t, %5, %6;\n\t"
+      "subc.u32 %0, 0, 0;\n\t}"
+      : "=r"(b)
+      : "r"((uint32_t)ix), "r"((uint32_t)iy), "r"((uint32_t)ky), "r"((uint32_t)kx), "r"((uint32_t)(ky >> 32)),
+        "r"((uint32_t)(kx >> 32)));
+  return b != 0;
 }
 
 // Warp bitonic network over (key, src) pairs, best-first; EPL elements per lane, element e =
