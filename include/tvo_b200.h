@@ -76,6 +76,14 @@ const char *tvo_last_error(void);
 /* number of kernels launched by this library in the calling process since load / last reset */
 int64_t tvo_launch_count(void);
 void tvo_reset_launch_count(void);
+/* Opt-in timing of the dominant kernels (measurement aid, no reference counterpart): while enabled, every
+ * launch of a timed kernel is bracketed by a cudaEvent pair on the stream it is launched on.
+ * tvo_kernel_timing_enable(on) also discards earlier samples; tvo_kernel_timing_read synchronises the
+ * recorded events and returns the summed duration and the number of launches of kernel `which`. */
+#define TVO_TIMED_ESTEP_EVO_BSC 1 /* estep_evo_bsc_gram_kernel / estep_evo_bsc_kernel */
+#define TVO_TIMED_BSC_MSTEP 2     /* bsc_mstep_kernel */
+void tvo_kernel_timing_enable(int32_t on);
+int tvo_kernel_timing_read(int32_t which, double *total_ms, int64_t *launches);
 int tvo_device_sm_count(int *out);
 
 /* ---- state layout: replaces `states.to(dtype=...)` casts (bsc.py:102, noisyor.py:78) ---- */

@@ -42,6 +42,8 @@ _PROTOS = {
     "tvo_last_error": [],
     "tvo_launch_count": [],
     "tvo_reset_launch_count": [],
+    "tvo_kernel_timing_enable": [_I32],
+    "tvo_kernel_timing_read": [_I32, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
     "tvo_device_sm_count": [C.POINTER(C.c_int)],
     "tvo_pack_states": [_P, _P, _I64, _I32, _P],
     "tvo_unpack_states": [_P, _P, _I64, _I32, _P],
@@ -89,6 +91,7 @@ _RESTYPES = {
     "tvo_last_error": C.c_char_p,
     "tvo_launch_count": _I64,
     "tvo_reset_launch_count": None,
+    "tvo_kernel_timing_enable": None,
     "tvo_bsc_theta_ws_bytes": _I64,
     "tvo_bsc_stats_len": _I64,
     "tvo_bsc_estep_scratch_bytes": _I64,
@@ -167,3 +170,17 @@ def launch_count():
 
 def reset_launch_count():
     lib().tvo_reset_launch_count()
+
+
+TIMED_ESTEP_EVO_BSC, TIMED_BSC_MSTEP = 1, 2
+
+
+def kernel_timing_enable(on=True):
+    lib().tvo_kernel_timing_enable(1 if on else 0)
+
+
+def kernel_timing_read(which):
+    """(total ms, launches) of timed kernel `which` since kernel_timing_enable; synchronises its events."""
+    ms, n = C.c_double(0.0), C.c_int64(0)
+    check(lib().tvo_kernel_timing_read(which, C.byref(ms), C.byref(n)), "tvo_kernel_timing_read")
+    return float(ms.value), int(n.value)

@@ -215,8 +215,11 @@ int launch_estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *
   occ = max(occ, 1);
   const int64_t want = (B + wpb - 1) / wpb;
   const int grid = (int)max((int64_t)1, min(want, (int64_t)sm_count() * occ));
+  void *tok;
+  kernel_timing_begin(TVO_TIMED_ESTEP_EVO_BSC, stream, &tok);
   kern<<<grid, wpb * 32, smem, stream>>>(Y, ldY, idx, K, lpj, ws, ep, sparsity, dims, B, H, D,
                                          (unsigned long long *)nsubs);
+  kernel_timing_end(tok, stream);
   TVO_AFTER_LAUNCH("estep_evo_bsc");
   return TVO_OK;
 }

@@ -442,8 +442,11 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
     rc = gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, A, Bc, H, D);
     if (rc) return rc;
     const int grid = (int)max((int64_t)1, min((int64_t)(Bc + wpb - 1) / wpb, (int64_t)sm_count() * occ));
+    void *tok;
+    kernel_timing_begin(TVO_TIMED_ESTEP_EVO_BSC, st, &tok);
     kern<<<grid, wpb * 32, smem, st>>>(Y + c0 * ldY, ldY, A, idx ? idx + c0 : nullptr, c0, K, lpj, ws, ep, sparsity, dims,
                                        Bc, H, D, (unsigned long long *)nsubs);
+    kernel_timing_end(tok, st);
     TVO_AFTER_LAUNCH("estep_evo_bsc_gram");
   }
   return TVO_OK;
@@ -480,8 +483,11 @@ int bsc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, in
     double *E = (double *)scratch;
     double *Yd = sizeof(T) == 8 ? nullptr : E + (size_t)Bc * H;
     const int grid = (int)max((int64_t)1, min((int64_t)(Bc + wpb - 1) / wpb, (int64_t)sm_count() * occ));
+    void *tok;
+    kernel_timing_begin(TVO_TIMED_BSC_MSTEP, st, &tok);
     kern<<<grid, wpb * 32, smem, st>>>(Y + c0 * ldY, ldY, idx ? idx + c0 : nullptr, c0, K, k_stride_n, lpj, lpj_stride_n, ws,
                                        stats, E, Yd, Bc, S, H, D, exact, wbytes);
+    kernel_timing_end(tok, st);
     TVO_AFTER_LAUNCH("bsc_mstep");
     // WpT (H x D, row-major) += E^T (H x Bc) * Y (Bc x D)     (bsc.py:145,153)
     const double *Yp = sizeof(T) == 8 ? (const double *)(Y + c0 * ldY) : Yd;

@@ -10,6 +10,10 @@ namespace tvo {
 int set_error(int code, const char *fmt, ...);  // capi.cu; returns `code`
 void count_launch(int n = 1);
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
+// opt-in per-kernel timing (tvo_kernel_timing_enable): event pair on the launching stream
+bool kernel_timing_on();
+void kernel_timing_begin(int which, cudaStream_t st, void **token);
+void kernel_timing_end(void *token, cudaStream_t st);
 
 #define TVO_REQUIRE(cond, ...)                                          \
   do {                                                                  \
