@@ -278,6 +278,133 @@ nor_mstep_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *__re
   }
 }
 
+// M-step, register-stationary form (Dpad in {32,64,128,256}).  A CTA of 512 threads owns the h-tile
+// [h0, h0 + Ht), Ht = 8 * (512 / Dpad): thread (hg, d) keeps the Btilde / Ctilde accumulators of its 8
+// consecutive h and its column d in REGISTERS together with 1 - W_dh and its reciprocal, so the
+// datapoint loop has no atomics and no accumulator traffic at all.  Per datapoint:
+//   phase 1: Q_sd = prod_{h in s} (1 - W_dh) for all (s, d) into shared memory (threads over (s, d));
+//   phase 2: every thread walks the S states; the byte of the state covering its 8 h is warp-uniform,
+//            so warps whose h-group is inactive in a state skip it in 4 instructions.
+constexpr int kNorHpt = 8;
+// a / b of the accumulation terms: IEEE division in fp64; in the stated fp32 mode the 2-ulp MUFU.RCP form
+// (the terms carry 1e-4 tolerance and there are 2 S |s| D of them per datapoint)
+__device__ __forceinline__ double nor_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float nor_div(float a, float b) { return __fdividef(a, b); }
+template <typename T>
+__global__ void __launch_bounds__(512, 2)
+nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx,
+                     const uint64_t *__restrict__ K, int64_t k_stride_n, const T *__restrict__ lpj, int64_t lpj_stride_n,
+                     const void *ws, double *__restrict__ stats, int64_t B, int S, int H, int D) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const NorTheta<T> th = nor_theta_view<T>(ws, H, D);
+  const int W64 = n_words(H), Dpad = th.Dpad;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int HG = 512 / Dpad, Ht = kNorHpt * HG;
+  const int d = tid % Dpad, hg = tid / Dpad;
+  const int h0 = blockIdx.y * Ht;          // first h of the tile (multiple of 8)
+  const int hb = h0 + hg * kNorHpt;        // first h of this thread
+  T *Qsm = (T *)smem_raw;                                           // S x Dpad
+  double *q = (double *)(smem_raw + align16((size_t)S * Dpad * sizeof(T)));  // S
+  uint64_t *Ksm = (uint64_t *)(q + S);                              // S x W64
+  __shared__ double red[2];
+  double accB[kNorHpt], accC[kNorHpt];  // the only long-lived per-thread state (32 registers)
+#pragma unroll
+  for (int j = 0; j < kNorHpt; ++j) {
+    accB[j] = 0.0;
+    accC[j] = 0.0;
+  }
+  const T *Wcol = th.W1mT + (size_t)min(hb, H - 1) * Dpad + d;  // 1 - W_dh of this thread's h (L1-resident)
+  double pi_acc = 0.0, accF = 0.0, accN = 0.0;  // pi: thread tid < Ht owns h0 + tid
+  const T eps = (T)kNorEps;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const int64_t row = idx ? idx[b] : b;
+    const T *l = lpj + row * lpj_stride_n;
+    __syncthreads();  // previous datapoint fully consumed
+    for (int t = tid; t < S * W64; t += 512) Ksm[t] = K[row * k_stride_n + t];
+    if (tid < 32) {  // softmax weights by warp 0 (lpj2pjc, _utils.py:182-191)
+      double mx = -INFINITY;
+      for (int s = lane; s < S; s += 32) mx = fmax(mx, (double)l[s]);
+      mx = warp_max(mx);
+      double se = 0.0;
+      for (int s = lane; s < S; s += 32) {
+        const double e = exp((double)l[s] - mx);
+        q[s] = e;
+        se += e;
+      }
+      se = warp_sum(se);
+      for (int s = lane; s < S; s += 32) q[s] = q[s] / se;  // q_s, normalised once
+      if (lane == 0) red[1] = mx + log(se);
+    }
+    __syncthreads();
+    if (tid == 0 && blockIdx.y == 0) {
+      accF += red[1] + th.hdr->prior_sum;
+      accN += 1.0;
+    }
+    // phase 1: Q_sd over ALL active h of the state (noisyor.py:123-124), ascending h
+    for (int s = hg; s < S; s += HG) {
+      const uint64_t *st = Ksm + (size_t)s * W64;
+      T Q = T(1);
+      for (int w = 0; w < W64; ++w) {
+        uint64_t word = st[w];
+        while (word) {
+          const int h = (w << 6) + __ffsll((long long)word) - 1;
+          word &= word - 1;
+          Q *= __ldg(th.W1mT + (size_t)h * Dpad + d);
+        }
+      }
+      Qsm[(size_t)s * Dpad + d] = Q;
+    }
+    if (tid < Ht && h0 + tid < H) {  // new_pi += <s_h>  (noisyor.py:117)
+      const int h = h0 + tid;
+      double e = 0.0;
+      for (int s = 0; s < S; ++s)
+        if ((Ksm[s * W64 + (h >> 6)] >> (h & 63)) & 1ull) e += q[s];
+      pi_acc += e;
+    }
+    __syncthreads();
+    // phase 2: Btilde, Ctilde (noisyor.py:121-132) for this thread's 8 h and column d
+    if (hb < H) {
+      const T ym1 = (d < D ? (T)Y[b * ldY + d] : T(1)) - T(1);
+      const int sh = hb & 63;
+      const uint64_t *kp = Ksm + (hb >> 6);
+      const T *qp = Qsm + d;
+      for (int s = 0; s < S; ++s, kp += W64, qp += Dpad) {
+        const uint32_t m = (uint32_t)(*kp >> sh) & 0xFFu;
+        if (m == 0) continue;  // warp-uniform
+        const double qs = q[s];
+        const T Q = *qp;
+        const T omq = T(1) - Q;
+#pragma unroll
+        for (int j = 0; j < kNorHpt; ++j) {
+          if ((m >> j) & 1u) {
+            const T Ws = __ldg(Wcol + j * Dpad);
+            const T Bv = nor_div(T(1), Ws * omq + eps);
+            const T Cv = nor_div(Bv * Q, Ws);
+            accB[j] += qs * (double)(Bv * ym1);
+            accC[j] += qs * (double)Cv;
+          }
+        }
+      }
+    }
+  }
+  const size_t HD = (size_t)H * D;
+  if (d < D) {
+#pragma unroll
+    for (int j = 0; j < kNorHpt; ++j) {
+      const int h = hb + j;
+      if (h < H) {
+        if (accB[j] != 0.0) atomicAdd(stats + (size_t)h * D + d, accB[j]);
+        if (accC[j] != 0.0) atomicAdd(stats + HD + (size_t)h * D + d, accC[j]);
+      }
+    }
+  }
+  if (tid < Ht && h0 + tid < H && pi_acc != 0.0) atomicAdd(stats + 2 * HD + h0 + tid, pi_acc);
+  if (tid == 0 && accN != 0.0) {
+    atomicAdd(stats + 2 * HD + H, accN);
+    atomicAdd(stats + 2 * HD + H + 1, accF);
+  }
+}
+
 // ------------------------------------------------------------------------------------ host side
 template <typename T>
 int nor_prepare(const T *W, const T *pies, int H, int D, void *ws, void *stream) {
@@ -323,6 +450,21 @@ int nor_mstep(const uint8_t *Y, int64_t ldY, const int64_t *idx, const uint64_t 
   TVO_REQUIRE(B >= 0 && S > 0 && H > 0 && D > 0, "noisyor_mstep: bad sizes");
   if (B == 0) return TVO_OK;
   const int Dpad = nor_dpad(D), W64 = n_words(H);
+  if (Dpad <= 256 && 512 % Dpad == 0) {  // register-stationary accumulators
+    const size_t smem2 = align16((size_t)S * Dpad * sizeof(T)) + (size_t)S * 8 + (size_t)S * W64 * 8;
+    if (smem2 <= 100 * 1024) {
+      const int Ht = kNorHpt * (512 / Dpad), ntile = (H + Ht - 1) / Ht;
+      auto kern2 = nor_mstep_reg_kernel<T>;
+      TVO_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      int occ2 = 1;
+      TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, 512, smem2));
+      const int gx2 = (int)max((int64_t)1, min(B, (int64_t)max(1, sm_count() * max(occ2, 1) / ntile)));
+      kern2<<<dim3(gx2, ntile), 512, smem2, (cudaStream_t)stream>>>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, ws, stats,
+                                                                    B, S, H, D);
+      TVO_AFTER_LAUNCH("noisyor_mstep_reg");
+      return TVO_OK;
+    }
+  }
   const size_t fixed = (size_t)S * 8 + (size_t)S * W64 * 8 + 64;
   const size_t budget = 200 * 1024;
   TVO_REQUIRE(fixed + (size_t)(2 * Dpad + 1) * 8 <= budget, "noisyor_mstep: S/D too large for shared memory");
