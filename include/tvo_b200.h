@@ -178,6 +178,24 @@ int tvo_estep_evo_bsc_f32(const float *Y, int64_t ldY, const int64_t *idx, uint6
                           int64_t scratch_bytes, int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs,
                           void *stream);
 
+/* ---- TVS (tvo/variational/tvs.py:47-81) and BSC.data_estimator (tvo/models/bsc.py:241-252) ----
+ * tvo_state_marginals: out[b, h] = sum_s softmax(lpj[row])_s * K[row, s, h]  (mean_posterior of the states
+ *      themselves, tvs.py:66-70), row = idx ? idx[b] : b; K packed with row stride k_stride_n words.
+ * tvo_sample_states_probs: new states (b, S_off + j), j < S_new, of the packed buffer `out` (row stride
+ *      out_stride_n words) with bit h ~ Bernoulli(probs[b * probs_stride_n + h]) (stride 0 = one row for all
+ *      datapoints: the prior pies, tvs.py:60-63); 24-bit uniforms from the counter stream (seed, step, group,
+ *      global datapoint index n_offset + row, j, h).  group < 64 separates the prior and marginal draws. */
+int tvo_state_marginals_f64(const uint64_t *K, int64_t k_stride_n, const double *lpj, int64_t lpj_stride_n,
+                            const int64_t *idx, double *out, int64_t B, int32_t S, int32_t H, void *stream);
+int tvo_state_marginals_f32(const uint64_t *K, int64_t k_stride_n, const float *lpj, int64_t lpj_stride_n,
+                            const int64_t *idx, float *out, int64_t B, int32_t S, int32_t H, void *stream);
+int tvo_sample_states_probs_f64(uint64_t *out, int64_t out_stride_n, int32_t S_off, const double *probs,
+                                int64_t probs_stride_n, const int64_t *idx, int64_t B, int32_t S_new, int32_t H,
+                                uint64_t seed, uint32_t step, uint32_t group, uint32_t n_offset, void *stream);
+int tvo_sample_states_probs_f32(uint64_t *out, int64_t out_stride_n, int32_t S_off, const float *probs,
+                                int64_t probs_stride_n, const int64_t *idx, int64_t B, int32_t S_new, int32_t H,
+                                uint64_t seed, uint32_t step, uint32_t group, uint32_t n_offset, void *stream);
+
 /* ---- posterior weights: lpj2pjc / mean_posterior (_utils.py:182-230) ---- */
 int tvo_lpj2pjc_f64(const double *lpj, double *pjc, int64_t N, int32_t S, void *stream);
 int tvo_lpj2pjc_f32(const float *lpj, float *pjc, int64_t N, int32_t S, void *stream);

@@ -398,3 +398,36 @@ def random_states(N, S_new, H, sparsity, n_glob, seed, step):
                 out[n, j, w] = np.uint64(
                     px.bernoulli_mask64(seed, np.uint32(n_glob[n]), np.uint32((j << 8) | w), tag, sparsity, valid))
     return unpack_states(out, H)
+
+
+# ----------------------------------------------------------------------------- TVS (tvs.py:47-81)
+def state_marginals(K, lpj):
+    """(N,H) approximate marginals p(s_h=1|y_n) = mean_posterior of the states themselves (tvs.py:66-70):
+    sum_s softmax(lpj_n)_s K[n,s,h], evaluated as (sum_s e_s K) / (sum_s e_s) with e_s = exp(lpj - max)."""
+    lpj = np.asarray(lpj, dtype=np.float64)
+    e = np.exp(lpj - lpj.max(axis=1, keepdims=True))
+    return (e[:, :, None] * K.astype(np.float64)).sum(axis=1) / e.sum(axis=1, keepdims=True)
+
+
+def sample_states_probs(probs, S_new, H, n_glob, seed, step, group):
+    """(N,S_new,H) uint8: bit h of state (n, j) = [u < probs[n, h]] with the 24-bit uniform
+    u = (r >> 8) * 2^-24, r = u32 stream element h of sub-stream (n_glob[n], slot j, tag (step, group, SAMPLE))
+    (tvs.py:60-63 / :71-74 draw float32 uniforms).  ``probs`` is (N,H) or one row (H,) for all datapoints."""
+    n_glob = np.asarray(n_glob, dtype=np.uint32)
+    N = len(n_glob)
+    probs = np.broadcast_to(np.asarray(probs, dtype=np.float64), (N, H))
+    tag = px.make_tag(step, group, px.PUR_SAMPLE)
+    j = np.arange(S_new, dtype=np.uint32)[None, :, None]
+    h = np.arange(H, dtype=np.uint32)[None, None, :]
+    r = px.stream_u32(seed, n_glob[:, None, None], j, tag, h)
+    u = (r >> np.uint32(8)).astype(np.float64) * 2.0 ** -24
+    return (u < probs[:, None, :]).astype(np.uint8)
+
+
+def tvs_new_states(K, lpj, pies, S_new_prior, S_new_marg, n_glob, seed, step):
+    """tvs.py:60-76: prior samples (group 0) followed by marginal samples (group 1)."""
+    H = K.shape[2]
+    prior = sample_states_probs(np.broadcast_to(np.asarray(pies, dtype=np.float64), (H,)), S_new_prior, H, n_glob, seed,
+                                step, 0)
+    marg = sample_states_probs(state_marginals(K, lpj), S_new_marg, H, n_glob, seed, step, 1)
+    return np.concatenate([prior, marg], axis=1)

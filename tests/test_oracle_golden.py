@@ -384,3 +384,30 @@ def test_pack_unpack_roundtrip():
         assert P.shape == (3, 4, ost.n_words(H)) and P.dtype == np.uint64
         assert np.array_equal(ost.unpack_states(P, H), K)
     assert np.array_equal(ost.state_matrix(3)[5], [1, 0, 1])  # MSB first (fullem.py:26)
+
+
+# ----------------------------------------------------------------------------- TVS restatement (tvs.py:47-81)
+def test_tvs_marginals_are_the_mean_posterior_of_the_states():
+    rng = np.random.default_rng(3)
+    K = (rng.random((6, 9, 33)) < 0.3).astype(np.uint8)
+    lpj = 4 * rng.standard_normal((6, 9))
+    assert np.allclose(oevo.state_marginals(K, lpj), ost.mean_posterior(K.astype(np.float64), lpj), rtol=1e-13, atol=1e-15)
+
+
+def test_tvs_sampling_rates_and_layout():
+    rng = np.random.default_rng(4)
+    N, S, H = 300, 6, 24
+    K = (rng.random((N, S, H)) < 0.2).astype(np.uint8)
+    lpj = rng.standard_normal((N, S))
+    pies = np.linspace(0.05, 0.6, H)
+    new = oevo.tvs_new_states(K, lpj, pies, 40, 30, np.arange(N), 11, 0)
+    assert new.shape == (N, 70, H) and new.dtype == np.uint8
+    fp = new[:, :40].reshape(-1, H).mean(axis=0)  # prior block ~ Bernoulli(pies) (tvs.py:60-63)
+    assert np.all(np.abs(fp - pies) < 5 * np.sqrt(pies * (1 - pies) / (N * 40)) + 1e-3)
+    marg = oevo.state_marginals(K, lpj)             # marginal block ~ Bernoulli(marginals) (tvs.py:65-74)
+    fm = new[:, 40:].mean(axis=1)
+    assert np.abs(fm - marg).mean() < 0.05
+    assert not new[:, 40:][:, :, :][np.broadcast_to(marg[:, None, :] == 0, (N, 30, H))].any()
+    # a different step / seed gives a different draw, the same arguments the same draw
+    assert np.array_equal(new, oevo.tvs_new_states(K, lpj, pies, 40, 30, np.arange(N), 11, 0))
+    assert not np.array_equal(new, oevo.tvs_new_states(K, lpj, pies, 40, 30, np.arange(N), 11, 1))

@@ -71,6 +71,8 @@ for _sfx in ("f64", "f32"):
         f"tvo_estep_evo_bsc_{_sfx}": [_P, _I64, _P, _P, _P, _P, C.POINTER(EvoConfig), _P, _P, _I64, _I64, _I32, _I32,
                                       _I32, _P, _P],
         f"tvo_lpj2pjc_{_sfx}": [_P, _P, _I64, _I32, _P],
+        f"tvo_state_marginals_{_sfx}": [_P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _P],
+        f"tvo_sample_states_probs_{_sfx}": [_P, _I64, _I32, _P, _I64, _P, _I64, _I32, _I32, _U64, _U32, _U32, _U32, _P],
         f"tvo_mean_posterior_{_sfx}": [_P, _P, _P, _I64, _I32, _I64, _P],
         f"tvo_bsc_free_energy_{_sfx}": [_P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _P, _P],
         f"tvo_noisyor_prepare_{_sfx}": [_P, _P, _I32, _I32, _P, _P],

@@ -301,6 +301,84 @@ mean_posterior_kernel(const T *__restrict__ g, const T *__restrict__ lpj, T *__r
 }
 
 // ------------------------------------------------------------------------------------ host wrappers
+
+// ------------------------------------------------------------------------------------ TVS (tvs.py:47-81)
+// Approximate marginals p(s_h = 1 | y_n) = sum_s q_ns s_nsh (mean_posterior of the states themselves,
+// tvs.py:66-70; also W <s>_q of BSC.data_estimator, bsc.py:241-252) straight from the packed K: one warp
+// per datapoint, softmax weights in shared memory, lanes over h.
+template <typename T>
+__global__ void __launch_bounds__(256)
+state_marginals_kernel(const uint64_t *__restrict__ K, int64_t k_stride_n, const T *__restrict__ lpj,
+                       int64_t lpj_stride_n, const int64_t *__restrict__ idx, T *__restrict__ out, int64_t B, int S,
+                       int H) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int W64 = n_words(H);
+  double *q = (double *)smem_raw + (size_t)wib * S;
+  for (int64_t b = (int64_t)blockIdx.x * wpb + wib; b < B; b += (int64_t)gridDim.x * wpb) {
+    const int64_t row = idx ? idx[b] : b;
+    const T *l = lpj + row * lpj_stride_n;
+    const uint64_t *Kn = K + row * k_stride_n;
+    __syncwarp();
+    double mx = -INFINITY;
+    for (int s = lane; s < S; s += 32) mx = fmax(mx, (double)l[s]);
+    mx = warp_max(mx);
+    double se = 0.0;
+    for (int s = lane; s < S; s += 32) {
+      const double e = exp((double)l[s] - mx);
+      q[s] = e;
+      se += e;
+    }
+    se = warp_sum(se);
+    __syncwarp();
+    for (int h = lane; h < H; h += 32) {
+      double acc = 0.0;
+      const int w = h >> 6, sh = h & 63;
+      for (int s = 0; s < S; ++s)
+        if ((Kn[(size_t)s * W64 + w] >> sh) & 1ull) acc += q[s];
+      out[b * (int64_t)H + h] = (T)(acc / se);
+    }
+  }
+}
+
+// Bit h of new state (b, j) = [u < p_h], u = (r >> 8) * 2^-24 with r = u32 stream element h of sub-stream
+// (n, slot j, tag (step, group, PUR_SAMPLE)) — a 24-bit uniform like torch.rand's float32 draw
+// (tvs.py:60-74).  probs: (B, H) with row stride probs_stride_n, or one broadcast row (stride 0).
+// One thread per (b, j, word).
+template <typename T>
+__global__ void __launch_bounds__(256)
+sample_states_probs_kernel(uint64_t *__restrict__ out, int64_t out_stride_n, int S_off, const T *__restrict__ probs,
+                           int64_t probs_stride_n, const int64_t *__restrict__ idx, int64_t B, int S_new, int H, uint2 key,
+                           uint32_t step, uint32_t group, uint32_t n_offset) {
+  const int W64 = n_words(H);
+  const int64_t total = B * S_new * W64;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W64);
+    const int j = (int)((i / W64) % S_new);
+    const int64_t b = i / ((int64_t)W64 * S_new);
+    Stream st;
+    st.key = key;
+    st.n = n_offset + (uint32_t)(idx ? idx[b] : b);
+    st.tag = make_tag(step, group, PUR_SAMPLE);
+    const T *p = probs + b * probs_stride_n;
+    uint64_t word = 0;
+    const int nb = min(64, H - 64 * w);
+    for (int c = 0; c < nb; c += 4) {
+      const uint4 r = st.block((uint32_t)j, (uint32_t)((64 * w + c) >> 2));
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int h = 64 * w + c + t;
+        if (c + t < nb) {
+          const double u = (double)(rr[t] >> 8) * 0x1.0p-24;
+          if (u < (double)p[h]) word |= 1ull << (c + t);
+        }
+      }
+    }
+    out[b * out_stride_n + (int64_t)(S_off + j) * W64 + w] = word;
+  }
+}
+
 static int grid_for(int64_t items, int per_block, int blocks_per_sm) {
   const int64_t want = (items + per_block - 1) / per_block;
   return (int)max((int64_t)1, min(want, (int64_t)sm_count() * blocks_per_sm));
@@ -431,6 +509,36 @@ int mean_posterior_host(const T *g, const T *lpj, T *out, int64_t N, int S, int6
   return TVO_OK;
 }
 
+
+template <typename T>
+int state_marginals_host(const uint64_t *K, int64_t k_stride_n, const T *lpj, int64_t lpj_stride_n, const int64_t *idx,
+                         T *out, int64_t B, int S, int H, void *stream) {
+  TVO_REQUIRE(K && lpj && out, "state_marginals: null pointer");
+  TVO_REQUIRE(B >= 0 && S > 0 && H > 0, "state_marginals: bad sizes");
+  if (B == 0) return TVO_OK;
+  const size_t smem = (size_t)8 * S * 8;
+  TVO_REQUIRE(smem <= 200 * 1024, "state_marginals: S=%d too large", S);
+  auto kern = state_marginals_kernel<T>;
+  if (smem > 40 * 1024) TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid_for(B, 8, 8), 256, smem, (cudaStream_t)stream>>>(K, k_stride_n, lpj, lpj_stride_n, idx, out, B, S, H);
+  TVO_AFTER_LAUNCH("state_marginals");
+  return TVO_OK;
+}
+
+template <typename T>
+int sample_states_probs_host(uint64_t *out, int64_t out_stride_n, int S_off, const T *probs, int64_t probs_stride_n,
+                             const int64_t *idx, int64_t B, int S_new, int H, uint64_t seed, uint32_t step, uint32_t group,
+                             uint32_t n_offset, void *stream) {
+  TVO_REQUIRE(out && probs, "sample_states_probs: null pointer");
+  TVO_REQUIRE(B >= 0 && S_new >= 0 && S_off >= 0 && H > 0 && S_new < (1 << 24) && group < 64, "sample_states_probs: bad sizes");
+  if (B == 0 || S_new == 0) return TVO_OK;
+  const uint2 key = make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+  sample_states_probs_kernel<T><<<grid_for(B * S_new * n_words(H), 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      out, out_stride_n, S_off, probs, probs_stride_n, idx, B, S_new, H, key, step, group, n_offset);
+  TVO_AFTER_LAUNCH("sample_states_probs");
+  return TVO_OK;
+}
+
 }  // namespace tvo
 
 using namespace tvo;
@@ -519,5 +627,25 @@ int tvo_mean_posterior_f64(const double *g, const double *lpj, double *out, int6
 }
 int tvo_mean_posterior_f32(const float *g, const float *lpj, float *out, int64_t N, int32_t S, int64_t G, void *stream) {
   return mean_posterior_host<float>(g, lpj, out, N, S, G, stream);
+}
+int tvo_state_marginals_f64(const uint64_t *K, int64_t k_stride_n, const double *lpj, int64_t lpj_stride_n,
+                            const int64_t *idx, double *out, int64_t B, int32_t S, int32_t H, void *stream) {
+  return state_marginals_host<double>(K, k_stride_n, lpj, lpj_stride_n, idx, out, B, S, H, stream);
+}
+int tvo_state_marginals_f32(const uint64_t *K, int64_t k_stride_n, const float *lpj, int64_t lpj_stride_n,
+                            const int64_t *idx, float *out, int64_t B, int32_t S, int32_t H, void *stream) {
+  return state_marginals_host<float>(K, k_stride_n, lpj, lpj_stride_n, idx, out, B, S, H, stream);
+}
+int tvo_sample_states_probs_f64(uint64_t *out, int64_t out_stride_n, int32_t S_off, const double *probs,
+                                int64_t probs_stride_n, const int64_t *idx, int64_t B, int32_t S_new, int32_t H,
+                                uint64_t seed, uint32_t step, uint32_t group, uint32_t n_offset, void *stream) {
+  return sample_states_probs_host<double>(out, out_stride_n, S_off, probs, probs_stride_n, idx, B, S_new, H, seed, step,
+                                          group, n_offset, stream);
+}
+int tvo_sample_states_probs_f32(uint64_t *out, int64_t out_stride_n, int32_t S_off, const float *probs,
+                                int64_t probs_stride_n, const int64_t *idx, int64_t B, int32_t S_new, int32_t H,
+                                uint64_t seed, uint32_t step, uint32_t group, uint32_t n_offset, void *stream) {
+  return sample_states_probs_host<float>(out, out_stride_n, S_off, probs, probs_stride_n, idx, B, S_new, H, seed, step,
+                                         group, n_offset, stream);
 }
 }

@@ -28,7 +28,7 @@ from tvo_b200.utils.model_protocols import Optimized, Reconstructor, Sampler
 from tvo_b200.utils.parallel import all_reduce, broadcast, pprint
 from tvo_b200.utils.sanity import fix_theta
 from tvo_b200.variational._packed import PackedStates, as_packed
-from tvo_b200.variational._utils import mean_posterior
+from tvo_b200.variational._utils import mean_posterior, state_marginals
 
 
 class BSC(Optimized, Sampler, Reconstructor):
@@ -306,6 +306,8 @@ class BSC(Optimized, Sampler, Reconstructor):
         return (Y, hidden_state) if must_return_hidden_state else Y
 
     def data_estimator(self, idx: Tensor, batch: Tensor, states) -> Tensor:
-        """bsc.py:241-252: <W s>_q = W <s>_q"""
-        K = states.K[idx].to(dtype=self.precision)
-        return mean_posterior(K, states.lpj[idx]) @ self.theta["W"].t()
+        """bsc.py:241-252: <W s>_q = W <s>_q, with <s>_q taken from the packed K (tvo_state_marginals)."""
+        lpj = states.lpj
+        idx = idx.to(device=lpj.device, dtype=to.int64).contiguous()
+        marg = state_marginals(states._Kp, lpj, idx, states._H)
+        return marg.to(self.precision) @ self.theta["W"].t()

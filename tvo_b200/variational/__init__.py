@@ -2,6 +2,8 @@ from .TVOVariationalStates import TVOVariationalStates
 from .fullem import FullEM
 from .RandomSampledVarStates import RandomSampledVarStates
 from .evo import EVOVariationalStates
+from .tvs import TVSVariationalStates
 from ._packed import PackedStates
 
-__all__ = ["TVOVariationalStates", "FullEM", "RandomSampledVarStates", "EVOVariationalStates", "PackedStates"]
+__all__ = ["TVOVariationalStates", "FullEM", "RandomSampledVarStates", "EVOVariationalStates", "TVSVariationalStates",
+           "PackedStates"]

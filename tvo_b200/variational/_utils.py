@@ -53,6 +53,19 @@ def select_topS_packed(new_packed, new_lpj, K_packed, lpj, idx, H, nsubs_dev):
               _lib.ptr(lpj), _lib.ptr(idx), B, S_new, S, H, _lib.ptr(nsubs_dev), _lib.stream())
 
 
+def state_marginals(K_packed: to.Tensor, lpj: to.Tensor, idx, H: int) -> to.Tensor:
+    """(B,H) posterior mean of the states, sum_s q_ns K[n,s,:], rows idx (None = all) — mean_posterior of the
+    states themselves (tvs.py:66-70, bsc.py:249-252) without the (B,S,H) float temporary."""
+    N, S, W = K_packed.shape
+    bc = N == 1 and lpj.shape[0] != 1
+    B = idx.numel() if idx is not None else lpj.shape[0]
+    assert lpj.is_contiguous() and K_packed.is_contiguous()
+    out = to.empty((B, H), dtype=lpj.dtype, device=lpj.device)
+    _lib.call(f"tvo_state_marginals_{_lib.sfx(lpj.dtype)}", _lib.ptr(K_packed), 0 if bc else S * W, _lib.ptr(lpj),
+              lpj.shape[1], _lib.ptr(idx) if idx is not None else None, _lib.ptr(out), B, S, H, _lib.stream())
+    return out
+
+
 def set_redundant_lpj_to_low(new_states, new_lpj: to.Tensor, old_states):
     """Reference signature (_utils.py:88): uint8 (B,S',H), lpj (B,S') modified in place, uint8 (B,S,H)."""
     npk, H, _ = as_packed(new_states)
