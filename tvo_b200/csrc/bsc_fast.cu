@@ -11,7 +11,6 @@
 // per chunk so that  WpT += E^T Y  is one DGEMM (the union of active bits per datapoint is ~100 of 256,
 // so the outer product is effectively dense).
 #include <cublas_v2.h>
-#include <stdlib.h>
 
 #include "bsc_device.cuh"
 
@@ -171,7 +170,7 @@ __device__ __forceinline__ void score_states(const uint64_t *states, int count, 
 
 // EVOVariationalStates.update (evo.py:80-115) for BSC, Gram form.  Same structure and same random
 // stream as estep_evo_bsc_kernel (bsc.cu); `A` holds a = W^T y for the B datapoints of this launch.
-template <typename T, bool LOCKSTEP>
+template <typename T>
 __global__ void __launch_bounds__(256, 3)
 estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                           int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
@@ -192,13 +191,11 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
   const int pcap = H <= 65536 ? (int)(keys_region_bytes(dims) / 64) : 0;
 
   // All warps of a CTA walk the phases of the E-step in lockstep (PHASE_SYNC): the fused program is
-  // ~100 KB of SASS, far beyond the instruction cache, and 24 independent warps at 24 different places
-  // thrash it (ncu: 35% of stalls were instruction fetch).  With the barriers the 8 warps of a CTA
+  // ~160 KB of SASS (~50 KB executed for one configuration), far beyond the instruction cache, and 24
+  // independent warps at 24 different places thrash it (ncu: 35% of stalls were instruction fetch; without
+  // the barriers the kernel is 15% slower).  With the barriers the 8 warps of a CTA
   // share the cache lines of the phase they are all in.
-#define PHASE_SYNC()                \
-  do {                              \
-    if (LOCKSTEP) __syncthreads();  \
-  } while (0)
+#define PHASE_SYNC() __syncthreads()
   for (int64_t b0 = (int64_t)blockIdx.x * wpb; b0 < B; b0 += (int64_t)gridDim.x * wpb) {
     const int64_t b = b0 + wib;
     const bool active = b < B;
@@ -419,13 +416,12 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
   const size_t wbytes = warp_buf_bytes<T>(dims) + align16((size_t)H * sizeof(T));
   // 8 warps per CTA, 3 CTAs per SM (one 24-warp CTA per SM in lockstep measured the same)
-  int wpb = getenv("TVO_B200_WPB") ? atoi(getenv("TVO_B200_WPB")) : 8;
+  int wpb = 8;
   while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmemFast) wpb >>= 1;
   TVO_REQUIRE(wbytes * wpb <= (size_t)kMaxSmemFast, "estep_evo_bsc: per-datapoint working set %zu B exceeds shared memory",
               wbytes);
   const size_t smem = wbytes * wpb;
-  static const bool lockstep = !getenv("TVO_B200_NO_LOCKSTEP");
-  auto kern = lockstep ? estep_evo_bsc_gram_kernel<T, true> : estep_evo_bsc_gram_kernel<T, false>;
+  auto kern = estep_evo_bsc_gram_kernel<T>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));

@@ -25,16 +25,9 @@ class TVOVariationalStates(ABC):
         self.config = conf
         N, H, S, _, precision = get(conf, *required_keys)
         dev = tvo_b200.get_device()
-        if conf.get("K_init_file") is not None:
-            try:
-                import h5py  # noqa: F401
-            except ImportError as e:  # pragma: no cover
-                raise RuntimeError("K_init_file needs h5py, which is not installed") from e
-            from tvo_b200.utils.parallel import scatter_to_processes
-            import h5py
-            with h5py.File(conf["K_init_file"], "r") as f:
-                key = "initial_states" if "initial_states" in f else "states"
-                K_init = scatter_to_processes(to.tensor(f[key][...]))
+        if conf.get("K_init_file") is not None:  # TVOVariationalStates.py:30-38 (.h5 needs h5py; .npz always works)
+            from tvo_b200.utils.io import load_initial_states
+            K_init = load_initial_states(conf["K_init_file"], N, S, H)
         if K_init is not None:
             assert tuple(K_init.shape) == (N, S, H)
             K_u8 = K_init.clone().to(dtype=to.uint8, device=dev)
