@@ -178,24 +178,24 @@ def binomial_inverse(u, n, p):
 INV_TAB = [0.0] + [1.0 / k for k in range(1, 65)]  # 1/(k+1) factors of the pmf recurrence
 
 
-def _choose_positions(k, cand, H, seed, n_glob, slot, tag):
-    """Absolute positions of k of the candidates ``cand`` (ascending), uniform without replacement.
-    For k > n/2 the n-k candidates that are NOT flipped are drawn instead.  u32 stream elements
-    4, 5, ... of the sub-stream are consumed one per attempt:
+def _choose_positions(k, cand, H, seed, n_glob, slot, tag, t):
+    """Absolute positions of k of the candidates ``cand`` (ascending), uniform without replacement, and the
+    advanced attempt counter.  For k > n/2 the n-k candidates that are NOT flipped are drawn instead.
+    u32 stream elements 4 + t of the child's sub-stream are consumed one per attempt (t runs on across the
+    two classes of a child):
 
       dense class (2 n >= H): rejection — pos = randint(H) is accepted when it is a candidate that
           has not been drawn yet (after 64 + 64*draws attempts the sparse rule finishes the job);
-      sparse class: draw picks the t-th REMAINING candidate, t = randint(#remaining)."""
+      sparse class: draw picks the i-th REMAINING candidate, i = randint(#remaining)."""
     n = len(cand)
     if k <= 0:
-        return []
+        return [], t
     if k >= n:
-        return list(cand)
+        return list(cand), t
     complement = 2 * k > n
     draws = n - k if complement else k
     remaining = list(cand)
     picked = []
-    t = 0
 
     def u32():
         nonlocal t
@@ -204,7 +204,7 @@ def _choose_positions(k, cand, H, seed, n_glob, slot, tag):
         return r
 
     if 2 * n >= H:
-        cap = 64 + 64 * draws
+        cap = t + 64 + 64 * draws
         while len(picked) < draws and t < cap:
             pos = (u32() * H) >> 32
             if pos in remaining:
@@ -212,7 +212,7 @@ def _choose_positions(k, cand, H, seed, n_glob, slot, tag):
                 picked.append(pos)
     while len(picked) < draws:
         picked.append(remaining.pop((u32() * len(remaining)) >> 32))
-    return sorted(remaining) if complement else picked
+    return (sorted(remaining) if complement else picked), t
 
 
 def sparseflip(parents, C, sparsity, p_bf, n_glob, seed, step, gen):
@@ -223,8 +223,7 @@ def sparseflip(parents, C, sparsity, p_bf, n_glob, seed, step, gen):
     are uniform subsets.  This is the same joint law as H independent `rand < p` draws (evo.py:325)
     while using ~2 Philox blocks per child instead of H uniforms."""
     N, P, H = parents.shape
-    tag0 = px.make_tag(step, gen, px.PUR_FLIP0)
-    tag1 = px.make_tag(step, gen, px.PUR_FLIP1)
+    tag = px.make_tag(step, gen, px.PUR_FLIP0)
     a = parents.sum(axis=2)
     p0, p1 = sparseflip_probs(a, H, sparsity, p_bf)
     children = np.repeat(parents, C, axis=1).copy()
@@ -233,10 +232,13 @@ def sparseflip(parents, C, sparsity, p_bf, n_glob, seed, step, gen):
             p = j // C
             par = parents[n, p]
             zeros, ones = np.flatnonzero(par == 0), np.flatnonzero(par == 1)
-            for cls, tag, cand, prob in ((0, tag0, zeros, p0[n, p]), (1, tag1, ones, p1[n, p])):
-                u = float(px.u64_to_unit_double(px.stream_u64(seed, np.uint32(n_glob[n]), np.uint32(j), tag, np.uint32(0))))
+            t = 0  # attempt counter of the child's sub-stream (slot j), shared by the two classes
+            for cls, cand, prob in ((0, zeros, p0[n, p]), (1, ones, p1[n, p])):
+                # count uniform: u64 element 0 (zero bits) / 1 (one bits) of the child's block 0
+                u = float(px.u64_to_unit_double(px.stream_u64(seed, np.uint32(n_glob[n]), np.uint32(j), tag, np.uint32(cls))))
                 k = binomial_inverse(u, len(cand), prob)
-                for h in _choose_positions(k, cand, H, seed, n_glob[n], j, tag):
+                flips, t = _choose_positions(k, cand, H, seed, n_glob[n], j, tag, t)
+                for h in flips:
                     children[n, j, h] ^= 1
     return children
 

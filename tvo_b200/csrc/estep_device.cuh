@@ -122,12 +122,12 @@ __device__ __forceinline__ void randparents_sort(int S_c, int P, int bits, const
 #pragma unroll 1
     for (int j = k >> 1; j >= EPL; j >>= 1) {  // partner in another lane
       const int lm = j / EPL;
+      // j and k are multiples of EPL here, so the direction is a property of the lane, not of the element
+      const bool take_min = ((lane & lm) == 0) == ((lane & (k / EPL)) == 0);
 #pragma unroll
       for (int r = 0; r < EPL; ++r) {
-        const int e = lane * EPL + r;
         const uint32_t o = __shfl_xor_sync(FULL, key[r], lm);
-        const bool take_min = ((e & j) == 0) == ((e & k) == 0);
-        key[r] = take_min ? min(key[r], o) : max(key[r], o);
+        key[r] = ((o < key[r]) == take_min) ? o : key[r];
       }
     }
 #pragma unroll
@@ -417,6 +417,12 @@ __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int 
       }
       double p0 = 0.0, p1 = 0.0;
       if (!tab) sparseflip_probs((double)a, Hf, crowd, p_bf, p0, p1);
+      // ONE sub-stream per child (slot j of st0): block 0 holds the two count uniforms (u64 element 0 for
+      // the zero bits, element 1 for the one bits), u32 elements 4, 5, ... feed the position attempts of
+      // both classes in turn — typically two Philox blocks per child in total
+      uint4 b0 = make_uint4(0, 0, 0, 0), r = make_uint4(0, 0, 0, 0);
+      bool have_b0 = false;
+      uint32_t t = 0;
 #pragma unroll 1
       for (int cls = 0; cls < 2; ++cls) {
         const int n = cls ? a : H - a;
@@ -430,16 +436,22 @@ __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int 
         } else {
           fc = flip_class_make(n, cls ? p1 : p0);
         }
-        const Stream &st = cls ? st1 : st0;
-        const int k = fc.kconst >= 0 ? fc.kconst : flip_class_sample(fc, unit_double(st.u64((uint32_t)j, 0)), n);
+        const Stream &st = st0;
+        int k = fc.kconst;
+        if (k < 0) {
+          if (!have_b0) {
+            b0 = st.block((uint32_t)j, 0);
+            have_b0 = true;
+          }
+          const uint64_t uw = cls ? ((uint64_t)b0.w << 32 | b0.z) : ((uint64_t)b0.y << 32 | b0.x);
+          k = flip_class_sample(fc, unit_double(uw), n);
+        }
         if (k == 0) continue;
         const bool complement = 2 * k > n;  // draw the smaller of {flipped, not flipped}
         const int draws = k >= n ? 0 : (complement ? n - k : k);
-        uint4 r = make_uint4(0, 0, 0, 0);
         int got = 0;
-        uint32_t t = 0;  // u32 stream elements 4 + t, one per attempt
         if (2 * n >= H) {  // dense class: rejection sampling over all H positions
-          const uint32_t cap = 64u + 64u * (uint32_t)draws;
+          const uint32_t cap = t + 64u + 64u * (uint32_t)draws;
           while (got < draws && t < cap) {
             if ((t & 3) == 0) r = st.block((uint32_t)j, 1 + (t >> 2));
             const uint32_t ri = (t & 3) == 0 ? r.x : (t & 3) == 1 ? r.y : (t & 3) == 2 ? r.z : r.w;
@@ -708,12 +720,12 @@ __device__ __forceinline__ void bitonic_network(uint64_t (&key)[EPL], int (&src)
 #pragma unroll 1
     for (int j = k >> 1; j >= EPL; j >>= 1) {  // partner in another lane
       const int lm = j / EPL;
+      // j and k are multiples of EPL here, so the direction is a property of the lane, not of the element
+      const bool want_better = ((lane & lm) == 0) == ((lane & (k / EPL)) == 0);
 #pragma unroll
       for (int r = 0; r < EPL; ++r) {
-        const int e = lane * EPL + r;
         const uint64_t ok = __shfl_xor_sync(FULL, key[r], lm);
         const int oi = __shfl_xor_sync(FULL, src[r], lm);
-        const bool want_better = ((e & j) == 0) == ((e & k) == 0);
         if (ranks_before(ok, oi, key[r], src[r]) == want_better) {
           key[r] = ok;
           src[r] = oi;
