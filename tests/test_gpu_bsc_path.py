@@ -390,6 +390,59 @@ def test_fused_estep_bit_exact(gram, dtype, H, D, S, sel, mut, P, Cn, G):
     assert total > 0
 
 
+@pytest.mark.parametrize("case", range(14))
+def test_fused_estep_random_shapes_bit_exact(case):
+    """Randomised edge shapes (S not a multiple of 32, S' above 64 / 128, many duplicates at small H, one
+    parent, several generations) through the fused kernels against the oracle, fp64, K bit-exact."""
+    rng = np.random.default_rng(1000 + case)
+    shapes = [
+        # H,  D,  S,  sel,               mut,               P, C,    G
+        (3, 4, 5, "randparents", "randflip", 2, 2, 3),            # 2^3 states only: children are mostly duplicates
+        (5, 6, 33, "randparents", "sparseflip", 7, 3, 2),         # S > 32 = all states but one; S' = 42
+        (9, 5, 1, "randparents", "randflip", 1, 4, 1),            # single state, single parent
+        (12, 7, 31, "fitparents_fixed", "randflip", 5, 9, 2),     # S' = 90 (CPL 4 dedup), EPL 1 old sort
+        (20, 9, 65, "randparents", "sparseflip", 33, 4, 1),       # S = 65 (EPL 4), P > 32, S' = 132
+        (64, 16, 17, "randparents", "cross", 6, None, 2),         # S' = 60
+        (65, 12, 40, "randparents", "cross_randflip", 9, None, 1),   # S' = 72
+        (128, 20, 20, "fitparents_fixed", "cross_sparseflip", 5, None, 3),  # S' = 60, 3 generations
+        (130, 30, 100, "randparents", "sparseflip", 20, 3, 2),    # S = 100, S' = 120
+        (200, 10, 64, "randparents", "randflip", 16, 5, 2),       # S' = 160 > 128
+        (256, 24, 130, "randparents", "sparseflip", 8, 2, 1),     # S = 130 (EPL 8)
+        (70, 8, 270, "randparents", "sparseflip", 10, 2, 1),      # S > 256: rank-by-counting merge, parents by counting
+        (40, 6, 12, "randparents", "sparseflip", 12, 30, 1),      # S' = 360 > 256 survivors possible
+        (1, 3, 2, "randparents", "randflip", 1, 1, 2),            # H = 1
+    ]
+    H, D, S, sel, mut, P, Cn, G = shapes[case]
+    S = min(S, 2 ** H)
+    P = min(P, S)
+    N = 10
+    W = rng.standard_normal((D, H))
+    pies = np.full(H, min(0.4, 3.0 / H))
+    sigma2 = np.array([1.3])
+    Y = (rng.random((N, H)) < pies) @ W.T + rng.standard_normal((N, D))
+    K = rand_K(rng, N, S, H, p=min(0.4, 3.0 / H))
+    tvo_b200._set_device(to.device(DEV))
+    m = BSC(H, D, dev(W), dev(sigma2), dev(pies), precision=to.float64)
+    crossover = mut.startswith("cross")
+    kw = dict(bitflip_frequency=1.5 / H, seed=17 + case, K_init=dev(K))
+    if mut == "cross":
+        st = EVOVariationalStates(N, H, S, to.float64, sel, "cross", P, G, n_children=P - 1, **kw)
+    elif crossover:
+        st = EVOVariationalStates(N, H, S, to.float64, sel, mut[len("cross_"):], P, G, crossover=True, **kw)
+    else:
+        st = EVOVariationalStates(N, H, S, to.float64, sel, mut, P, G, n_children=Cn, **kw)
+    st.n_offset = 7
+    o = om.BSC(H, D, W, sigma2, pies)
+    Kw = K
+    for step in range(2):
+        Kw, Lw, nsubs_w = oracle_estep(o, Y, Kw, np.float64, sel, st.config["mutation"], P, P - 1 if crossover else Cn, G,
+                                       1.5 / H, 7 + np.arange(N), 17 + case, step, sparsity=float(m._tvo_sparsity().item()))
+        nsubs = st.update(to.arange(N, device=DEV), dev(Y), m)
+        assert np.array_equal(st.K.unpack().cpu().numpy(), Kw), f"K differs at step {step}"
+        assert nsubs == nsubs_w
+        assert np.allclose(st.lpj.cpu().numpy(), Lw, rtol=RT64, atol=RT64)
+
+
 def test_fused_estep_gram_nan_rows_and_chunking():
     """Datapoints with NaN in y take the direct (nansum) form inside the Gram kernel; a scratch smaller
     than the batch splits it into chunks without changing the result."""
