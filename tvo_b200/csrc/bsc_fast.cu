@@ -97,22 +97,18 @@ __device__ __noinline__ T bsc_gram_lpj_walk(const uint64_t *st, int W64, int H, 
 template <typename T>
 __device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, const T *a, const double *__restrict__ G,
                                           const T *__restrict__ prior, double yy, double coef, uint16_t *plist, int cap) {
-  int n = 0;
-  for (int w = 0; w < W64; ++w) {
-    const uint64_t m = st[w];
-    uint32_t x = (uint32_t)m;
-    int base = w << 6;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      while (x) {
-        const int pos = base + __ffs((int)x) - 1;
-        x &= x - 1;
-        if (n < cap) plist[n * 32] = (uint16_t)pos;
-        ++n;
-      }
-      x = (uint32_t)(m >> 32);
-      base += 32;
-    }
+  // states are sparse (|s| ~ 1-5 of H): walk the set bits with one loop over "next set bit of the multi-word
+  // mask" (empty words cost one test) instead of a bit loop per half word
+  int n = 0, w = 0;
+  uint64_t m = st[0];
+  while (true) {
+    while (m == 0 && ++w < W64) m = st[w];
+    if (w >= W64) break;
+    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    const int pos = (w << 6) + (lo ? __ffs((int)lo) - 1 : 32 + __ffs((int)hi) - 1);
+    m &= m - 1;
+    if (n < cap) plist[n * 32] = (uint16_t)pos;
+    ++n;
   }
   if (n > cap) return bsc_gram_lpj_walk<T>(st, W64, H, a, G, prior, yy, coef);
   double f = 0.0, pr = 0.0;
