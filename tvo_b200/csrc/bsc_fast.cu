@@ -238,6 +238,7 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
 }
 
 // ------------------------------------------------------------------------------------ M-step
+constexpr int kMstepListCap = 16;  // positions per lane in the M-step's list (denser states walk their bits)
 // stats layout: [WpT (H*D) | WqU (H*H, UPPER triangle incl. diagonal of my_Wq) | pies (H) | sigma2 | N | F]
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -257,10 +258,13 @@ bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict
   double *Esm = (double *)p;
   p += align16((size_t)H * 8);
   double *pies_w = (double *)p;  // per-warp running sum of E over this warp's datapoints
+  p += align16((size_t)H * 8);
+  uint16_t *plist = (uint16_t *)p;  // kMstepListCap x 32 lane-strided positions
 
   double *WqU = stats + (size_t)H * D, *pies = WqU + (size_t)H * H;
   double *sig = pies + H, *Ncnt = sig + 1, *Facc = Ncnt + 1;
-  const double coef = th.hdr->coef;
+  const double inv_coef = 1.0 / th.hdr->coef;  // -2 sigma2
+  const int lcap = H <= 65536 ? kMstepListCap : 0;  // uint16 positions
   double acc_sig = 0.0, acc_F = 0.0, acc_N = 0.0;
   for (int h = lane; h < H; h += 32) pies_w[h] = 0.0;
 
@@ -293,35 +297,58 @@ bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict
     acc_F += mx + log(se) + th.hdr->prior_sum - 0.5 * (double)dn * th.hdr->log_2pi_sigma2;
     acc_N += 1.0;
     __syncwarp();
-    // one lane per state: E_h += q_s, WqU[h,h'] += q_s (h <= h'), sigma2 term from lpj
+    // one lane per state: E_h += q_s, WqU[h,h'] += q_s (h <= h'), sigma2 term from lpj.  The active
+    // positions go to a lane-strided list first (states are sparse; same walk as the E-step scorer).
     double part = 0.0;
+    const double inv_se = 1.0 / se;
     for (int s = lane; s < S; s += 32) {
-      const double qs = q[s] / se;
+      const double qs = q[s] * inv_se;
       q[s] = qs;
       const uint64_t *st = Ksm + (size_t)s * W64;
       double pr = 0.0;
-      for (int w1 = 0; w1 < W64; ++w1) {
-        uint64_t m1 = st[w1];
-        while (m1) {
-          const int h1 = (w1 << 6) + __ffsll((long long)m1) - 1;
+      int n = 0, w = 0;
+      uint64_t m = st[0];
+      while (true) {
+        while (m == 0 && ++w < W64) m = st[w];
+        if (w >= W64) break;
+        const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+        const int pos = (w << 6) + (lo ? __ffs((int)lo) - 1 : 32 + __ffs((int)hi) - 1);
+        m &= m - 1;
+        if (n < lcap) plist[n * 32 + lane] = (uint16_t)pos;
+        ++n;
+      }
+      if (n <= lcap) {
+        for (int i = 0; i < n; ++i) {
+          const int h1 = plist[i * 32 + lane];
           pr += (double)__ldg(th.prior + h1);
           atomicAdd(Esm + h1, qs);
           double *Wrow = WqU + (size_t)h1 * H;
-          uint64_t m2 = m1;  // includes h1 itself: the diagonal
-          int w2 = w1;
-          while (true) {
-            while (m2) {
-              const int h2 = (w2 << 6) + __ffsll((long long)m2) - 1;
-              m2 &= m2 - 1;
-              atomicAdd(Wrow + h2, qs);
+          for (int j = i; j < n; ++j) atomicAdd(Wrow + plist[j * 32 + lane], qs);  // j == i: the diagonal
+        }
+      } else {  // dense state: walk the bits in place
+        for (int w1 = 0; w1 < W64; ++w1) {
+          uint64_t m1 = st[w1];
+          while (m1) {
+            const int h1 = (w1 << 6) + __ffsll((long long)m1) - 1;
+            pr += (double)__ldg(th.prior + h1);
+            atomicAdd(Esm + h1, qs);
+            double *Wrow = WqU + (size_t)h1 * H;
+            uint64_t m2 = m1;  // includes h1 itself: the diagonal
+            int w2 = w1;
+            while (true) {
+              while (m2) {
+                const int h2 = (w2 << 6) + __ffsll((long long)m2) - 1;
+                m2 &= m2 - 1;
+                atomicAdd(Wrow + h2, qs);
+              }
+              if (++w2 >= W64) break;
+              m2 = st[w2];
             }
-            if (++w2 >= W64) break;
-            m2 = st[w2];
+            m1 &= m1 - 1;
           }
-          m1 &= m1 - 1;
         }
       }
-      if (!exact_resid) part += qs * (((double)l[s] - pr) / coef);
+      if (!exact_resid) part += qs * (((double)l[s] - pr) * inv_coef);
     }
     if (!exact_resid) acc_sig += warp_sum(part);
     __syncwarp();
@@ -367,7 +394,8 @@ bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict
 
 template <typename T>
 static size_t bsc_mstep_warp_bytes(int S, int H) {
-  return align16((size_t)S * n_words(H) * 8) + align16((size_t)S * 8) + 2 * align16((size_t)H * 8);
+  return align16((size_t)S * n_words(H) * 8) + align16((size_t)S * 8) + 2 * align16((size_t)H * 8) +
+         (size_t)kMstepListCap * 32 * 2;
 }
 
 // ------------------------------------------------------------------------------------ host side
