@@ -157,3 +157,49 @@ def test_sssc_fullem_train_increases_F():
         m.update_param_epoch()
         st.lpj[:] = m.log_pseudo_joint(data, st.K)
         assert m.free_energy(to.arange(N), data, st) > F0
+
+
+def test_sssc_dense_states_all_solver_levels_and_overflow():
+    """States with 0..8 active units run in sub-warp groups, 9..16 with the full warp in shared memory,
+    17..32 in the warp's global scratch row, more than 32 set the overflow flag (finfo.min, raise at epoch
+    end): lpj and the M-step statistics against the oracle for a K that mixes all levels."""
+    rng = np.random.default_rng(21)
+    N, D, H, S = 6, 40, 48, 12
+    W = rng.standard_normal((D, H))
+    A = rng.standard_normal((H, H)) * 0.1
+    Psi = A @ A.T + np.eye(H)
+    mus = rng.standard_normal(H) * 0.3
+    pies = rng.uniform(0.02, 0.3, H)
+    Y = rng.standard_normal((N, D)) * 2
+    counts = [0, 1, 2, 5, 8, 9, 12, 16, 17, 24, 32, 3]
+    K = np.zeros((N, S, H), np.uint8)
+    for n in range(N):
+        for s, c in enumerate(counts):
+            K[n, s, rng.permutation(H)[:c]] = 1
+    tvo_b200._set_device(to.device(DEV))
+    m = SSSC(H, D, dev(W), dev(np.array([0.5])), dev(mus), dev(Psi), dev(pies), precision=to.float64)
+    o = om.SSSC(H, D, W, np.array([0.5]), mus, Psi, pies)
+    want = o.log_pseudo_joint(Y, K)
+    got = m.log_pseudo_joint(dev(Y), dev(K)).cpu().numpy()
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+    # M-step statistics with posterior weights that give every level a non-negligible share
+    lpj = rng.standard_normal((N, S))
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "randflip", 2, 1, 1, K_init=dev(K))
+    st.lpj[:] = dev(lpj)
+    m.update_param_batch(to.arange(N), dev(Y), st)
+    o.update_param_batch(Y, K, lpj)
+    for attr in ("_my_sum_xpt_s", "_my_sum_xpt_sz", "_my_sum_xpt_ssT", "_my_sum_xpt_szszT", "_my_sum_xpt_sz_xpt_szT",
+                 "_my_sum_y_szT", "_my_sum_diag_yyT"):
+        a, b = getattr(m, attr).cpu().numpy(), getattr(o, attr[len("_my_"):])
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(b).max())), attr
+    m._check_overflow()  # nothing overflowed so far
+    # one state beyond 32 active units: finfo.min and a loud error at the next overflow check
+    K2 = K.copy()
+    K2[2, 4, :40] = 1
+    got2 = m.log_pseudo_joint(dev(Y), dev(K2)).cpu().numpy()
+    assert got2[2, 4] == np.finfo(np.float64).min
+    mask = np.ones_like(got2, bool)
+    mask[2, 4] = False
+    assert np.allclose(got2[mask], want[mask], rtol=1e-9, atol=1e-9 * np.abs(want).max())
+    with pytest.raises(RuntimeError):
+        m._check_overflow()

@@ -101,7 +101,17 @@ __global__ void sssc_prepare_kernel(const T *__restrict__ W, const T *__restrict
 }
 
 // ------------------------------------------------------------------------------------ per-state solve
-// Per-warp scratch for one state with up to `amax` active units.
+// One state is solved cooperatively by a GROUP of GS lanes.  States are sparse (|A| ~ 1-4), so a whole
+// warp per state leaves most lanes idle: the scorers below run 32/kSsscGS states of a datapoint
+// concurrently in sub-warp groups (scratch for up to kSsscAS active units each), then the rare denser
+// states with the full warp (up to kSsscAM units in the same shared memory, up to kSsscAB in a global
+// scratch row of the warp).  States beyond kSsscAB set the overflow flag (finfo.min, sssc.py:343-345).
+constexpr int kSsscGS = 8;   // lanes per sub-warp group
+constexpr int kSsscNG = 32 / kSsscGS;
+constexpr int kSsscAS = 8;   // active units handled by a sub-warp group
+constexpr int kSsscAM = 16;  // ... by the full warp in shared memory
+constexpr int kSsscAB = 32;  // ... by the full warp in its global scratch row
+
 struct SsscScratch {
   double *R;    // amax*amax : Psi_A -> Cholesky factor R (lower)
   double *Gm;   // amax*amax : G_AA  -> M -> Cholesky factor C (lower)
@@ -111,6 +121,11 @@ struct SsscScratch {
 };
 __host__ __device__ inline size_t sssc_scratch_bytes(int amax) {
   return (size_t)3 * amax * amax * 8 + (size_t)6 * amax * 8 + align16((size_t)amax * 4);
+}
+// per-warp shared scratch: kSsscNG group scratches, re-carved as ONE kSsscAM scratch for the full warp
+__host__ __device__ inline size_t sssc_warp_scratch_bytes() {
+  const size_t g = (size_t)kSsscNG * sssc_scratch_bytes(kSsscAS), m = sssc_scratch_bytes(kSsscAM);
+  return align16(g > m ? g : m);
 }
 __device__ inline SsscScratch sssc_carve(unsigned char *p, int amax) {
   SsscScratch s;
@@ -122,45 +137,52 @@ __device__ inline SsscScratch sssc_carve(unsigned char *p, int amax) {
   return s;
 }
 
+template <int GS>
+__device__ __forceinline__ double group_sum(double v, unsigned gmask) {
+#pragma unroll
+  for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
 // in-place Cholesky (lower) of the a x a SPD matrix A (row stride ld); returns false on a bad pivot
-__device__ inline bool chol_lower(double *A, int a, int ld, int lane) {
+template <int GS>
+__device__ inline bool chol_lower(double *A, int a, int ld, int gl, unsigned gmask) {
   bool ok = true;
   for (int j = 0; j < a; ++j) {
-    __syncwarp();
+    __syncwarp(gmask);
     double djj = A[j * ld + j];
     for (int k = 0; k < j; ++k) djj -= A[j * ld + k] * A[j * ld + k];
     ok = ok && (djj > 0.0);
     const double ljj = sqrt(djj);
-    for (int i = j + 1 + lane; i < a; i += 32) {
+    for (int i = j + 1 + gl; i < a; i += GS) {
       double v = A[i * ld + j];
       for (int k = 0; k < j; ++k) v -= A[i * ld + k] * A[j * ld + k];
       A[i * ld + j] = v / ljj;
     }
-    __syncwarp();
-    if (lane == 0) A[j * ld + j] = ljj;
+    __syncwarp(gmask);
+    if (gl == 0) A[j * ld + j] = ljj;
   }
-  __syncwarp();
+  __syncwarp(gmask);
   return ok;
 }
 
-// lpj of one state (warp-cooperative).  a_vec: shared (H) = W^T y; yy = ||y||^2.  If want_moments,
-// sc.vec[4*amax ..] receives kappa (a) and sc.X receives Lambda + kappa kappa^T (a x a).
-// y_nan_row != nullptr selects the restricted (NaN-aware) path.  Returns lpj (double; NaN if the state
-// cannot be evaluated) and the number of active units through n_act (-1: more than amax).
-template <typename T>
-__device__ inline double sssc_state(const uint64_t *st, int W64, int H, int D, const SsscTheta<T> &th,
-                                    const double *a_vec, double yy, const T *y_nan_row, const SsscScratch &sc, int amax,
-                                    bool want_moments, int &n_act, int lane) {
-  const double s2 = th.hdr->sigma2;
-  // active set
+__device__ __forceinline__ int state_popcount(const uint64_t *st, int W64) {
   int a = 0;
   for (int w = 0; w < W64; ++w) a += __popcll(st[w]);
-  n_act = a;
-  if (a > amax) {
-    n_act = -1;
-    return __longlong_as_double(0x7ff8000000000000ll);  // NaN -> finfo.min at the caller (sssc.py:343-345)
-  }
-  if (lane == 0) {
+  return a;
+}
+
+// lpj of one state, cooperatively by the GS lanes of `gmask` (gl = lane within the group).  The state has
+// a <= amax active units (checked by the caller).  a_vec: shared (H) = W^T y; yy = ||y||^2.  If
+// want_moments, sc.vec[4*amax ..] receives kappa (a) and sc.X receives Lambda + kappa kappa^T (a x a).
+// y_nan_row != nullptr selects the restricted (NaN-aware) path.  Returns lpj (NaN if not evaluable).
+template <typename T, int GS>
+__device__ inline double sssc_state(const uint64_t *st, int W64, int H, int D, const SsscTheta<T> &th,
+                                    const double *a_vec, double yy, const T *y_nan_row, const SsscScratch &sc, int amax,
+                                    bool want_moments, int a, int gl, unsigned gmask) {
+  const double s2 = th.hdr->sigma2;
+  __syncwarp(gmask);
+  if (gl == 0) {
     int k = 0;
     for (int w = 0; w < W64; ++w) {
       uint64_t m = st[w];
@@ -170,7 +192,7 @@ __device__ inline double sssc_state(const uint64_t *st, int W64, int H, int D, c
       }
     }
   }
-  __syncwarp();
+  __syncwarp(gmask);
   double *mu = sc.vec, *aA = sc.vec + amax, *bv = sc.vec + 2 * amax, *vz = sc.vec + 3 * amax, *kap = sc.vec + 4 * amax;
   double prior = 0.0;
   for (int i = 0; i < a; ++i) prior += th.prior[sc.act[i]];
@@ -178,27 +200,27 @@ __device__ inline double sssc_state(const uint64_t *st, int W64, int H, int D, c
     double yyn = yy;
     if (y_nan_row) {
       double t = 0.0;
-      for (int d = lane; d < D; d += 32) {
+      for (int d = gl; d < D; d += GS) {
         const double v = (double)y_nan_row[d];
         if (v == v) t += v * v;
       }
-      yyn = warp_sum(t);
+      yyn = group_sum<GS>(t, gmask);
     }
     return -0.5 * (yyn / s2);
   }
   const int ld = amax;
   // Psi_A, G_AA, mu_A, a_A
-  for (int t = lane; t < a * a; t += 32) {
+  for (int t = gl; t < a * a; t += GS) {
     const int i = t / a, j = t % a;
     sc.R[i * ld + j] = th.Psi[(size_t)sc.act[i] * H + sc.act[j]];
     if (!y_nan_row) sc.Gm[i * ld + j] = th.G[(size_t)sc.act[i] * H + sc.act[j]];
   }
-  for (int i = lane; i < a; i += 32) {
+  for (int i = gl; i < a; i += GS) {
     mu[i] = th.mus[sc.act[i]];
     if (!y_nan_row) aA[i] = a_vec[sc.act[i]];
   }
   if (y_nan_row) {  // restricted to the observed dimensions (sssc.py:283-298)
-    for (int t = lane; t < a * a + a; t += 32) {
+    for (int t = gl; t < a * a + a; t += GS) {
       const int i = t < a * a ? t / a : t - a * a, j = t < a * a ? t % a : -1;
       const T *wi = th.Wt + (size_t)sc.act[i] * th.Dpad;
       const T *wj = j >= 0 ? th.Wt + (size_t)sc.act[j] * th.Dpad : nullptr;
@@ -210,60 +232,60 @@ __device__ inline double sssc_state(const uint64_t *st, int W64, int H, int D, c
       if (j >= 0) sc.Gm[i * ld + j] = acc; else aA[i] = acc;
     }
     double t = 0.0;
-    for (int d = lane; d < D; d += 32) {
+    for (int d = gl; d < D; d += GS) {
       const double v = (double)y_nan_row[d];
       if (v == v) t += v * v;
     }
-    yy = warp_sum(t);
+    yy = group_sum<GS>(t, gmask);
   }
-  __syncwarp();
+  __syncwarp(gmask);
   // b = a_A - G mu,  rr = yy - 2 mu.a_A + mu^T G mu
-  for (int i = lane; i < a; i += 32) {
+  for (int i = gl; i < a; i += GS) {
     double gm = 0.0;
     for (int k = 0; k < a; ++k) gm += sc.Gm[i * ld + k] * mu[k];
     bv[i] = aA[i] - gm;
     vz[i] = mu[i] * (gm - 2.0 * aA[i]);
   }
-  __syncwarp();
+  __syncwarp(gmask);
   double rr = yy;
   for (int i = 0; i < a; ++i) rr += vz[i];
   // Psi_A = R R^T
-  bool ok = chol_lower(sc.R, a, ld, lane);
+  bool ok = chol_lower<GS>(sc.R, a, ld, gl, gmask);
   // X = G R  (R lower: k >= j)
-  for (int t = lane; t < a * a; t += 32) {
+  for (int t = gl; t < a * a; t += GS) {
     const int i = t / a, j = t % a;
     double acc = 0.0;
     for (int k = j; k < a; ++k) acc += sc.Gm[i * ld + k] * sc.R[k * ld + j];
     sc.X[i * ld + j] = acc;
   }
-  __syncwarp();
+  __syncwarp(gmask);
   // M = I + R^T X / s2  (into Gm)
-  for (int t = lane; t < a * a; t += 32) {
+  for (int t = gl; t < a * a; t += GS) {
     const int i = t / a, j = t % a;
     double acc = 0.0;
     for (int k = i; k < a; ++k) acc += sc.R[k * ld + i] * sc.X[k * ld + j];
     sc.Gm[i * ld + j] = acc / s2 + (i == j ? 1.0 : 0.0);
   }
-  __syncwarp();
-  ok = chol_lower(sc.Gm, a, ld, lane) && ok;  // M = C C^T
+  __syncwarp(gmask);
+  ok = chol_lower<GS>(sc.Gm, a, ld, gl, gmask) && ok;  // M = C C^T
   double logdet = 0.0;
   for (int i = 0; i < a; ++i) logdet += log(sc.Gm[i * ld + i]);
   logdet *= 2.0;
   // v = R^T b ; z = C^-1 v (forward substitution)
-  for (int i = lane; i < a; i += 32) {
+  for (int i = gl; i < a; i += GS) {
     double acc = 0.0;
     for (int k = i; k < a; ++k) acc += sc.R[k * ld + i] * bv[k];
     vz[i] = acc;
   }
-  __syncwarp();
-  if (lane == 0) {
+  __syncwarp(gmask);
+  if (gl == 0) {
     for (int i = 0; i < a; ++i) {
       double v = vz[i];
       for (int k = 0; k < i; ++k) v -= sc.Gm[i * ld + k] * vz[k];
       vz[i] = v / sc.Gm[i * ld + i];
     }
   }
-  __syncwarp();
+  __syncwarp(gmask);
   double zz = 0.0;
   for (int i = 0; i < a; ++i) zz += vz[i] * vz[i];
   const double quad = rr / s2 - zz / (s2 * s2);
@@ -271,41 +293,41 @@ __device__ inline double sssc_state(const uint64_t *st, int W64, int H, int D, c
   if (!ok) lpj = __longlong_as_double(0x7ff8000000000000ll);
   if (want_moments) {
     // Cinv = C^-1 (lower) column by column into X ; U = R Cinv^T ; Lambda = U U^T
-    for (int j = lane; j < a; j += 32) {
+    for (int j = gl; j < a; j += GS) {
       for (int i = 0; i < a; ++i) {
         double v = (i == j) ? 1.0 : 0.0;
         for (int k = j; k < i; ++k) v -= sc.Gm[i * ld + k] * sc.X[k * ld + j];
         sc.X[i * ld + j] = i < j ? 0.0 : v / sc.Gm[i * ld + i];
       }
     }
-    __syncwarp();
+    __syncwarp(gmask);
     // t = C^-T z  -> kappa = mu + R t / s2 ;  U = R Cinv^T written over Gm (C no longer needed)
-    for (int i = lane; i < a; i += 32) {
+    for (int i = gl; i < a; i += GS) {
       double acc = 0.0;
       for (int k = i; k < a; ++k) acc += sc.X[k * ld + i] * vz[k];
       kap[i] = acc;  // t_i
     }
-    __syncwarp();
-    for (int t = lane; t < a * a; t += 32) {
+    __syncwarp(gmask);
+    for (int t = gl; t < a * a; t += GS) {
       const int i = t / a, j = t % a;
       double acc = 0.0;
       for (int k = 0; k <= i; ++k) acc += sc.R[i * ld + k] * sc.X[j * ld + k];  // Cinv^T[k][j] = Cinv[j][k]
       sc.Gm[i * ld + j] = acc;  // U
     }
-    for (int i = lane; i < a; i += 32) {
+    for (int i = gl; i < a; i += GS) {
       double acc = 0.0;
       for (int k = 0; k <= i; ++k) acc += sc.R[i * ld + k] * kap[k];
       bv[i] = mu[i] + acc / s2;  // kappa_i (bv reused; b no longer needed)
     }
-    __syncwarp();
-    for (int i = lane; i < a; i += 32) kap[i] = bv[i];
-    for (int t = lane; t < a * a; t += 32) {
+    __syncwarp(gmask);
+    for (int i = gl; i < a; i += GS) kap[i] = bv[i];
+    for (int t = gl; t < a * a; t += GS) {
       const int i = t / a, j = t % a;
       double acc = 0.0;
       for (int k = 0; k < a; ++k) acc += sc.Gm[i * ld + k] * sc.Gm[j * ld + k];
       sc.X[i * ld + j] = acc + bv[i] * bv[j];  // Lambda + kappa kappa^T  (sssc.py:421-423)
     }
-    __syncwarp();
+    __syncwarp(gmask);
   }
   return lpj;
 }
@@ -326,20 +348,21 @@ struct SsscModel {
     int64_t ldY;
     const T *A;  // B x H : W^T y per datapoint of this launch
     const void *ws;
-    int H, D, amax;
-    int *overflow;  // set when a state has more than amax active units
+    int H, D;
+    unsigned char *big;  // global scratch, one sssc_scratch_bytes(kSsscAB) row per warp of the grid (or nullptr)
+    int *overflow;       // set when a state has more active units than can be evaluated
   };
-  __host__ __device__ static size_t smem_bytes(const Params &p) { return (size_t)p.H * 8 + sssc_scratch_bytes(p.amax); }
+  __host__ __device__ static size_t smem_bytes(const Params &p) { return (size_t)p.H * 8 + sssc_warp_scratch_bytes(); }
   struct Ctx {
     double yy;
     bool has_nan;
     const T *y;
     double *a_sm;
-    SsscScratch sc;
+    unsigned char *scr;  // the warp's shared scratch
     __device__ void load(const Params &p, int64_t b, unsigned char *smem, int lane) {
       y = p.Y + b * p.ldY;
       a_sm = (double *)smem;
-      sc = sssc_carve(smem + (size_t)p.H * 8, p.amax);
+      scr = smem + (size_t)p.H * 8;
       double t = 0.0;
       bool nan = false;
       for (int d = lane; d < p.D; d += 32) {
@@ -351,18 +374,60 @@ struct SsscModel {
       has_nan = __any_sync(FULL, nan);
       for (int h = lane; h < p.H; h += 32) a_sm[h] = (double)p.A[b * (int64_t)p.H + h];
     }
-    __device__ void score(const Params &p, const uint64_t *states, int count, int W64, T *out, int lane) {
+    // Evaluate `count` states.  `sink(s, value, n_active, scratch, amax, gl, GS-lane-count, gmask)` is called by
+    // every lane of the group that solved state s (want_moments: scratch holds kappa and Lambda + kappa kappa^T).
+    template <bool MOMENTS, typename Sink>
+    __device__ __forceinline__ void for_each_state(const Params &p, const uint64_t *states, int count, int W64, int lane,
+                                                   Sink &&sink) {
       const SsscTheta<T> th = sssc_theta_view<T>(p.ws, p.H, p.D);
-      for (int s = 0; s < count; ++s) {
-        int na;
-        const double v = sssc_state<T>(states + (size_t)s * W64, W64, p.H, p.D, th, a_sm, yy, has_nan ? y : nullptr, sc,
-                                       p.amax, false, na, lane);
-        if (lane == 0) {
-          out[s] = sssc_finish<T>(v);
-          if (na < 0) *p.overflow = 1;
+      const int grp = lane / kSsscGS, gl = lane % kSsscGS;
+      const unsigned gmask = ((1u << kSsscGS) - 1u) << (grp * kSsscGS);
+      const SsscScratch scg = sssc_carve(scr + (size_t)grp * sssc_scratch_bytes(kSsscAS), kSsscAS);
+      const T *ynan = has_nan ? y : nullptr;
+      bool dense_seen = false;
+      __syncwarp();
+      for (int s0 = 0; s0 < count; s0 += kSsscNG) {  // sparse states: one per sub-warp group
+        const int s = s0 + grp;
+        if (s < count) {
+          const uint64_t *st = states + (size_t)s * W64;
+          const int a = state_popcount(st, W64);
+          if (a <= kSsscAS) {
+            const double v = sssc_state<T, kSsscGS>(st, W64, p.H, p.D, th, a_sm, yy, ynan, scg, kSsscAS, MOMENTS, a, gl, gmask);
+            sink(s, v, a, scg, kSsscAS, gl, kSsscGS, gmask);
+          } else {
+            dense_seen = true;
+          }
+        }
+      }
+      __syncwarp();
+      if (!__any_sync(FULL, dense_seen)) return;
+      const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+      for (int s = 0; s < count; ++s) {  // denser states: the full warp, one at a time
+        const uint64_t *st = states + (size_t)s * W64;
+        const int a = state_popcount(st, W64);
+        if (a <= kSsscAS) continue;
+        double v = __longlong_as_double(0x7ff8000000000000ll);  // NaN -> finfo.min (sssc.py:343-345)
+        if (a <= kSsscAM) {
+          const SsscScratch sc = sssc_carve(scr, kSsscAM);
+          v = sssc_state<T, 32>(st, W64, p.H, p.D, th, a_sm, yy, ynan, sc, kSsscAM, MOMENTS, a, lane, FULL);
+          sink(s, v, a, sc, kSsscAM, lane, 32, FULL);
+        } else if (a <= kSsscAB && p.big) {
+          const SsscScratch sc = sssc_carve(p.big + (size_t)wid * sssc_scratch_bytes(kSsscAB), kSsscAB);
+          v = sssc_state<T, 32>(st, W64, p.H, p.D, th, a_sm, yy, ynan, sc, kSsscAB, MOMENTS, a, lane, FULL);
+          sink(s, v, a, sc, kSsscAB, lane, 32, FULL);
+        } else {
+          if (lane == 0) *p.overflow = 1;
+          sink(s, v, -1, scg, kSsscAS, lane, 32, FULL);
         }
         __syncwarp();
       }
+    }
+    __device__ void score(const Params &p, const uint64_t *states, int count, int W64, T *out, int lane) {
+      for_each_state<false>(p, states, count, W64, lane,
+                            [&](int s, double v, int, const SsscScratch &, int, int gl, int, unsigned) {
+                              if (gl == 0) out[s] = sssc_finish<T>(v);
+                            });
+      __syncwarp();
     }
   };
 };
@@ -403,7 +468,7 @@ sssc_mstep_kernel(typename SsscModel<T>::Params p, const int64_t *__restrict__ i
                   double *__restrict__ Yd_out, int64_t B, int S, size_t wbytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int H = p.H, D = p.D, W64 = n_words(H), amax = p.amax;
+  const int H = p.H, D = p.D, W64 = n_words(H);
   const SsscTheta<T> th = sssc_theta_view<T>(p.ws, H, D);
   unsigned char *base = smem_raw + (size_t)wib * wbytes;
   typename SsscModel<T>::Ctx ctx;
@@ -446,29 +511,30 @@ sssc_mstep_kernel(typename SsscModel<T>::Params p, const int64_t *__restrict__ i
     accF += mx + log(se) + th.hdr->prior_sum - 0.5 * (double)dn * th.hdr->log_2pi_sigma2;
     accN += 1.0;
     __syncwarp();
-    for (int s = 0; s < S; ++s) {
-      const double qs = q[s] / se;
-      int na;
-      sssc_state<T>(Ksm + (size_t)s * W64, W64, H, D, th, ctx.a_sm, ctx.yy, nullptr, ctx.sc, amax, true, na, lane);
-      if (na < 0 && lane == 0) *p.overflow = 1;
-      if (na <= 0 || qs == 0.0) {
-        __syncwarp();
-        continue;
-      }
-      const double *kap = ctx.sc.vec + 4 * amax;
-      for (int i = lane; i < na; i += 32) {
-        const int h = ctx.sc.act[i];
-        xe[h] += qs;
-        xk[h] += qs * kap[i];
-      }
-      for (int t = lane; t < na * na; t += 32) {
-        const int i = t / na, j = t % na;
-        const int hi = ctx.sc.act[i], hj = ctx.sc.act[j];
-        atomicAdd(szszT + (size_t)hi * H + hj, qs * ctx.sc.X[i * amax + j]);  // <Lambda + kappa kappa^T>
-        if (j >= i) atomicAdd(ssT + (size_t)hi * H + hj, qs);                 // <s s^T>, upper triangle
-      }
-      __syncwarp();
-    }
+    // M-step moments with the batch's own y (NaNs were filled by the Trainer): the plain path
+    const bool saved_nan = ctx.has_nan;
+    ctx.has_nan = false;
+    ctx.template for_each_state<true>(
+        p, Ksm, S, W64, lane, [&](int s, double, int na, const SsscScratch &sc, int amax, int gl, int gs, unsigned gmask) {
+          const double qs = q[s] / se;
+          if (na > 0 && qs != 0.0) {
+            const double *kap = sc.vec + 4 * amax;
+            for (int i = gl; i < na; i += gs) {
+              const int h = sc.act[i];
+              atomicAdd(xe + h, qs);  // groups of the warp work on different states of the same datapoint
+              atomicAdd(xk + h, qs * kap[i]);
+            }
+            for (int t = gl; t < na * na; t += gs) {
+              const int i = t / na, j = t % na;
+              const int hi = sc.act[i], hj = sc.act[j];
+              atomicAdd(szszT + (size_t)hi * H + hj, qs * sc.X[i * amax + j]);  // <Lambda + kappa kappa^T>
+              if (j >= i) atomicAdd(ssT + (size_t)hi * H + hj, qs);             // <s s^T>, upper triangle
+            }
+          }
+          __syncwarp(gmask);
+        });
+    ctx.has_nan = saved_nan;
+    __syncwarp();
     for (int h = lane; h < H; h += 32) {
       const double e = xe[h], k = xk[h];
       X_out[b * (int64_t)H + h] = k;
@@ -515,13 +581,22 @@ static int sssc_gemm_A(cublasHandle_t h, const float *Wt, int Dpad, const float 
   return TVO_OK;
 }
 
-static int sssc_pick_amax(int H, size_t other_bytes, int min_wpb) {
-  const int cands[4] = {32, 24, 16, 8};
-  for (int c : cands) {
-    const int amax = H < c ? H : c;
-    if ((other_bytes + (size_t)H * 8 + sssc_scratch_bytes(amax)) * min_wpb <= (size_t)227 * 1024) return amax;
+// Global scratch rows for states with kSsscAM < |A| <= kSsscAB: one row per warp of the launch, stream-ordered.
+static int sssc_big_alloc(cudaStream_t st, int64_t warps, unsigned char **out) {
+  *out = nullptr;
+  static bool pool_set[64];
+  int dev = 0;
+  TVO_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !pool_set[dev]) {  // keep freed blocks in the pool between calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    pool_set[dev] = true;
   }
-  return 0;
+  TVO_CUDA(cudaMallocAsync((void **)out, (size_t)warps * sssc_scratch_bytes(kSsscAB), st));
+  return TVO_OK;
 }
 
 template <typename T>
@@ -551,27 +626,30 @@ int sssc_lpj(const T *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, con
   int rc = sssc_cublas(st, hb);
   if (rc) return rc;
   const SsscTheta<T> th = sssc_theta_view<T>(ws, H, D);
-  const int amax = sssc_pick_amax(H, 0, 4);
-  TVO_REQUIRE(amax > 0, "sssc_lpj: H=%d too large for shared memory", H);
-  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, amax, overflow};
+  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, nullptr, overflow};
   const size_t msm = align16(SsscModel<T>::smem_bytes(p));
   int wpb = 8;
   while (wpb > 1 && msm * wpb > (size_t)227 * 1024) wpb >>= 1;
+  TVO_REQUIRE(msm * wpb <= (size_t)227 * 1024, "sssc_lpj: H=%d too large for shared memory", H);
   auto kern = sssc_lpj_kernel<T>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(msm * wpb)));
   const int CH = S <= 32 ? S : 32;
+  const int64_t max_grid = (int64_t)sm_count() * 4;
+  rc = sssc_big_alloc(st, max_grid * wpb, &p.big);
+  if (rc) return rc;
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
     const int Bc = (int)min(cap, B - c0);
     rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, (T *)scratch, Bc, H, D);
     if (rc) return rc;
     p.Y = Y + c0 * ldY;
     const int64_t ntask = (int64_t)Bc * ((S + CH - 1) / CH);
-    const int grid = (int)max((int64_t)1, min((ntask + wpb - 1) / wpb, (int64_t)sm_count() * 4));
+    const int grid = (int)max((int64_t)1, min((ntask + wpb - 1) / wpb, max_grid));
     // rows of K / lpj are addressed through idx (or consecutively from c0)
     kern<<<grid, wpb * 32, msm * wpb, st>>>(p, idx ? K : K + c0 * k_stride_n, k_stride_n, idx ? idx + c0 : nullptr,
                                             idx ? lpj_out : lpj_out + c0 * lpj_stride_n, lpj_stride_n, Bc, S, CH, msm);
     TVO_AFTER_LAUNCH("sssc_lpj");
   }
+  TVO_CUDA(cudaFreeAsync(p.big, st));
   return TVO_OK;
 }
 
@@ -593,9 +671,9 @@ int sssc_estep(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj,
   rc = evo_params_from_cfg(cfg, S, H, ep, dims, "estep_evo_sssc");
   if (rc) return rc;
   const SsscTheta<T> th = sssc_theta_view<T>(ws, H, D);
-  const int amax = sssc_pick_amax(H, warp_buf_bytes<T>(dims), 2);
-  TVO_REQUIRE(amax > 0, "estep_evo_sssc: working set too large for shared memory");
-  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, amax, overflow};
+  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, nullptr, overflow};
+  rc = sssc_big_alloc(st, (int64_t)sm_count() * 3 * 8, &p.big);  // estep_evo_fused_kernel: <= 3 CTAs x 8 warps per SM
+  if (rc) return rc;
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
     const int Bc = (int)min(cap, B - c0);
     rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, (T *)scratch, Bc, H, D);
@@ -603,9 +681,10 @@ int sssc_estep(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj,
     p.Y = Y + c0 * ldY;
     rc = launch_estep_evo_fused<T, SsscModel<T>>(p, idx ? idx + c0 : nullptr, c0, K, lpj, cfg, sparsity, Bc, S, H, nsubs, st,
                                                  "estep_evo_sssc");
-    if (rc) return rc;
+    if (rc) break;
   }
-  return TVO_OK;
+  TVO_CUDA(cudaFreeAsync(p.big, st));
+  return rc;
 }
 
 template <typename T>
@@ -626,16 +705,17 @@ int sssc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, i
   const SsscTheta<T> th = sssc_theta_view<T>(ws, H, D);
   const int W64 = n_words(H);
   const size_t extra = (size_t)2 * H * 8 + (size_t)S * 8 + (size_t)S * W64 * 8;
-  const int amax = sssc_pick_amax(H, extra, 2);
-  TVO_REQUIRE(amax > 0, "sssc_mstep: working set too large for shared memory");
-  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, amax, overflow};
+  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, nullptr, overflow};
   const size_t wbytes = align16(SsscModel<T>::smem_bytes(p) + extra);
   int wpb = 8;
   while (wpb > 1 && wbytes * wpb > (size_t)227 * 1024) wpb >>= 1;
+  TVO_REQUIRE(wbytes * wpb <= (size_t)227 * 1024, "sssc_mstep: working set too large for shared memory");
   auto kern = sssc_mstep_kernel<T>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wbytes * wpb)));
   int occ = 1;
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, wbytes * wpb));
+  rc = sssc_big_alloc(st, (int64_t)sm_count() * max(occ, 1) * wpb, &p.big);
+  if (rc) return rc;
   const size_t HD = (size_t)H * D, HH = (size_t)H * H;
   const double one = 1.0;
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
@@ -661,6 +741,7 @@ int sssc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, i
     if (with_ssz)
       TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, H, H, Bc, &one, X, H, E, H, &one, stats + HD + 3 * HH, H));
   }
+  TVO_CUDA(cudaFreeAsync(p.big, st));
   return TVO_OK;
 }
 
