@@ -106,7 +106,7 @@ __global__ void sssc_prepare_kernel(const T *__restrict__ W, const T *__restrict
 // concurrently in sub-warp groups (scratch for up to kSsscAS active units each), then the rare denser
 // states with the full warp (up to kSsscAM units in the same shared memory, up to kSsscAB in a global
 // scratch row of the warp).  States beyond kSsscAB set the overflow flag (finfo.min, sssc.py:343-345).
-constexpr int kSsscGS = 8;   // lanes per sub-warp group
+constexpr int kSsscGS = 4;   // lanes per sub-warp group
 constexpr int kSsscNG = 32 / kSsscGS;
 constexpr int kSsscAS = 8;   // active units handled by a sub-warp group
 constexpr int kSsscAM = 16;  // ... by the full warp in shared memory
