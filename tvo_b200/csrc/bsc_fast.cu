@@ -71,7 +71,7 @@ __device__ __noinline__ T bsc_gram_lpj_walk(const uint64_t *st, int W64, int H, 
       const int h1 = (w1 << 6) + __ffsll((long long)m1) - 1;
       m1 &= m1 - 1;
       const double *Grow = G + (size_t)h1 * H;
-      f += __ldg(Grow + h1) - 2.0 * (double)a[h1];
+      f += __ldg(Grow + h1) - 2.0 * (double)__ldg(a + h1);
       pr += (double)__ldg(prior + h1);
       double g2 = 0.0;
       uint64_t m2 = m1;
@@ -115,7 +115,7 @@ __device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, co
   for (int i = 0; i < n; ++i) {
     const int h1 = plist[i * 32];
     const double *Grow = G + (size_t)h1 * H;
-    f += __ldg(Grow + h1) - 2.0 * (double)a[h1];
+    f += __ldg(Grow + h1) - 2.0 * (double)__ldg(a + h1);
     pr += (double)__ldg(prior + h1);
     double g2 = 0.0;
     for (int j = i + 1; j < n; ++j) g2 += __ldg(Grow + plist[j * 32]);
@@ -166,8 +166,10 @@ __device__ __forceinline__ void score_states(const uint64_t *states, int count, 
 
 // EVOVariationalStates.update (evo.py:80-115) for BSC, Gram form.  Same structure and same random
 // stream as estep_evo_bsc_kernel (bsc.cu); `A` holds a = W^T y for the B datapoints of this launch.
-template <typename T>
-__global__ void __launch_bounds__(256, 3)
+// MINB = 4: the per-warp working set allows 4 CTAs (32 warps) per SM, registers are capped at 64 for it;
+// MINB = 1: large H*S configurations are shared-memory-limited to a few warps per SM, no register cap.
+template <typename T, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                           int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
                           const double *__restrict__ sparsity_p, EstepDims dims, int64_t B, int H, int D,
@@ -175,10 +177,9 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
-  const size_t wbytes = warp_buf_bytes<T>(dims) + align16((size_t)H * sizeof(T));
+  const size_t wbytes = warp_buf_bytes<T>(dims);
   unsigned char *base = smem_raw + (size_t)wib * wbytes;
   const WarpBuf<T> wb = carve_warp_buf<T>(base, dims);
-  T *a_sm = (T *)(base + warp_buf_bytes<T>(dims));
   const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64;
   const double sparsity = sparsity_p ? *sparsity_p : 0.0;
   unsigned long long my_subs = 0;
@@ -210,11 +211,11 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
       }
       yy = warp_sum(yy);
       has_nan = __any_sync(FULL, has_nan);
-      for (int h = lane; h < H; h += 32) a_sm[h] = A[b * (int64_t)H + h];
       for (int t = lane; t < S * W64; t += 32) wb.oldK[t] = Krow[t];
       __syncwarp();
     }
     PHASE_SYNC();
+    const T *a_sm = A + (active ? b : 0) * (int64_t)H;  // a = W^T y row, read through L1/L2 (written by the DGEMM)
     if (active) score_states<T>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, plist, pcap, lane);  // evo.py:95
     for (int g = 0; g < ep.G; ++g) {
       const uint64_t *cand = g == 0 ? wb.oldK : wb.newK + (size_t)(g - 1) * Sgen * W64;
@@ -438,14 +439,14 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   rc = cublas_for_stream(st, hb);
   if (rc) return rc;
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
-  const size_t wbytes = warp_buf_bytes<T>(dims) + align16((size_t)H * sizeof(T));
-  // 8 warps per CTA, 3 CTAs per SM (one 24-warp CTA per SM in lockstep measured the same)
+  const size_t wbytes = warp_buf_bytes<T>(dims);
+  // 8 warps per CTA, 4 CTAs per SM at the headline shape (6.9 kB per warp)
   int wpb = 8;
   while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmemFast) wpb >>= 1;
   TVO_REQUIRE(wbytes * wpb <= (size_t)kMaxSmemFast, "estep_evo_bsc: per-datapoint working set %zu B exceeds shared memory",
               wbytes);
   const size_t smem = wbytes * wpb;
-  auto kern = estep_evo_bsc_gram_kernel<T>;
+  auto kern = smem * 4 <= (size_t)kMaxSmemFast ? estep_evo_bsc_gram_kernel<T, 4> : estep_evo_bsc_gram_kernel<T, 1>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));

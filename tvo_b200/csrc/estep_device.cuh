@@ -41,14 +41,20 @@ __host__ __device__ inline size_t keys_region_bytes(const EstepDims &d) {
   return align16(k > f ? k : f);
 }
 
+// the parents (selection / mutation) and the dedup hashes + survivor list (dedup / top-S) are never live at the
+// same time either
+__host__ __device__ inline size_t parents_hash_bytes(const EstepDims &d) {
+  const size_t p = (size_t)d.P * d.W64 * 8, h = (size_t)(((d.S + 3) & ~3) + ((d.Snew + 3) & ~3)) * 4;  // hash_len
+  return align16(p > h ? p : h);
+}
+
 template <typename T>
 __host__ __device__ inline size_t warp_buf_bytes(const EstepDims &d) {
   size_t b = 0;
-  b += align16((size_t)d.S * d.W64 * 8) + align16((size_t)d.Snew * d.W64 * 8) + align16((size_t)d.P * d.W64 * 8);
+  b += align16((size_t)d.S * d.W64 * 8) + align16((size_t)d.Snew * d.W64 * 8) + parents_hash_bytes(d);
   b += keys_region_bytes(d);
   b += align16(d.need_fit ? (size_t)d.Scmax * 8 : 0);
   b += align16((size_t)(d.S + d.Snew) * sizeof(T));
-  b += align16((size_t)(((d.S + 3) & ~3) + ((d.Snew + 3) & ~3)) * 4);  // hash_len(S, Snew)
   const int isz = d.Scmax > 2 * d.Sgen ? d.Scmax : 2 * d.Sgen;
   b += align16((size_t)isz * 4);
   return b;
@@ -62,7 +68,8 @@ __device__ inline WarpBuf<T> carve_warp_buf(unsigned char *p, const EstepDims &d
   w.newK = (uint64_t *)p;
   p += align16((size_t)d.Snew * d.W64 * 8);
   w.parents = (uint64_t *)p;
-  p += align16((size_t)d.P * d.W64 * 8);
+  w.hash = (uint32_t *)p;
+  p += parents_hash_bytes(d);
   w.keys = (uint64_t *)p;
   w.fmask = (uint64_t *)p;
   p += keys_region_bytes(d);
@@ -70,8 +77,6 @@ __device__ inline WarpBuf<T> carve_warp_buf(unsigned char *p, const EstepDims &d
   p += align16(d.need_fit ? (size_t)d.Scmax * 8 : 0);
   w.lpj = (T *)p;
   p += align16((size_t)(d.S + d.Snew) * sizeof(T));
-  w.hash = (uint32_t *)p;
-  p += align16((size_t)(((d.S + 3) & ~3) + ((d.Snew + 3) & ~3)) * 4);
   w.iscr = (int32_t *)p;
   return w;
 }
