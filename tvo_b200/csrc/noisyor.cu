@@ -76,22 +76,30 @@ __device__ inline T nor_state_lpj(const uint64_t *st, int W64, const NorTheta<T>
   if (!any) return any_y ? T(-1e30) : T(0);  // noisyor.py:83-86,102
   const T lo = (T)kNorEps, hi = T(1) - (T)kNorEps;
   T acc = T(0), pr = T(0);
-  for (int c = 0, ci = 0; c < th.Dpad; c += 32, ++ci) {
-    T P = T(1);
+  // the set bits are walked once per group of 4 column chunks (128 observables), products in registers
+  for (int c0 = 0, ci0 = 0; c0 < th.Dpad; c0 += 128, ci0 += 4) {
+    T P[4] = {T(1), T(1), T(1), T(1)};
     for (int w = 0; w < W64; ++w) {
       uint64_t word = st[w];
       while (word) {
         const int h = (w << 6) + __ffsll((long long)word) - 1;
         word &= word - 1;
-        P *= __ldg(th.W1mT + (size_t)h * th.Dpad + c + lane);
-        if (c == 0) pr += __ldg(th.prior + h);
+        const T *row = th.W1mT + (size_t)h * th.Dpad + c0 + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c0 + 32 * q < th.Dpad) P[q] *= __ldg(row + 32 * q);
+        if (c0 == 0) pr += __ldg(th.prior + h);
       }
     }
-    if (c + lane < D) {
-      P = P < lo ? lo : (P > hi ? hi : P);  // to.clamp (noisyor.py:89)
-      const bool yd = (ybits[ci >> 5] >> (ci & 31)) & 1u;
-      // y log(1/P - 1) + log P  ==  y ? log(1 - P) : log P   (noisyor.py:91-97)
-      acc += yd ? log(T(1) - P) : log(P);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (c0 + 32 * q + lane < D) {
+        T Pc = P[q] < lo ? lo : (P[q] > hi ? hi : P[q]);  // to.clamp (noisyor.py:89)
+        const int ci = ci0 + q;
+        const bool yd = (ybits[ci >> 5] >> (ci & 31)) & 1u;
+        // y log(1/P - 1) + log P  ==  y ? log(1 - P) : log P   (noisyor.py:91-97)
+        acc += log(yd ? T(1) - Pc : Pc);
+      }
     }
   }
   return pr + warp_sum(acc);
