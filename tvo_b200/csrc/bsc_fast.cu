@@ -252,8 +252,6 @@ bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
   const int W64 = n_words(H);
   unsigned char *p = smem_raw + (size_t)wib * warp_bytes;
-  uint64_t *Ksm = (uint64_t *)p;
-  p += align16((size_t)S * W64 * 8);
   double *q = (double *)p;
   p += align16((size_t)S * 8);
   double *Esm = (double *)p;
@@ -275,7 +273,6 @@ bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict
     const T *l = lpj + row * lpj_stride_n;
     const T *y = Y + b * ldY;
     __syncwarp();
-    for (int t = lane; t < S * W64; t += 32) Ksm[t] = Kn[t];
     for (int h = lane; h < H; h += 32) Esm[h] = 0.0;
     // softmax weights (lpj2pjc, _utils.py:182-191)
     double mx = -INFINITY;
@@ -305,7 +302,7 @@ bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict
     for (int s = lane; s < S; s += 32) {
       const double qs = q[s] * inv_se;
       q[s] = qs;
-      const uint64_t *st = Ksm + (size_t)s * W64;
+      const uint64_t *st = Kn + (size_t)s * W64;  // lane s reads its own 8*W64 contiguous bytes: coalesced, no staging
       double pr = 0.0;
       int n = 0, w = 0;
       uint64_t m = st[0];
@@ -365,7 +362,7 @@ bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict
         for (int c = 0; c < th.Dpad; c += 32) {
           T a = T(0);
           for (int w = 0; w < W64; ++w) {
-            uint64_t word = Ksm[(size_t)s * W64 + w];
+            uint64_t word = Kn[(size_t)s * W64 + w];
             while (word) {
               const int h = (w << 6) + __ffsll((long long)word) - 1;
               word &= word - 1;
@@ -395,8 +392,7 @@ bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict
 
 template <typename T>
 static size_t bsc_mstep_warp_bytes(int S, int H) {
-  return align16((size_t)S * n_words(H) * 8) + align16((size_t)S * 8) + 2 * align16((size_t)H * 8) +
-         (size_t)kMstepListCap * 32 * 2;
+  return align16((size_t)S * 8) + 2 * align16((size_t)H * 8) + (size_t)kMstepListCap * 32 * 2;
 }
 
 // ------------------------------------------------------------------------------------ host side
