@@ -539,6 +539,44 @@ def test_estep_baseline_shape_properties():
 
 
 # ----------------------------------------------------------------------------- trainer / generic models
+def test_estep_c5_shape_properties_and_oracle_subset():
+    """BASELINE configs[4] shape (BSC H=1024 D=256 S=128, P=16 C=4 G=2 => S'=128, fp64): the size-independent
+    properties on 2000 datapoints and a bit-exact oracle comparison on 6 of them."""
+    np.random.seed(0)
+    N, H, D, S, P, Cn, G = 2000, 1024, 256, 128, 16, 4, 2
+    tvo_b200._set_device(to.device(DEV))
+    rng = np.random.default_rng(5)
+    Wgen = rng.standard_normal((D, H))
+    Y = ((rng.random((N, H)) < 8.0 / H) @ Wgen.T + rng.standard_normal((N, D)))
+    W0 = Wgen + 0.5 * rng.standard_normal((D, H))
+    pies = np.full(H, 1.0 / H)
+    m = BSC(H, D, dev(W0), to.tensor([1.0], dtype=to.float64), dev(pies), precision=to.float64)
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", P, G, Cn, bitflip_frequency=1.0 / H, seed=11)
+    K0 = st.K.unpack().cpu().numpy()
+    idx = to.arange(N, device=DEV)
+    Yd = dev(Y)
+    sub = np.array([0, 1, 999, 1500, 1998, 1999])
+    o = om.BSC(H, D, W0, [1.0], pies)
+    Kw = K0[sub]
+    prev_sum = None
+    for it in range(2):
+        Kw, Lw, _ = oracle_estep(o, Y[sub], Kw, np.float64, "randparents", "sparseflip", P, Cn, G, 1.0 / H, sub, 11, it,
+                                 sparsity=float(m._tvo_sparsity().item()))
+        nsubs = st.update(idx, Yd, m)
+        assert 0 < nsubs <= N * S
+        lpj = st.lpj
+        assert bool((lpj[:, 1:] >= lpj[:, :-1]).all())
+        if prev_sum is not None:
+            assert bool((lpj.sum(dim=1) >= prev_sum - 1e-6).all())
+        prev_sum = lpj.sum(dim=1).clone()
+        assert to.allclose(m._tvo_lpj_packed(Yd, st._Kp, H), lpj, rtol=1e-12, atol=1e-9)
+        rows = to.cat([idx[:, None, None].expand(-1, S, 1), st._Kp], dim=2).reshape(N * S, -1)
+        assert to.unique(rows, dim=0).shape[0] == N * S
+        got = st.K.unpack()[dev(sub)].cpu().numpy()
+        assert np.array_equal(got, Kw), f"K differs from the oracle at step {it}"
+        assert np.allclose(lpj[dev(sub)].cpu().numpy(), Lw, rtol=RT64, atol=RT64)
+
+
 def test_trainer_golden_bsc_fullem():
     g = load_golden("trainer_bsc_fullem.npz")
     tvo_b200._set_device(to.device(DEV))
