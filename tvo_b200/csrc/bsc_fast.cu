@@ -166,20 +166,26 @@ __device__ __forceinline__ void score_states(const uint64_t *states, int count, 
 
 // EVOVariationalStates.update (evo.py:80-115) for BSC, Gram form.  Same structure and same random
 // stream as estep_evo_bsc_kernel (bsc.cu); `A` holds a = W^T y for the B datapoints of this launch.
-// MINB = 4: the per-warp working set allows 4 CTAs (32 warps) per SM, registers are capped at 64 for it;
-// MINB = 1: large H*S configurations are shared-memory-limited to a few warps per SM, no register cap.
+// MINB = 4: the per-warp working set allows 4 CTAs (32 warps) per SM, registers are capped at 64 for it, the old
+//           states are staged in shared memory;
+// MINB = 1: large H*S shapes are shared-memory-limited to a few warps per SM: no register cap, and the old states
+//           stay in global memory (dims.old_in_global; compile-time here so that the staged variant keeps plain
+//           shared-memory loads for wb.oldK).
 template <typename T, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                           int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
                           const double *__restrict__ sparsity_p, EstepDims dims, int64_t B, int H, int D,
-                          unsigned long long *nsubs) {
+                          unsigned long long *nsubs, uint64_t *stage_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
   const size_t wbytes = warp_buf_bytes<T>(dims);
   unsigned char *base = smem_raw + (size_t)wib * wbytes;
-  const WarpBuf<T> wb = carve_warp_buf<T>(base, dims);
+  WarpBuf<T> wb = carve_warp_buf<T>(base, dims);
+  // large H*S shapes: the old states stay in global memory (L1/L2), the merge goes through this warp's staging row
+  constexpr bool kOldInGlobal = MINB == 1;
+  uint64_t *stage = kOldInGlobal ? stage_rows + ((size_t)blockIdx.x * wpb + wib) * dims.S * dims.W64 : nullptr;
   const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64;
   const double sparsity = sparsity_p ? *sparsity_p : 0.0;
   unsigned long long my_subs = 0;
@@ -211,7 +217,11 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
       }
       yy = warp_sum(yy);
       has_nan = __any_sync(FULL, has_nan);
-      for (int t = lane; t < S * W64; t += 32) wb.oldK[t] = Krow[t];
+      if (kOldInGlobal) {
+        wb.oldK = Krow;
+      } else {
+        for (int t = lane; t < S * W64; t += 32) wb.oldK[t] = Krow[t];
+      }
       __syncwarp();
     }
     PHASE_SYNC();
@@ -232,7 +242,7 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
     PHASE_SYNC();
     if (active) mark_redundant<T>(wb, S, Snew, W64, lane);
     PHASE_SYNC();
-    if (active) my_subs += (unsigned long long)select_topS<T>(wb, S, Snew, W64, Krow, lrow, lane);
+    if (active) my_subs += (unsigned long long)select_topS<T>(wb, S, Snew, W64, Krow, lrow, lane, stage);
   }
 #undef PHASE_SYNC
   if (lane == 0 && my_subs) atomicAdd(nsubs, my_subs);
@@ -435,18 +445,26 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   rc = cublas_for_stream(st, hb);
   if (rc) return rc;
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
-  const size_t wbytes = warp_buf_bytes<T>(dims);
-  // 8 warps per CTA, 4 CTAs per SM at the headline shape (6.9 kB per warp)
+  size_t wbytes = warp_buf_bytes<T>(dims);
+  // 8 warps per CTA, 4 CTAs per SM at the headline shape (6.9 kB per warp).  Working sets that do not allow that
+  // (large H*S) leave the old states in global memory instead of staging them: more resident warps.
+  if (wbytes * 8 * 4 > (size_t)kMaxSmemFast) {
+    dims.old_in_global = 1;
+    wbytes = warp_buf_bytes<T>(dims);
+  }
   int wpb = 8;
   while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmemFast) wpb >>= 1;
   TVO_REQUIRE(wbytes * wpb <= (size_t)kMaxSmemFast, "estep_evo_bsc: per-datapoint working set %zu B exceeds shared memory",
               wbytes);
   const size_t smem = wbytes * wpb;
-  auto kern = smem * 4 <= (size_t)kMaxSmemFast ? estep_evo_bsc_gram_kernel<T, 4> : estep_evo_bsc_gram_kernel<T, 1>;
+  auto kern = dims.old_in_global ? estep_evo_bsc_gram_kernel<T, 1> : estep_evo_bsc_gram_kernel<T, 4>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
   occ = max(occ, 1);
+  uint64_t *stage_rows = nullptr;
+  if (dims.old_in_global)
+    TVO_CUDA(cudaMallocAsync((void **)&stage_rows, (size_t)sm_count() * occ * wpb * S * dims.W64 * 8, st));
   T *A = (T *)scratch_a;
   if (use_tab) {
     FlipEntry *tab = (FlipEntry *)scratch;
@@ -462,10 +480,11 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
     void *tok;
     kernel_timing_begin(TVO_TIMED_ESTEP_EVO_BSC, st, &tok);
     kern<<<grid, wpb * 32, smem, st>>>(Y + c0 * ldY, ldY, A, idx ? idx + c0 : nullptr, c0, K, lpj, ws, ep, sparsity, dims,
-                                       Bc, H, D, (unsigned long long *)nsubs);
+                                       Bc, H, D, (unsigned long long *)nsubs, stage_rows);
     kernel_timing_end(tok, st);
     TVO_AFTER_LAUNCH("estep_evo_bsc_gram");
   }
+  if (stage_rows) TVO_CUDA(cudaFreeAsync(stage_rows, st));
   return TVO_OK;
 }
 

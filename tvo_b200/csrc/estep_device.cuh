@@ -20,6 +20,10 @@ struct EstepDims {
   int Dpad;    // padded observables (0 when y is not staged)
   int Scmax;   // max candidates a selection sees = max(S, Sgen)
   int need_fit;  // cum_p scratch needed
+  int need_fmask;     // separate flip-mask buffer (sparseflip in place on crossed children); otherwise the masks
+                      // are built in the children's own slots
+  int old_in_global;  // the S old states are NOT staged in shared memory: WarpBuf::oldK points at the K row in
+                      // global memory (large H*S working sets) and the top-S merge goes through a staging row
 };
 
 template <typename T>
@@ -37,7 +41,7 @@ struct WarpBuf {
 
 // keys (select) and fmask (mutation) are never live at the same time: one region
 __host__ __device__ inline size_t keys_region_bytes(const EstepDims &d) {
-  const size_t k = (size_t)(d.S + d.Snew) * 8, f = (size_t)d.Sgen * d.W64 * 8;
+  const size_t k = (size_t)(d.S + d.Snew) * 8, f = d.need_fmask ? (size_t)d.Sgen * d.W64 * 8 : 0;
   return align16(k > f ? k : f);
 }
 
@@ -51,7 +55,8 @@ __host__ __device__ inline size_t parents_hash_bytes(const EstepDims &d) {
 template <typename T>
 __host__ __device__ inline size_t warp_buf_bytes(const EstepDims &d) {
   size_t b = 0;
-  b += align16((size_t)d.S * d.W64 * 8) + align16((size_t)d.Snew * d.W64 * 8) + parents_hash_bytes(d);
+  b += (d.old_in_global ? 0 : align16((size_t)d.S * d.W64 * 8)) + align16((size_t)d.Snew * d.W64 * 8) +
+       parents_hash_bytes(d);
   b += keys_region_bytes(d);
   b += align16(d.need_fit ? (size_t)d.Scmax * 8 : 0);
   b += align16((size_t)(d.S + d.Snew) * sizeof(T));
@@ -63,8 +68,8 @@ __host__ __device__ inline size_t warp_buf_bytes(const EstepDims &d) {
 template <typename T>
 __device__ inline WarpBuf<T> carve_warp_buf(unsigned char *p, const EstepDims &d) {
   WarpBuf<T> w;
-  w.oldK = (uint64_t *)p;
-  p += align16((size_t)d.S * d.W64 * 8);
+  w.oldK = d.old_in_global ? nullptr : (uint64_t *)p;  // old_in_global: the kernel points it at the K row
+  p += d.old_in_global ? 0 : align16((size_t)d.S * d.W64 * 8);
   w.newK = (uint64_t *)p;
   p += align16((size_t)d.Snew * d.W64 * 8);
   w.parents = (uint64_t *)p;
@@ -560,7 +565,8 @@ __device__ inline void evo_generation(const WarpBuf<T> &wb, const uint64_t *cand
       mutate_randflip(wb.parents, ep.P, ep.C, W64, H, st, wb.iscr, children, lane);
       break;
     case TVO_MUT_SPARSEFLIP:
-      mutate_sparseflip(wb.parents, ep.P, ep.C, W64, H, sparsity, ep.p_bf, s0, s1, wb.fmask, children, lane, ep.flip_tab);
+      mutate_sparseflip(wb.parents, ep.P, ep.C, W64, H, sparsity, ep.p_bf, s0, s1, /*fmask=*/children, children, lane,
+                        ep.flip_tab);  // the masks are built in the children's own slots
       break;
     default: {
       st.tag = make_tag(ep.step, gen, PUR_CROSS);
@@ -855,9 +861,11 @@ __device__ __forceinline__ bool select_merge(const WarpBuf<T> &wb, int S, int Sn
   return true;
 }
 
+// `stage` (S*W64 words, private to the warp) is required when wb.oldK aliases K_row (old states not staged in
+// shared memory): the selected rows are assembled there first, then copied over the K row.
 template <typename T>
 __device__ inline int select_topS(const WarpBuf<T> &wb, int S, int Snew, int W64, uint64_t *K_row, T *lpj_row,
-                                  int lane) {
+                                  int lane, uint64_t *stage = nullptr) {
   const int M = S + Snew;
   for (int i = lane; i < M; i += 32) wb.keys[i] = sort_key((double)wb.lpj[i]);
   __syncwarp();
@@ -886,12 +894,17 @@ __device__ inline int select_topS(const WarpBuf<T> &wb, int S, int Snew, int W64
     }
   }
   __syncwarp();
+  uint64_t *dst = stage ? stage : K_row;
   for (int t = lane; t < S * W64; t += 32) {
     const int src = wb.iscr[t / W64];
     const uint64_t *row = src < S ? wb.oldK + (size_t)src * W64 : wb.newK + (size_t)(src - S) * W64;
-    K_row[t] = row[t % W64];
+    dst[t] = row[t % W64];
   }
   __syncwarp();
+  if (stage) {
+    for (int t = lane; t < S * W64; t += 32) K_row[t] = stage[t];
+    __syncwarp();
+  }
   return warp_sum(nsub);
 }
 

@@ -87,6 +87,8 @@ int evo_params_from_cfg(const tvo_evo_config *cfg, int S, int H, EvoParams &ep, 
   dims.Dpad = 0;
   dims.Scmax = S > Sgen ? S : Sgen;
   dims.need_fit = ep.sel != TVO_SEL_RANDPARENTS;
+  dims.need_fmask = ep.mut == TVO_MUT_CROSS_SPARSEFLIP;
+  dims.old_in_global = 0;
   return TVO_OK;
 }
 
