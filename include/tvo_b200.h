@@ -196,6 +196,41 @@ int tvo_sample_states_probs_f32(uint64_t *out, int64_t out_stride_n, int32_t S_o
                                 int64_t probs_stride_n, const int64_t *idx, int64_t B, int32_t S_new, int32_t H,
                                 uint64_t seed, uint32_t step, uint32_t group, uint32_t n_offset, void *stream);
 
+/* ---- single-cause mixture models under full EM ----
+ * GMM (tvo/models/gmm.py:91-180) and PMM (tvo/models/pmm.py:76-153) with FullEMSingleCauseModels
+ * (tvo/variational/fullem.py:61-82: K_n = identity, every cause evaluated for every datapoint).
+ * kind: 0 = GMM, 1 = PMM.  W is (D,H) row-major, pies (H), sigma2 (1, GMM only), all in the model precision.
+ *   tvo_mixture_prepare: digest theta into `ws` (tvo_mixture_ws_bytes).
+ *   tvo_mixture_lpj:     lpj_out[row, c] for all c < H, row = idx ? idx[b] : b  (log_pseudo_joint with K = identity).
+ *   tvo_mixture_mstep:   update_param_batch: stats (tvo_mixture_stats_len doubles)
+ *                        [Wp^T (H*D) | sum_n q (H) = my_Wq = my_pies | my_sigma2 | N | F]  +=  this batch;
+ *                        `scratch` (tvo_mixture_scratch_bytes) holds the posterior weights of one chunk for the
+ *                        Wp += Y^T q GEMM.
+ *   tvo_mixture_free_energy: *F_out += sum_b logsumexp_c log_joint  (model_protocols.py:179-193). */
+int64_t tvo_mixture_ws_bytes(int32_t H, int32_t D, int32_t is_f64);
+int64_t tvo_mixture_stats_len(int32_t H, int32_t D);
+int64_t tvo_mixture_scratch_bytes(int64_t B, int32_t H, int32_t D, int32_t is_f64);
+int tvo_mixture_prepare_f64(int32_t kind, const double *W, const double *pies, const double *sigma2, int32_t H, int32_t D,
+                            void *ws, void *stream);
+int tvo_mixture_prepare_f32(int32_t kind, const float *W, const float *pies, const float *sigma2, int32_t H, int32_t D,
+                            void *ws, void *stream);
+int tvo_mixture_lpj_f64(int32_t kind, const double *Y, int64_t ldY, const int64_t *idx, const void *ws, double *lpj_out,
+                        int64_t lpj_stride_n, int64_t B, int32_t H, int32_t D, void *stream);
+int tvo_mixture_lpj_f32(int32_t kind, const float *Y, int64_t ldY, const int64_t *idx, const void *ws, float *lpj_out,
+                        int64_t lpj_stride_n, int64_t B, int32_t H, int32_t D, void *stream);
+int tvo_mixture_mstep_f64(int32_t kind, const double *Y, int64_t ldY, const int64_t *idx, const double *lpj,
+                          int64_t lpj_stride_n, const void *ws, double *stats, void *scratch, int64_t scratch_bytes,
+                          int64_t B, int32_t H, int32_t D, void *stream);
+int tvo_mixture_mstep_f32(int32_t kind, const float *Y, int64_t ldY, const int64_t *idx, const float *lpj,
+                          int64_t lpj_stride_n, const void *ws, double *stats, void *scratch, int64_t scratch_bytes,
+                          int64_t B, int32_t H, int32_t D, void *stream);
+int tvo_mixture_free_energy_f64(int32_t kind, const double *Y, int64_t ldY, const int64_t *idx, const double *lpj,
+                                int64_t lpj_stride_n, const void *ws, int64_t B, int32_t H, int32_t D, double *F_out,
+                                void *stream);
+int tvo_mixture_free_energy_f32(int32_t kind, const float *Y, int64_t ldY, const int64_t *idx, const float *lpj,
+                                int64_t lpj_stride_n, const void *ws, int64_t B, int32_t H, int32_t D, double *F_out,
+                                void *stream);
+
 /* ---- posterior weights: lpj2pjc / mean_posterior (_utils.py:182-230) ---- */
 int tvo_lpj2pjc_f64(const double *lpj, double *pjc, int64_t N, int32_t S, void *stream);
 int tvo_lpj2pjc_f32(const float *lpj, float *pjc, int64_t N, int32_t S, void *stream);

@@ -270,3 +270,97 @@ class SSSC:
         W = th["W"]
         th["sigma2"][:] = (self.sum_diag_yyT.sum() - np.trace(self.sum_xpt_sz_xpt_szT @ (W.T @ W))) / N / D + eps
         self._zero()
+
+
+class _Mixture:
+    """Shared bookkeeping of the single-cause mixture models (gmm.py:82-88, pmm.py:70-75)."""
+
+    def _zero(self):
+        D, H, p = self.D, self.H, self.precision
+        self.my_Wp = np.zeros((D, H), p)
+        self.my_Wq = np.zeros(H, p)
+        self.my_pies = np.zeros(H, p)
+        self.my_sigma2 = np.zeros(1, p)
+        self.my_N = 0
+
+    def free_energy(self, data, states, lpj):  # model_protocols.py:179-193
+        return float(logsumexp(self.log_joint(data, states, lpj), axis=1).sum())
+
+
+class GMM(_Mixture):
+    """tvo/models/gmm.py:20-221.  ``states`` is float/uint8 (N,S,H); single-cause use passes eye(H) per datapoint."""
+
+    def __init__(self, H, D, W_init, sigma2_init, pies_init, precision=np.float64):
+        self.H, self.D, self.precision = H, D, precision
+        self.theta = {"pies": np.array(pies_init, dtype=precision), "W": np.array(W_init, dtype=precision),
+                      "sigma2": np.array(sigma2_init, dtype=precision).reshape(1)}
+        self._zero()
+
+    def log_pseudo_joint(self, data, states):  # gmm.py:91-102
+        th = self.theta
+        Kf = states.astype(th["W"].dtype)
+        Wbar = Kf @ th["W"].T
+        return ((Wbar - data[:, None, :]) ** 2).sum(axis=2) * (-1 / 2 / th["sigma2"]) + Kf @ np.log(th["pies"])
+
+    def log_joint(self, data, states, lpj=None):  # gmm.py:104-109
+        if lpj is None:
+            lpj = self.log_pseudo_joint(data, states)
+        return lpj - self.D / 2 * np.log(2 * math.pi * self.theta["sigma2"])
+
+    def update_param_batch(self, batch, K, lpj):  # gmm.py:111-131
+        Kf = K.astype(lpj.dtype)
+        Wbar = Kf @ self.theta["W"].T
+        s_pjc = mean_posterior(Kf, lpj)
+        self.my_pies += s_pjc.sum(axis=0)
+        self.my_Wp += batch.T @ s_pjc
+        self.my_Wq += s_pjc.sum(axis=0)
+        self.my_sigma2 += mean_posterior(((batch[:, None, :] - Wbar) ** 2).sum(axis=2), lpj).sum()
+        self.my_N += batch.shape[0]
+
+    def update_param_epoch(self):  # gmm.py:133-180
+        th, N, D = self.theta, self.my_N, self.D
+        eps = 1.0e-5
+        with np.errstate(all="ignore"):
+            W_new = self.my_Wp / self.my_Wq[None, :]
+        th["W"] = _fix(W_new, th["W"], None, None)
+        th["pies"] = _fix(self.my_pies / N, th["pies"], eps, 1.0 - eps)
+        th["sigma2"] = _fix(self.my_sigma2 / N / D, th["sigma2"], eps, None)
+        self._zero()
+
+
+class PMM(_Mixture):
+    """tvo/models/pmm.py:20-198 (Poisson mixture)."""
+
+    def __init__(self, H, D, W_init, pies_init, precision=np.float64):
+        self.H, self.D, self.precision = H, D, precision
+        self.theta = {"pies": np.array(pies_init, dtype=precision), "W": np.array(W_init, dtype=precision)}
+        self._zero()
+
+    def log_pseudo_joint(self, data, states):  # pmm.py:76-91
+        th = self.theta
+        Kf = states.astype(th["W"].dtype)
+        Wbar = Kf @ th["W"].T + np.finfo(np.float32).tiny
+        return (data[:, None, :] * np.log(Wbar)).sum(axis=2) - Wbar.sum(axis=2) + Kf @ np.log(th["pies"])
+
+    def log_joint(self, data, states, lpj=None):  # pmm.py:93-97
+        from scipy.special import gammaln
+        if lpj is None:
+            lpj = self.log_pseudo_joint(data, states)
+        return lpj - gammaln(data + 1).sum(axis=1)[:, None]
+
+    def update_param_batch(self, batch, K, lpj):  # pmm.py:99-113
+        Kf = K.astype(lpj.dtype)
+        s_pjc = mean_posterior(Kf, lpj)
+        self.my_pies += s_pjc.sum(axis=0)
+        self.my_Wp += batch.T @ s_pjc
+        self.my_Wq += s_pjc.sum(axis=0)
+        self.my_N += batch.shape[0]
+
+    def update_param_epoch(self):  # pmm.py:115-153
+        th, N = self.theta, self.my_N
+        eps = 1.0e-5
+        with np.errstate(all="ignore"):
+            W_new = self.my_Wp / self.my_Wq[None, :]
+        th["W"] = _fix(W_new, th["W"], eps, None)
+        th["pies"] = _fix(self.my_pies / N, th["pies"], eps, 1.0 - eps)
+        self._zero()

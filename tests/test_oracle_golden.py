@@ -411,3 +411,27 @@ def test_tvs_sampling_rates_and_layout():
     # a different step / seed gives a different draw, the same arguments the same draw
     assert np.array_equal(new, oevo.tvs_new_states(K, lpj, pies, 40, 30, np.arange(N), 11, 0))
     assert not np.array_equal(new, oevo.tvs_new_states(K, lpj, pies, 40, 30, np.arange(N), 11, 1))
+
+
+# ----------------------------------------------------------------------------- mixtures (gmm.py / pmm.py)
+@pytest.mark.parametrize("name,prec,tol", [("gmm_f64", np.float64, 1e-10), ("gmm_f32", np.float32, 2e-5),
+                                           ("pmm_f64", np.float64, 1e-10)])
+def test_golden_mixtures(name, prec, tol):
+    g = load_golden(f"{name}.npz")
+    D, H = g["theta0_W"].shape
+    N = g["Y"].shape[0]
+    m = (om.GMM(H, D, g["theta0_W"], g["theta0_sigma2"], g["theta0_pies"], precision=prec) if name.startswith("gmm")
+         else om.PMM(H, D, g["theta0_W"], g["theta0_pies"], precision=prec))
+    K = np.tile(np.eye(H, dtype=prec)[None], (N, 1, 1))   # FullEMSingleCauseModels (fullem.py:79)
+    Y = g["Y"].astype(prec)
+    lpj = m.log_pseudo_joint(Y, K)
+    assert np.allclose(lpj, g["lpj"], rtol=tol, atol=tol)
+    assert np.allclose(m.log_joint(Y, K, lpj), g["log_joint"], rtol=tol, atol=tol * 10)
+    assert math.isclose(m.free_energy(Y, K, lpj), float(g["F"]), rel_tol=max(tol, 1e-12))
+    m.update_param_batch(Y, K, lpj)
+    assert np.allclose(m.my_Wp, g["my_Wp"], rtol=tol * 10, atol=tol * 10)
+    assert np.allclose(m.my_pies, g["my_pies"], rtol=tol * 10) and m.my_N == int(np.asarray(g["my_N"]).reshape(-1)[0])
+    m.update_param_epoch()
+    for k in m.theta:
+        assert np.allclose(m.theta[k], g["theta1_" + k], rtol=tol * 10, atol=tol * 10), k
+    assert math.isclose(m.free_energy(Y, K, m.log_pseudo_joint(Y, K)), float(g["F2"]), rel_tol=max(tol * 10, 1e-12))

@@ -19,8 +19,8 @@ sys.path.insert(0, ROOT)
 from oracle.ref_loader import import_reference  # noqa: E402
 
 tvo = import_reference()
-from tvo.models import BSC, NoisyOR, SSSC  # noqa: E402
-from tvo.variational import FullEM, EVOVariationalStates  # noqa: E402
+from tvo.models import BSC, NoisyOR, SSSC, GMM, PMM  # noqa: E402
+from tvo.variational import FullEM, EVOVariationalStates, FullEMSingleCauseModels  # noqa: E402
 from tvo.variational import evo as ref_evo  # noqa: E402
 from tvo.variational._utils import (  # noqa: E402
     set_redundant_lpj_to_low, update_states_for_batch, lpj2pjc, mean_posterior)
@@ -151,6 +151,44 @@ def golden_sssc():
             Psi_new=m.theta["Psi"], sigma2_new=m.theta["sigma2"], **acc)))
 
 
+def golden_mixtures():
+    """GMM / PMM with FullEMSingleCauseModels (gmm.py:91-180, pmm.py:76-143, fullem.py:61-82): lpj, log_joint,
+    free energy, accumulators after one batch, theta after the epoch update, F after a second E-step."""
+    rng = np.random.default_rng(12)
+    for name, prec in (("gmm_f64", to.float64), ("gmm_f32", to.float32), ("pmm_f64", to.float64)):
+        N, D, H = 23, 7, 5
+        to.manual_seed(3)
+        if name.startswith("gmm"):
+            W = rng.standard_normal((D, H)) * 2
+            Y = (W[:, rng.integers(0, H, N)].T + 0.7 * rng.standard_normal((N, D)))
+            m = GMM(H, D, to.tensor(W + 0.3 * rng.standard_normal((D, H))), to.tensor([0.9]),
+                    to.tensor(rng.dirichlet(np.ones(H))), precision=prec)
+        else:
+            W = rng.uniform(0.5, 9.0, (D, H))
+            Y = rng.poisson(W[:, rng.integers(0, H, N)].T).astype(np.float64)
+            m = PMM(H, D, to.tensor(W * rng.uniform(0.7, 1.3, (D, H))), to.tensor(rng.dirichlet(np.ones(H))),
+                    precision=prec)
+        theta0 = {k: v.clone() for k, v in m.theta.items()}
+        st = FullEMSingleCauseModels(N, H, prec)
+        Yt = to.tensor(Y, dtype=prec)
+        idx = to.arange(N)
+        st.update(idx, Yt, m)
+        lpj = st.lpj.clone()
+        lj = m.log_joint(Yt, st.K, lpj)
+        F = m.free_energy(idx, Yt, st)
+        m.update_param_batch(idx, Yt, st)
+        acc = {"my_Wp": m.my_Wp.clone(), "my_Wq": m.my_Wq.clone(), "my_pies": m.my_pies.clone(), "my_N": m.my_N.clone()}
+        if hasattr(m, "my_sigma2"):
+            acc["my_sigma2"] = m.my_sigma2.clone()
+        m.update_param_epoch()
+        st.update(idx, Yt, m)
+        F2 = m.free_energy(idx, Yt, st)
+        out = dict(Y=Y, lpj=lpj, log_joint=lj, F=F, F2=F2, lpj2=st.lpj.clone(), **acc)
+        out.update({f"theta0_{k}": v for k, v in theta0.items()})
+        out.update({f"theta1_{k}": v for k, v in m.theta.items()})
+        np.savez(os.path.join(OUT, f"{name}.npz"), **_np(out))
+
+
 def golden_dedup_merge():
     rng = np.random.default_rng(4)
     N, S, Snew, H, Ntot = 12, 6, 9, 4, 20  # H=4 -> many collisions
@@ -254,11 +292,9 @@ def golden_trainer():
 
 if __name__ == "__main__":
     to.set_default_dtype(to.float32)
-    golden_bsc()
-    golden_noisyor()
-    golden_sssc()
-    golden_dedup_merge()
-    golden_evo_stats()
-    golden_trainer()
+    todo = {"bsc": golden_bsc, "noisyor": golden_noisyor, "sssc": golden_sssc, "dedup_merge": golden_dedup_merge,
+            "evo_stats": golden_evo_stats, "trainer": golden_trainer, "mixtures": golden_mixtures}
+    for name in (sys.argv[1:] or list(todo)):  # python tools/make_golden.py [name ...]
+        todo[name]()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

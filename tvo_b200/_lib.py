@@ -58,6 +58,9 @@ _PROTOS = {
     "tvo_sssc_theta_ws_bytes": [_I32, _I32, _I32],
     "tvo_sssc_stats_len": [_I32, _I32],
     "tvo_sssc_scratch_bytes": [_I64, _I32, _I32, _I32],
+    "tvo_mixture_ws_bytes": [_I32, _I32, _I32],
+    "tvo_mixture_stats_len": [_I32, _I32],
+    "tvo_mixture_scratch_bytes": [_I64, _I32, _I32, _I32],
 }
 for _sfx in ("f64", "f32"):
     _PROTOS.update({
@@ -71,6 +74,10 @@ for _sfx in ("f64", "f32"):
         f"tvo_estep_evo_bsc_{_sfx}": [_P, _I64, _P, _P, _P, _P, C.POINTER(EvoConfig), _P, _P, _I64, _I64, _I32, _I32,
                                       _I32, _P, _P],
         f"tvo_lpj2pjc_{_sfx}": [_P, _P, _I64, _I32, _P],
+        f"tvo_mixture_prepare_{_sfx}": [_I32, _P, _P, _P, _I32, _I32, _P, _P],
+        f"tvo_mixture_lpj_{_sfx}": [_I32, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _P],
+        f"tvo_mixture_mstep_{_sfx}": [_I32, _P, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _P],
+        f"tvo_mixture_free_energy_{_sfx}": [_I32, _P, _I64, _P, _P, _I64, _P, _I64, _I32, _I32, _P, _P],
         f"tvo_state_marginals_{_sfx}": [_P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _P],
         f"tvo_sample_states_probs_{_sfx}": [_P, _I64, _I32, _P, _I64, _P, _I64, _I32, _I32, _U64, _U32, _U32, _U32, _P],
         f"tvo_mean_posterior_{_sfx}": [_P, _P, _P, _I64, _I32, _I64, _P],
@@ -103,6 +110,9 @@ _RESTYPES = {
     "tvo_sssc_theta_ws_bytes": _I64,
     "tvo_sssc_stats_len": _I64,
     "tvo_sssc_scratch_bytes": _I64,
+    "tvo_mixture_ws_bytes": _I64,
+    "tvo_mixture_stats_len": _I64,
+    "tvo_mixture_scratch_bytes": _I64,
 }
 
 _lib = None
