@@ -71,8 +71,31 @@ elif cfg == "c4":
     model = NoisyOR(H, D, to.rand(D, H, device=dev, generator=g), to.full((H,), 1.0 / H), precision=to.float32)
     states = EVOVariationalStates(N, H, S, to.float32, "fitparents_fixed", "randflip", P, G, crossover=True, seed=5)
     name = "C4 NoisyOR D100 H64 S64 EVO(fitparents_fixed,cross_randflip,P8,G1) fp32"
+elif cfg in ("gmm", "pmm"):
+    from tvo_b200.models import GMM, PMM
+    from tvo_b200.variational import FullEMSingleCauseModels
+    N = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+    H, D = 256, 144
+    if cfg == "gmm":
+        Wgen = 3 * to.randn(D, H, dtype=to.float64, device=dev, generator=g)
+        Y = to.empty(N, D, dtype=to.float64, device=dev)
+        for b0, b1 in chunks(N):
+            c = to.randint(0, H, (b1 - b0,), device=dev, generator=g)
+            Y[b0:b1] = Wgen.t()[c] + to.randn(b1 - b0, D, dtype=to.float64, device=dev, generator=g)
+        model = GMM(H, D, Wgen + to.randn(D, H, dtype=to.float64, device=dev, generator=g), to.tensor([2.0]),
+                    to.full((H,), 1.0 / H), precision=to.float64)
+    else:
+        Wgen = 1 + 9 * to.rand(D, H, dtype=to.float64, device=dev, generator=g)
+        Y = to.empty(N, D, dtype=to.float64, device=dev)
+        for b0, b1 in chunks(N):
+            c = to.randint(0, H, (b1 - b0,), device=dev, generator=g)
+            Y[b0:b1] = to.poisson(Wgen.t()[c])
+        model = PMM(H, D, Wgen * (0.5 + to.rand(D, H, dtype=to.float64, device=dev, generator=g)),
+                    to.full((H,), 1.0 / H), precision=to.float64)
+    states = FullEMSingleCauseModels(N, H, to.float64)
+    name = f"{cfg.upper()} full EM, single cause, D144 C256 fp64"
 else:
-    raise SystemExit("usage: bench_configs.py c3|c4|c5 [N] [iters]")
+    raise SystemExit("usage: bench_configs.py c3|c4|c5|gmm|pmm [N] [iters]")
 
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 idx = to.arange(N, device=dev)
