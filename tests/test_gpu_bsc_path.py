@@ -601,6 +601,48 @@ def test_trainer_golden_bsc_fullem():
         prev = F
 
 
+def test_c1_bars_em_epochs_match_oracle():
+    """BASELINE configs[0] (examples/bars-test): BSC H=8 D=16 N=500, EVO S=60 with fitness-proportional parents
+    (the reference's batch-global normaliser), randflip, P=5 C=3 G=2, batches of 32.  Three EM epochs through
+    Trainer.em_step against the oracle's EM loop: K bit-exact after every epoch, theta and F within 1e-8."""
+    rng = np.random.default_rng(42)
+    np.random.seed(1)
+    N, H, D, S, P, Cn, G, B = 500, 8, 16, 60, 5, 3, 2, 32
+    Wb = np.zeros((D, H))
+    for i in range(4):                       # 4 horizontal + 4 vertical bars on a 4x4 grid (tvo/utils/gen.py:9-47)
+        Wb.reshape(4, 4, H)[i, :, i] = 1.0
+        Wb.reshape(4, 4, H)[:, i, 4 + i] = 1.0
+    Y = (rng.random((N, H)) < 2.0 / H) @ Wb.T + 0.1 * rng.standard_normal((N, D))
+    W0 = Y.mean(axis=0)[:, None] + 0.1 * rng.standard_normal((D, H))      # init_W_data_mean
+    s20, pies0 = np.array([Y.var()]), np.full(H, 1.0 / H)
+    tvo_b200._set_device(to.device(DEV))
+    m = BSC(H, D, dev(W0), dev(s20), dev(pies0), precision=to.float64)
+    m.W_solver = "cpu"
+    st = EVOVariationalStates(N, H, S, to.float64, "batch_fitparents", "randflip", P, G, Cn, seed=13)
+    K = st.K.unpack().cpu().numpy().copy()
+    o = om.BSC(H, D, W0, s20, pies0)
+    tr = Trainer(m, TVODataLoader(dev(Y), batch_size=B), st)      # no shuffling: batches in index order
+    step = 0
+    Fs = []
+    for ep in range(3):
+        F_or = 0.0
+        for b0 in range(0, N, B):
+            sl = np.arange(b0, min(N, b0 + B))
+            Kb, Lb, _ = oracle_estep(o, Y[sl], K[sl], np.float64, "batch_fitparents", "randflip", P, Cn, G, None, sl, 13, step)
+            K[sl] = Kb
+            o.update_param_batch(Y[sl], Kb, Lb)
+            F_or += o.free_energy(Y[sl], Kb, Lb)
+            step += 1
+        o.update_param_epoch()
+        res = tr.em_step()
+        assert np.array_equal(st.K.unpack().cpu().numpy(), K), f"K differs after epoch {ep}"
+        assert math.isclose(res["train_F"] * N, F_or, rel_tol=1e-8)
+        for k in ("W", "pies", "sigma2"):
+            assert np.allclose(m.theta[k].cpu().numpy(), o.theta[k], rtol=1e-8, atol=1e-10), (ep, k)
+        Fs.append(res["train_F"])
+    assert Fs[-1] > Fs[0]
+
+
 def test_trainer_evo_bsc_free_energy_increases():
     rng = np.random.default_rng(0)
     np.random.seed(0)
