@@ -295,10 +295,18 @@ def run_gpu(args):
         dp_per_launch = N * args.steps / max(k_n, 1)
         launch_ms = k_ms / max(k_n, 1)
         achieved = ALG_BYTES_PER_DP * dp_per_launch / (launch_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, issue = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tj["estep_evo_bsc_bytes_per_dp"] * dp_per_launch
+            # second reading of the same launch: warp instructions issued per second against the scheduler peak
+            # (SMs x 4 schedulers x SM clock); the kernel is bound here, not by HBM
+            sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+            ipd = tj["estep_evo_bsc_warp_instructions_per_dp"]
+            ach = ipd * dp_per_launch / (launch_ms * 1e-3)
+            peak = 148 * 4 * sm_clock * 1e6
+            issue = {"achieved_warp_inst_per_s": ach, "peak_warp_inst_per_s": peak, "frac": ach / peak,
+                     "warp_instructions_per_datapoint": ipd, "source": "profiles/traffic.json (ncu smsp__inst_executed.sum)"}
         except Exception:
             pass
         line = {
@@ -326,10 +334,10 @@ def run_gpu(args):
                          "traffic_source": "profiles/traffic.json (ncu --set full dram bytes per datapoint x datapoints per launch)",
                          "share_of_estep": k_ms / args.steps / estep_ms,
                          "dense_equivalent_tflops": ALG_FLOP_PER_DP * N / (estep_ms * 1e-3) / 1e12,
-                         "mstep_kernel_ms_per_step": m_ms / args.steps,
+                         "mstep_kernel_ms_per_step": m_ms / args.steps, "issue_roofline": issue,
                          "note": "the kernel's DRAM traffic equals its algorithmic bytes (+ the a = W^T y row), but it is "
-                                 "bound by integer-ALU issue (selection, mutation, dedup, sort: ~7.5k warp instructions "
-                                 "per datapoint at ~54% issue utilisation), not by HBM; see DESIGN.md section 5"},
+                                 "bound by integer-ALU issue (selection, mutation, dedup, sort: ~7.7k warp instructions "
+                                 "per datapoint, see issue_roofline), not by HBM; see DESIGN.md section 5"},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(n_per_core=args.cpu_n_per_core).items()
