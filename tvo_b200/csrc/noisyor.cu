@@ -302,18 +302,19 @@ template <typename T>
 __global__ void __launch_bounds__(512, 2)
 nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx,
                      const uint64_t *__restrict__ K, int64_t k_stride_n, const T *__restrict__ lpj, int64_t lpj_stride_n,
-                     const void *ws, double *__restrict__ stats, int64_t B, int S, int H, int D) {
+                     const T *__restrict__ W1mT, const double *__restrict__ prior_sum, double *__restrict__ stats,
+                     int64_t B, int S, int H, int D, int W64, int Dpad, int q_off, int k_off) {
+  // W64, Dpad and the shared-memory offsets are kernel parameters (constant bank) on purpose: with 64 registers
+  // the compiler re-derived them from H, D and S inside the loops (19% of the executed instructions)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const NorTheta<T> th = nor_theta_view<T>(ws, H, D);
-  const int W64 = n_words(H), Dpad = th.Dpad;
   const int tid = threadIdx.x, lane = tid & 31;
   const int HG = 512 / Dpad, Ht = kNorHpt * HG;
   const int d = tid % Dpad, hg = tid / Dpad;
   const int h0 = blockIdx.y * Ht;          // first h of the tile (multiple of 8)
   const int hb = h0 + hg * kNorHpt;        // first h of this thread
-  T *Qsm = (T *)smem_raw;                                           // S x Dpad
-  double *q = (double *)(smem_raw + align16((size_t)S * Dpad * sizeof(T)));  // S
-  uint64_t *Ksm = (uint64_t *)(q + S);                              // S x W64
+  T *Qsm = (T *)smem_raw;                            // S x Dpad
+  double *q = (double *)(smem_raw + q_off);          // S
+  uint64_t *Ksm = (uint64_t *)(smem_raw + k_off);    // S x W64
   __shared__ double red[2];
   double accB[kNorHpt], accC[kNorHpt];  // the only long-lived per-thread state (32 registers)
 #pragma unroll
@@ -321,7 +322,7 @@ nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *
     accB[j] = 0.0;
     accC[j] = 0.0;
   }
-  const T *Wcol = th.W1mT + (size_t)min(hb, H - 1) * Dpad + d;  // 1 - W_dh of this thread's h (L1-resident)
+  const T *Wcol = W1mT + (size_t)min(hb, H - 1) * Dpad + d;  // 1 - W_dh of this thread's h (L1-resident)
   double pi_acc = 0.0, accF = 0.0, accN = 0.0;  // pi: thread tid < Ht owns h0 + tid
   const T eps = (T)kNorEps;
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
@@ -329,7 +330,9 @@ nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *
     const T *l = lpj + row * lpj_stride_n;
     __syncthreads();  // previous datapoint fully consumed
     for (int t = tid; t < S * W64; t += 512) Ksm[t] = K[row * k_stride_n + t];
-    if (tid < 32) {  // softmax weights by warp 0 (lpj2pjc, _utils.py:182-191)
+    const T ym1 = (d < D ? (T)Y[b * ldY + d] : T(1)) - T(1);  // issued early: consumed in phase 2
+    __syncthreads();
+    if (tid < 32) {  // softmax weights by warp 0 (lpj2pjc, _utils.py:182-191) while the other warps start phase 1
       double mx = -INFINITY;
       for (int s = lane; s < S; s += 32) mx = fmax(mx, (double)l[s]);
       mx = warp_max(mx);
@@ -343,24 +346,24 @@ nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *
       for (int s = lane; s < S; s += 32) q[s] = q[s] / se;  // q_s, normalised once
       if (lane == 0) red[1] = mx + log(se);
     }
-    __syncthreads();
-    if (tid == 0 && blockIdx.y == 0) {
-      accF += red[1] + th.hdr->prior_sum;
-      accN += 1.0;
-    }
     // phase 1: Q_sd over ALL active h of the state (noisyor.py:123-124), ascending h
     for (int s = hg; s < S; s += HG) {
-      const uint64_t *st = Ksm + (size_t)s * W64;
+      const uint64_t *st = Ksm + s * W64;
       T Q = T(1);
       for (int w = 0; w < W64; ++w) {
         uint64_t word = st[w];
         while (word) {
           const int h = (w << 6) + __ffsll((long long)word) - 1;
           word &= word - 1;
-          Q *= __ldg(th.W1mT + (size_t)h * Dpad + d);
+          Q *= __ldg(W1mT + (size_t)h * Dpad + d);
         }
       }
-      Qsm[(size_t)s * Dpad + d] = Q;
+      Qsm[s * Dpad + d] = Q;
+    }
+    __syncthreads();
+    if (tid == 0 && blockIdx.y == 0) {
+      accF += red[1] + *prior_sum;
+      accN += 1.0;
     }
     if (tid < Ht && h0 + tid < H) {  // new_pi += <s_h>  (noisyor.py:117)
       const int h = h0 + tid;
@@ -369,27 +372,32 @@ nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *
         if ((Ksm[s * W64 + (h >> 6)] >> (h & 63)) & 1ull) e += q[s];
       pi_acc += e;
     }
-    __syncthreads();
     // phase 2: Btilde, Ctilde (noisyor.py:121-132) for this thread's 8 h and column d
     if (hb < H) {
-      const T ym1 = (d < D ? (T)Y[b * ldY + d] : T(1)) - T(1);
-      const int sh = hb & 63;
-      const uint64_t *kp = Ksm + (hb >> 6);
-      const T *qp = Qsm + d;
-      for (int s = 0; s < S; ++s, kp += W64, qp += Dpad) {
-        const uint32_t m = (uint32_t)(*kp >> sh) & 0xFFu;
-        if (m == 0) continue;  // warp-uniform
-        const double qs = q[s];
-        const T Q = *qp;
-        const T omq = T(1) - Q;
+      const int sh = hb & 63, wsel = hb >> 6;
+      // a warp shares its h-group (Dpad is a multiple of 32): 32 states are tested at once, one per lane, and
+      // only the states with an active unit in the group are visited
+      for (int s0 = 0; s0 < S; s0 += 32) {
+        const int sl = s0 + lane;
+        const uint32_t ml = sl < S ? (uint32_t)(Ksm[sl * W64 + wsel] >> sh) & 0xFFu : 0u;
+        unsigned act = __ballot_sync(FULL, ml != 0u);
+        while (act) {
+          const int src = __ffs((int)act) - 1;
+          act &= act - 1;
+          const uint32_t m = __shfl_sync(FULL, ml, src);
+          const int s = s0 + src;
+          const double qs = q[s];
+          const T Q = Qsm[s * Dpad + d];
+          const T omq = T(1) - Q;
 #pragma unroll
-        for (int j = 0; j < kNorHpt; ++j) {
-          if ((m >> j) & 1u) {
-            const T Ws = __ldg(Wcol + j * Dpad);
-            const T Bv = nor_div(T(1), Ws * omq + eps);
-            const T Cv = nor_div(Bv * Q, Ws);
-            accB[j] += qs * (double)(Bv * ym1);
-            accC[j] += qs * (double)Cv;
+          for (int j = 0; j < kNorHpt; ++j) {
+            if ((m >> j) & 1u) {
+              const T Ws = __ldg(Wcol + j * Dpad);
+              const T Bv = nor_div(T(1), Ws * omq + eps);
+              const T Cv = nor_div(Bv * Q, Ws);
+              accB[j] += qs * (double)(Bv * ym1);
+              accC[j] += qs * (double)Cv;
+            }
           }
         }
       }
@@ -467,8 +475,11 @@ int nor_mstep(const uint8_t *Y, int64_t ldY, const int64_t *idx, const uint64_t 
       int occ2 = 1;
       TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, 512, smem2));
       const int gx2 = (int)max((int64_t)1, min(B, (int64_t)max(1, sm_count() * max(occ2, 1) / ntile)));
-      kern2<<<dim3(gx2, ntile), 512, smem2, (cudaStream_t)stream>>>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, ws, stats,
-                                                                    B, S, H, D);
+      const NorTheta<T> th2 = nor_theta_view<T>(ws, H, D);
+      const int q_off = (int)align16((size_t)S * Dpad * sizeof(T)), k_off = q_off + S * 8;
+      kern2<<<dim3(gx2, ntile), 512, smem2, (cudaStream_t)stream>>>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, th2.W1mT,
+                                                                    &th2.hdr->prior_sum, stats, B, S, H, D, W64, Dpad, q_off,
+                                                                    k_off);
       TVO_AFTER_LAUNCH("noisyor_mstep_reg");
       return TVO_OK;
     }
