@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Aggregate the CUDA-source view of an `ncu --page source --csv --print-source sass,cuda` dump by the
 device FUNCTION each source line belongs to (function spans are read from the current source files).
-usage: tools/ncu_funcs.py src.csv [kernel-substring]"""
+usage: tools/ncu_funcs.py src.csv [kernel-substring] [column]"""
 import csv, re, sys, collections, os
 path = sys.argv[1]; want = sys.argv[2] if len(sys.argv) > 2 else ""
+colname = sys.argv[3] if len(sys.argv) > 3 else "Instructions Executed"  # e.g. "# Samples", "stall_long_sb"
 rows = list(csv.reader(open(path)))
 spans = {}
 def func_spans(fpath):
@@ -32,7 +33,7 @@ while i < len(rows):
             body.append(rows[j]); j += 1
         cols = {n: k for k, n in enumerate(hdr)}
         if want in fn and "Line No" in cols and fpath and fpath.endswith((".cu", ".cuh")):
-            ie = cols["Instructions Executed"]; ln = cols["Line No"]
+            ie = cols[colname]; ln = cols["Line No"]
             sp = func_spans(fpath)
             for b in body:
                 try: n = float(b[ie]); l = int(b[ln])

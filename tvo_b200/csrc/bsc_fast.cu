@@ -11,12 +11,14 @@
 // per chunk so that  WpT += E^T Y  is one DGEMM (the union of active bits per datapoint is ~100 of 256,
 // so the outer product is effectively dense).
 #include <cublas_v2.h>
+#include <cstdlib>
 
 #include "bsc_device.cuh"
 
 namespace tvo {
 
 constexpr int kMaxSmemFast = 227 * 1024;
+constexpr int kMaxWarpsLarge = 12;  // warps per CTA of the one-CTA-per-SM E-step variant (large H*S)
 
 int evo_params_from_cfg(const tvo_evo_config *cfg, int S, int H, EvoParams &ep, EstepDims &dims, const char *who);
 template <typename T>
@@ -91,25 +93,59 @@ __device__ __noinline__ T bsc_gram_lpj_walk(const uint64_t *st, int W64, int H, 
   return (T)((yy + f) * coef + pr);
 }
 
+// Active positions of one state (ascending) into the lane-strided list plist[j * 32]; returns |s| (entries beyond
+// `cap` are counted, not stored).  The words are fetched four at a time — four loads in flight instead of a
+// load -> test -> load chain, which matters when the state sits in global memory (old states of large H*S shapes,
+// the M-step) — and each group is walked with ONE "next set bit of the group" loop, so a warp iterates
+// max-over-lanes(bits in the group) times (H <= 256: one group).
+// GROUPED = false: one "next set bit of the whole state" loop, words loaded as they are reached (states in shared
+// memory; fewer instructions, iterations = max-over-lanes |s|).
+template <bool GROUPED>
+__device__ __forceinline__ int position_list(const uint64_t *st, int W64, uint16_t *plist, int cap) {
+  int n = 0;
+  if (!GROUPED) {
+    int w = 0;
+    uint64_t m = st[0];
+    while (true) {
+      while (m == 0 && ++w < W64) m = st[w];
+      if (w >= W64) break;
+      const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+      const int pos = (w << 6) + (lo ? __ffs((int)lo) - 1 : 32 + __ffs((int)hi) - 1);
+      m &= m - 1;
+      if (n < cap) plist[n * 32] = (uint16_t)pos;
+      ++n;
+    }
+    return n;
+  }
+  for (int w0 = 0; w0 < W64; w0 += 4) {
+    const uint64_t d0 = st[w0], d1 = w0 + 1 < W64 ? st[w0 + 1] : 0ull, d2 = w0 + 2 < W64 ? st[w0 + 2] : 0ull,
+                   d3 = w0 + 3 < W64 ? st[w0 + 3] : 0ull;
+    uint64_t m = d0;
+    int u = 0;
+    while (true) {
+      while (m == 0 && ++u < 4) m = u == 1 ? d1 : (u == 2 ? d2 : d3);
+      if (u >= 4) break;
+      const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+      const int pos = ((w0 + u) << 6) + (lo ? __ffs((int)lo) - 1 : 32 + __ffs((int)hi) - 1);
+      m &= m - 1;
+      if (n < cap) plist[n * 32] = (uint16_t)pos;
+      ++n;
+    }
+  }
+  return n;
+}
+
 // Same sums in the same order, but the active positions are first written to a lane-strided list in
 // shared memory (plist[j * 32], the lane's base already applied), so the |s|(|s|-1)/2 pair loop is
 // LDS + address + LDG + DADD instead of a 64-bit find-first-set / clear-lowest-bit walk per pair.
-template <typename T>
+// LAT: latency-oriented variant for the shapes that run at a few warps per SM (grouped position list, four
+// gathers in flight); the 32-warps-per-SM shapes are issue-bound and keep the shorter code.
+template <typename T, bool LAT>
 __device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, const T *a, const double *__restrict__ G,
                                           const T *__restrict__ prior, double yy, double coef, uint16_t *plist, int cap) {
   // states are sparse (|s| ~ 1-5 of H): walk the set bits with one loop over "next set bit of the multi-word
   // mask" (empty words cost one test) instead of a bit loop per half word
-  int n = 0, w = 0;
-  uint64_t m = st[0];
-  while (true) {
-    while (m == 0 && ++w < W64) m = st[w];
-    if (w >= W64) break;
-    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-    const int pos = (w << 6) + (lo ? __ffs((int)lo) - 1 : 32 + __ffs((int)hi) - 1);
-    m &= m - 1;
-    if (n < cap) plist[n * 32] = (uint16_t)pos;
-    ++n;
-  }
+  const int n = position_list<LAT>(st, W64, plist, cap);
   if (n > cap) return bsc_gram_lpj_walk<T>(st, W64, H, a, G, prior, yy, coef);
   double f = 0.0, pr = 0.0;
   for (int i = 0; i < n; ++i) {
@@ -118,7 +154,16 @@ __device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, co
     f += __ldg(Grow + h1) - 2.0 * (double)__ldg(a + h1);
     pr += (double)__ldg(prior + h1);
     double g2 = 0.0;
-    for (int j = i + 1; j < n; ++j) g2 += __ldg(Grow + plist[j * 32]);
+    int j = i + 1;
+    for (; LAT && j + 4 <= n; j += 4) {  // four gathers in flight, summed in list order (same result as the plain loop)
+      const double v0 = __ldg(Grow + plist[j * 32]), v1 = __ldg(Grow + plist[(j + 1) * 32]),
+                   v2 = __ldg(Grow + plist[(j + 2) * 32]), v3 = __ldg(Grow + plist[(j + 3) * 32]);
+      g2 += v0;
+      g2 += v1;
+      g2 += v2;
+      g2 += v3;
+    }
+    for (; j < n; ++j) g2 += __ldg(Grow + plist[j * 32]);
     f += 2.0 * g2;
   }
   return (T)((yy + f) * coef + pr);
@@ -148,16 +193,16 @@ __device__ inline T bsc_direct_lpj_slow(const uint64_t *st, int W64, const BscTh
   return warp_sum(ss) * coef + pr;
 }
 
-template <typename T>
+template <typename T, bool LAT>
 __device__ __forceinline__ void score_states(const uint64_t *states, int count, int W64, int H, int D, const BscTheta<T> &th,
                                              const T *a_sm, const T *__restrict__ y, double yy, bool has_nan, T *out,
-                                             uint16_t *plist, int pcap, int lane) {
+                                             uint16_t *plist, int pcap, int lane, int rs) {
   if (!has_nan) {
     for (int s = lane; s < count; s += 32)
-      out[s] = bsc_gram_lpj<T>(states + (size_t)s * W64, W64, H, a_sm, th.G, th.prior, yy, th.hdr->coef, plist + lane, pcap);
+      out[s] = bsc_gram_lpj<T, LAT>(states + (size_t)s * rs, W64, H, a_sm, th.G, th.prior, yy, th.hdr->coef, plist + lane, pcap);
   } else {
     for (int s = 0; s < count; ++s) {
-      const T v = bsc_direct_lpj_slow<T>(states + (size_t)s * W64, W64, th, y, D, lane, (T)th.hdr->coef);
+      const T v = bsc_direct_lpj_slow<T>(states + (size_t)s * rs, W64, th, y, D, lane, (T)th.hdr->coef);
       if (lane == 0) out[s] = v;
     }
   }
@@ -172,7 +217,7 @@ __device__ __forceinline__ void score_states(const uint64_t *states, int count, 
 //           stay in global memory (dims.old_in_global; compile-time here so that the staged variant keeps plain
 //           shared-memory loads for wb.oldK).
 template <typename T, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+__global__ void __launch_bounds__(MINB == 1 ? 32 * kMaxWarpsLarge : 256, MINB)
 estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                           int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
                           const double *__restrict__ sparsity_p, EstepDims dims, int64_t B, int H, int D,
@@ -226,23 +271,23 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
     }
     PHASE_SYNC();
     const T *a_sm = A + (active ? b : 0) * (int64_t)H;  // a = W^T y row, read through L1/L2 (written by the DGEMM)
-    if (active) score_states<T>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, plist, pcap, lane);  // evo.py:95
+    if (active) score_states<T, kOldInGlobal>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, plist, pcap, lane, W64);  // evo.py:95
     for (int g = 0; g < ep.G; ++g) {
-      const uint64_t *cand = g == 0 ? wb.oldK : wb.newK + (size_t)(g - 1) * Sgen * W64;
+      const uint64_t *cand = g == 0 ? wb.oldK : wb.newK + (size_t)(g - 1) * Sgen * wb.rs;
       const T *cand_lpj = g == 0 ? wb.lpj : wb.lpj + S + (g - 1) * Sgen;
-      uint64_t *children = wb.newK + (size_t)g * Sgen * W64;
+      uint64_t *children = wb.newK + (size_t)g * Sgen * wb.rs;
       PHASE_SYNC();
       if (active)
         evo_generation<T>(wb, cand, cand_lpj, g == 0 ? S : Sgen, children, ep, g, n_glob, W64, H, sparsity, 0.0, 1.0,
-                          lane);
+                          lane, g == 0 ? W64 : wb.rs);
       PHASE_SYNC();
-      if (active) score_states<T>(children, Sgen, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj + S + g * Sgen, plist, pcap,
-                                  lane);
+      if (active) score_states<T, kOldInGlobal>(children, Sgen, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj + S + g * Sgen, plist, pcap,
+                                  lane, wb.rs);
     }
     PHASE_SYNC();
     if (active) mark_redundant<T>(wb, S, Snew, W64, lane);
     PHASE_SYNC();
-    if (active) my_subs += (unsigned long long)select_topS<T>(wb, S, Snew, W64, Krow, lrow, lane, stage);
+    if (active) my_subs += (unsigned long long)select_topS<T, kOldInGlobal>(wb, S, Snew, W64, Krow, lrow, lane, stage);
   }
 #undef PHASE_SYNC
   if (lane == 0 && my_subs) atomicAdd(nsubs, my_subs);
@@ -314,17 +359,7 @@ bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict
       q[s] = qs;
       const uint64_t *st = Kn + (size_t)s * W64;  // lane s reads its own 8*W64 contiguous bytes: coalesced, no staging
       double pr = 0.0;
-      int n = 0, w = 0;
-      uint64_t m = st[0];
-      while (true) {
-        while (m == 0 && ++w < W64) m = st[w];
-        if (w >= W64) break;
-        const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-        const int pos = (w << 6) + (lo ? __ffs((int)lo) - 1 : 32 + __ffs((int)hi) - 1);
-        m &= m - 1;
-        if (n < lcap) plist[n * 32 + lane] = (uint16_t)pos;
-        ++n;
-      }
+      const int n = position_list<true>(st, W64, plist + lane, lcap);
       if (n <= lcap) {
         for (int i = 0; i < n; ++i) {
           const int h1 = plist[i * 32 + lane];
@@ -450,14 +485,19 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   // (large H*S) leave the old states in global memory instead of staging them: more resident warps.
   if (wbytes * 8 * 4 > (size_t)kMaxSmemFast) {
     dims.old_in_global = 1;
+    if (!getenv("TVO_EXP_NOPAD")) dims.RS = dims.W64 | 1;  // conflict-free per-lane row access (see EstepDims::RS)
     wbytes = warp_buf_bytes<T>(dims);
   }
-  int wpb = 8;
+  auto kern = dims.old_in_global ? estep_evo_bsc_gram_kernel<T, 1> : estep_evo_bsc_gram_kernel<T, 4>;
+  // the one-CTA-per-SM variant takes as many warps as its shared memory holds (up to 12: it is latency-bound and
+  // every resident warp counts; 10 at H=1024 S=128)
+  int wpb = dims.old_in_global ? (int)min((size_t)kMaxWarpsLarge, (size_t)kMaxSmemFast / wbytes) : 8;
+  if (wpb > 8 && getenv("TVO_EXP_WPB")) wpb = atoi(getenv("TVO_EXP_WPB"));
+  if (wpb < 1) wpb = 1;
   while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmemFast) wpb >>= 1;
   TVO_REQUIRE(wbytes * wpb <= (size_t)kMaxSmemFast, "estep_evo_bsc: per-datapoint working set %zu B exceeds shared memory",
               wbytes);
   const size_t smem = wbytes * wpb;
-  auto kern = dims.old_in_global ? estep_evo_bsc_gram_kernel<T, 1> : estep_evo_bsc_gram_kernel<T, 4>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));

@@ -130,9 +130,20 @@ __device__ __forceinline__ uint64_t sort_key(double x) {
 
 __device__ __forceinline__ uint32_t hash_words(const uint64_t *s, int W64) {
   uint64_t h = 0x9E3779B97F4A7C15ull;
-  for (int w = 0; w < W64; ++w) {
-    h ^= s[w];
-    h *= 0xff51afd7ed558ccdull;
+  int w = 0;
+  for (; w + 4 <= W64; w += 4) {  // four loads in flight (the states may sit in global memory), mixed in order
+    const uint64_t a0 = s[w], a1 = s[w + 1], a2 = s[w + 2], a3 = s[w + 3];
+    h = (h ^ a0) * 0xff51afd7ed558ccdull;
+    h ^= h >> 32;
+    h = (h ^ a1) * 0xff51afd7ed558ccdull;
+    h ^= h >> 32;
+    h = (h ^ a2) * 0xff51afd7ed558ccdull;
+    h ^= h >> 32;
+    h = (h ^ a3) * 0xff51afd7ed558ccdull;
+    h ^= h >> 32;
+  }
+  for (; w < W64; ++w) {
+    h = (h ^ s[w]) * 0xff51afd7ed558ccdull;
     h ^= h >> 32;
   }
   return (uint32_t)h;

@@ -22,6 +22,9 @@ struct EstepDims {
   int need_fit;  // cum_p scratch needed
   int need_fmask;     // separate flip-mask buffer (sparseflip in place on crossed children); otherwise the masks
                       // are built in the children's own slots
+  int RS;             // row stride (words) of the children / parents / flip-mask rows in shared memory; 0 = W64.
+                      // W64 | 1 makes "lane j reads word w of row j" conflict-free (stride W64 = 16 words is a 32-way
+                      // bank conflict); used by the large-H*S variant of the fused BSC kernel
   int old_in_global;  // the S old states are NOT staged in shared memory: WarpBuf::oldK points at the K row in
                       // global memory (large H*S working sets) and the top-S merge goes through a staging row
 };
@@ -37,25 +40,27 @@ struct WarpBuf {
   T *lpj;             // S+Snew
   uint32_t *hash;     // S+Snew
   int32_t *iscr;      // max(Scmax, 2*Sgen)
+  int rs;             // row stride of newK / parents / fmask (words); oldK rows are always W64 apart
 };
+__host__ __device__ inline int row_stride(const EstepDims &d) { return d.RS ? d.RS : d.W64; }
 
 // keys (select) and fmask (mutation) are never live at the same time: one region
 __host__ __device__ inline size_t keys_region_bytes(const EstepDims &d) {
-  const size_t k = (size_t)(d.S + d.Snew) * 8, f = d.need_fmask ? (size_t)d.Sgen * d.W64 * 8 : 0;
+  const size_t k = (size_t)(d.S + d.Snew) * 8, f = d.need_fmask ? (size_t)d.Sgen * row_stride(d) * 8 : 0;
   return align16(k > f ? k : f);
 }
 
 // the parents (selection / mutation) and the dedup hashes + survivor list (dedup / top-S) are never live at the
 // same time either
 __host__ __device__ inline size_t parents_hash_bytes(const EstepDims &d) {
-  const size_t p = (size_t)d.P * d.W64 * 8, h = (size_t)(((d.S + 3) & ~3) + ((d.Snew + 3) & ~3)) * 4;  // hash_len
+  const size_t p = (size_t)d.P * row_stride(d) * 8, h = (size_t)(((d.S + 3) & ~3) + ((d.Snew + 3) & ~3)) * 4;  // hash_len
   return align16(p > h ? p : h);
 }
 
 template <typename T>
 __host__ __device__ inline size_t warp_buf_bytes(const EstepDims &d) {
   size_t b = 0;
-  b += (d.old_in_global ? 0 : align16((size_t)d.S * d.W64 * 8)) + align16((size_t)d.Snew * d.W64 * 8) +
+  b += (d.old_in_global ? 0 : align16((size_t)d.S * d.W64 * 8)) + align16((size_t)d.Snew * row_stride(d) * 8) +
        parents_hash_bytes(d);
   b += keys_region_bytes(d);
   b += align16(d.need_fit ? (size_t)d.Scmax * 8 : 0);
@@ -70,8 +75,9 @@ __device__ inline WarpBuf<T> carve_warp_buf(unsigned char *p, const EstepDims &d
   WarpBuf<T> w;
   w.oldK = d.old_in_global ? nullptr : (uint64_t *)p;  // old_in_global: the kernel points it at the K row
   p += d.old_in_global ? 0 : align16((size_t)d.S * d.W64 * 8);
+  w.rs = row_stride(d);
   w.newK = (uint64_t *)p;
-  p += align16((size_t)d.Snew * d.W64 * 8);
+  p += align16((size_t)d.Snew * row_stride(d) * 8);
   w.parents = (uint64_t *)p;
   w.hash = (uint32_t *)p;
   p += parents_hash_bytes(d);
@@ -163,8 +169,9 @@ __device__ __forceinline__ void randparents_sort(int S_c, int P, int bits, const
   }
 }
 
+// cs / ps: row strides (words) of the candidate and parent rows
 __device__ inline void select_randparents(const uint64_t *cand, int S_c, int P, int W64, const Stream &st,
-                                          int32_t *scr, uint64_t *parents, int lane) {
+                                          int32_t *scr, uint64_t *parents, int lane, int cs, int ps) {
   const int bits = index_bits(S_c);
   if (S_c <= 256) {
     if (S_c <= 32)
@@ -176,7 +183,10 @@ __device__ inline void select_randparents(const uint64_t *cand, int S_c, int P, 
     else
       randparents_sort<8>(S_c, P, bits, st, scr, lane);
     __syncwarp();
-    for (int t = lane; t < P * W64; t += 32) parents[t] = cand[scr[t / W64] * W64 + t % W64];
+    for (int t = lane; t < P * W64; t += 32) {
+      const int r = t / W64, w = t - r * W64;
+      parents[r * ps + w] = cand[scr[r] * cs + w];
+    }
   } else {  // large candidate sets: rank every key by counting (same result, O(S_c^2 / 32) per datapoint)
     const uint32_t himask = ~((1u << bits) - 1u);
     for (int i = lane; i < S_c; i += 32) scr[i] = (int32_t)((st.u32(0, (uint32_t)i) & himask) | (uint32_t)i);
@@ -187,7 +197,7 @@ __device__ inline void select_randparents(const uint64_t *cand, int S_c, int P, 
       int rank = 0;
       for (int j = 0; j < S_c; ++j) rank += ((uint32_t)scr[j] < ki) ? 1 : 0;
       if (i < S_c && rank < P)
-        for (int w = 0; w < W64; ++w) parents[rank * W64 + w] = cand[i * W64 + w];
+        for (int w = 0; w < W64; ++w) parents[rank * ps + w] = cand[i * cs + w];
     }
   }
   __syncwarp();
@@ -200,7 +210,7 @@ __device__ inline void select_randparents(const uint64_t *cand, int S_c, int P, 
 template <typename T>
 __device__ inline void select_fitparents(const uint64_t *cand, const T *cand_lpj, int S_c, int P, int W64,
                                          const Stream &st, bool fixed, double m_glob, double T_glob, double *cum,
-                                         int32_t *chosen, uint64_t *parents, int lane) {
+                                         int32_t *chosen, uint64_t *parents, int lane, int cs, int ps) {
   if (lane == 0) {
     double m = m_glob, Tn = T_glob;
     if (fixed) {
@@ -233,7 +243,10 @@ __device__ inline void select_fitparents(const uint64_t *cand, const T *cand_lpj
     chosen[i] = c;
   }
   __syncwarp();
-  for (int t = lane; t < P * W64; t += 32) parents[t] = cand[chosen[t / W64] * W64 + t % W64];
+  for (int t = lane; t < P * W64; t += 32) {
+    const int r = t / W64, w = t - r * W64;
+    parents[r * ps + w] = cand[chosen[r] * cs + w];
+  }
   __syncwarp();
 }
 
@@ -242,8 +255,11 @@ __device__ inline void select_fitparents(const uint64_t *cand, const T *cand_lpj
 // top-C of H uniforms = a uniform C-subset in random order) by a virtual Fisher-Yates shuffle over
 // [0,H); child p*C+c = parent p with bit pos[c] flipped.  `map` holds 2*C ints per parent.
 __device__ inline void mutate_randflip(const uint64_t *parents, int P, int C, int W64, int H, const Stream &st,
-                                       int32_t *map, uint64_t *children, int lane) {
-  for (int t = lane; t < P * C * W64; t += 32) children[t] = parents[(t / W64 / C) * W64 + t % W64];
+                                       int32_t *map, uint64_t *children, int lane, int rs) {
+  for (int t = lane; t < P * C * W64; t += 32) {
+    const int r = t / W64, w = t - r * W64;
+    children[r * rs + w] = parents[(r / C) * rs + w];
+  }
   __syncwarp();
   for (int p = lane; p < P; p += 32) {
     int32_t *mk = map + 2 * p * C, *mv = mk + C;
@@ -266,7 +282,7 @@ __device__ inline void mutate_randflip(const uint64_t *parents, int P, int C, in
         mk[kslot] = k;
       }
       mv[kslot] = vi;
-      children[(p * C + i) * W64 + (vk >> 6)] ^= 1ull << (vk & 63);
+      children[(p * C + i) * rs + (vk >> 6)] ^= 1ull << (vk & 63);
     }
   }
   __syncwarp();
@@ -411,15 +427,15 @@ __device__ __forceinline__ int nth_remaining(const uint64_t *src, const uint64_t
 // `fmask` (nchild x W64 words) collects the flips; dst = src ^ fmask, so src == dst (C == 1) is fine.
 __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int W64, int H, double sparsity,
                                          double p_bf, const Stream &st0, const Stream &st1, uint64_t *fmask,
-                                         uint64_t *dst, int lane, const FlipEntry *__restrict__ tab = nullptr) {
+                                         uint64_t *dst, int lane, int rs, const FlipEntry *__restrict__ tab = nullptr) {
   const double Hf = (double)H;
   const double crowd = __dmul_rn(sparsity, Hf);
   const int nchild = P * C;
   for (int j0 = 0; j0 < nchild; j0 += 32) {
     const int j = j0 + lane;
     if (j < nchild) {
-      const uint64_t *par = src + (size_t)(j / C) * W64;
-      uint64_t *fm = fmask + (size_t)j * W64;
+      const uint64_t *par = src + (size_t)(j / C) * rs;
+      uint64_t *fm = fmask + (size_t)j * rs;
       int a = 0;
       for (int w = 0; w < W64; ++w) {
         a += __popcll(par[w]);
@@ -491,7 +507,7 @@ __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int 
           }
         }
       }
-      for (int w = 0; w < W64; ++w) dst[(size_t)j * W64 + w] = par[w] ^ fm[w];
+      for (int w = 0; w < W64; ++w) dst[(size_t)j * rs + w] = par[w] ^ fm[w];
     }
     __syncwarp();
   }
@@ -500,7 +516,7 @@ __device__ inline void mutate_sparseflip(const uint64_t *src, int P, int C, int 
 // batch_cross (evo.py:335-380): pairs in combinations(range(P),2) order, cut ~ U{1..H-1} from u32
 // stream element k; child 2k = p1[:cut] | p2[cut:], child 2k+1 = p2[:cut] | p1[cut:].
 __device__ inline void mutate_cross(const uint64_t *parents, int P, int W64, int H, const Stream &st,
-                                    uint64_t *children, int lane) {
+                                    uint64_t *children, int lane, int rs) {
   const int npairs = P * (P - 1) / 2;
   for (int t = lane; t < npairs * W64; t += 32) {
     const int k = t / W64, w = t % W64;
@@ -513,9 +529,9 @@ __device__ inline void mutate_cross(const uint64_t *parents, int P, int W64, int
     const int cut = 1 + (int)randint_u32(st.u32(0, (uint32_t)k), (uint32_t)(H - 1));
     const int lo = cut - 64 * w;
     const uint64_t L = lo <= 0 ? 0ull : (lo >= 64 ? ~0ull : ((1ull << lo) - 1));
-    const uint64_t pa = parents[a * W64 + w], pb = parents[b * W64 + w];
-    children[(2 * k) * W64 + w] = (pa & L) | (pb & ~L);
-    children[(2 * k + 1) * W64 + w] = (pb & L) | (pa & ~L);
+    const uint64_t pa = parents[a * rs + w], pb = parents[b * rs + w];
+    children[(2 * k) * rs + w] = (pa & L) | (pb & ~L);
+    children[(2 * k + 1) * rs + w] = (pb & L) | (pa & ~L);
   }
   __syncwarp();
 }
@@ -546,42 +562,45 @@ __host__ inline int children_per_gen(int mut, int P, int C) { return mut >= TVO_
 template <typename T>
 __device__ inline void evo_generation(const WarpBuf<T> &wb, const uint64_t *cand, const T *cand_lpj, int S_c,
                                       uint64_t *children, const EvoParams &ep, int gen, uint32_t n_glob, int W64,
-                                      int H, double sparsity, double m_glob, double T_glob, int lane) {
+                                      int H, double sparsity, double m_glob, double T_glob, int lane, int cs = 0) {
+  if (cs == 0) cs = W64;  // row stride of `cand`; the children are written wb.rs words apart
+  const int rs = wb.rs;
   Stream st;
   st.key = ep.key;
   st.n = n_glob;
   st.tag = make_tag(ep.step, gen, PUR_SELECT);
   if (ep.sel == TVO_SEL_RANDPARENTS)
-    select_randparents(cand, S_c, ep.P, W64, st, wb.iscr, wb.parents, lane);
+    select_randparents(cand, S_c, ep.P, W64, st, wb.iscr, wb.parents, lane, cs, rs);
   else
     select_fitparents<T>(cand, cand_lpj, S_c, ep.P, W64, st, ep.sel == TVO_SEL_FITPARENTS_FIXED, m_glob, T_glob,
-                         wb.dscr, wb.iscr, wb.parents, lane);
+                         wb.dscr, wb.iscr, wb.parents, lane, cs, rs);
   Stream s0 = st, s1 = st;
   s0.tag = make_tag(ep.step, gen, PUR_FLIP0);
   s1.tag = make_tag(ep.step, gen, PUR_FLIP1);
   switch (ep.mut) {
     case TVO_MUT_RANDFLIP:
       st.tag = make_tag(ep.step, gen, PUR_RANDFLIP);
-      mutate_randflip(wb.parents, ep.P, ep.C, W64, H, st, wb.iscr, children, lane);
+      mutate_randflip(wb.parents, ep.P, ep.C, W64, H, st, wb.iscr, children, lane, rs);
       break;
     case TVO_MUT_SPARSEFLIP:
       mutate_sparseflip(wb.parents, ep.P, ep.C, W64, H, sparsity, ep.p_bf, s0, s1, /*fmask=*/children, children, lane,
-                        ep.flip_tab);  // the masks are built in the children's own slots
+                        rs, ep.flip_tab);  // the masks are built in the children's own slots
       break;
     default: {
       st.tag = make_tag(ep.step, gen, PUR_CROSS);
-      mutate_cross(wb.parents, ep.P, W64, H, st, children, lane);
+      mutate_cross(wb.parents, ep.P, W64, H, st, children, lane, rs);
       const int nc = ep.P * (ep.P - 1);
       if (ep.mut == TVO_MUT_CROSS_RANDFLIP) {
         // randflip with C = 1 on every crossed child (evo.py:383-387): flip bit randint(H)
         st.tag = make_tag(ep.step, gen, PUR_RANDFLIP);
         for (int j = lane; j < nc; j += 32) {
           const int k = (int)randint_u32(st.u32((uint32_t)j, 0), (uint32_t)H);
-          children[j * W64 + (k >> 6)] ^= 1ull << (k & 63);
+          children[j * rs + (k >> 6)] ^= 1ull << (k & 63);
         }
         __syncwarp();
       } else if (ep.mut == TVO_MUT_CROSS_SPARSEFLIP) {
-        mutate_sparseflip(children, nc, 1, W64, H, sparsity, ep.p_bf, s0, s1, wb.fmask, children, lane, ep.flip_tab);
+        mutate_sparseflip(children, nc, 1, W64, H, sparsity, ep.p_bf, s0, s1, wb.fmask, children, lane, rs,
+                          ep.flip_tab);
       }
     }
   }
@@ -666,14 +685,14 @@ __device__ __forceinline__ void mark_redundant_cpl(const WarpBuf<T> &wb, int S, 
     for (int t = 0; t < CPL; ++t) {
       const int c = c0 + 32 * t + lane;
       if (c < Snew && hit[t] >= 0) {
-        const uint64_t *sc = wb.newK + (size_t)c * W64;
+        const uint64_t *sc = wb.newK + (size_t)c * wb.rs;
         const int jj = hit[t];
-        bool dup = same_state(jj < S ? wb.oldK + (size_t)jj * W64 : wb.newK + (size_t)(jj - S) * W64, sc, W64);
+        bool dup = same_state(jj < S ? wb.oldK + (size_t)jj * W64 : wb.newK + (size_t)(jj - S) * wb.rs, sc, W64);
         if (!dup) {  // hash collision: exhaustive rescan (practically never)
           for (int j2 = 0; j2 < S && !dup; ++j2)
             if (ho[j2] == hc[t]) dup = same_state(wb.oldK + (size_t)j2 * W64, sc, W64);
           for (int j2 = c + 1; j2 < Snew && !dup; ++j2)
-            if (hn[j2] == hc[t]) dup = same_state(wb.newK + (size_t)j2 * W64, sc, W64);
+            if (hn[j2] == hc[t]) dup = same_state(wb.newK + (size_t)j2 * wb.rs, sc, W64);
         }
         if (dup) wb.lpj[S + c] = LowLpj<T>::v();
       }
@@ -687,7 +706,7 @@ __device__ inline void mark_redundant(const WarpBuf<T> &wb, int S, int Snew, int
   const int Sp = hash_old_pad(S), Snp = (Snew + 3) & ~3;
   for (int i = lane; i < Sp; i += 32) wb.hash[i] = i < S ? (hash_words(wb.oldK + (size_t)i * W64, W64) | 1u) : 0u;
   for (int i = lane; i < Snp; i += 32)
-    wb.hash[Sp + i] = i < Snew ? (hash_words(wb.newK + (size_t)i * W64, W64) | 1u) : 0u;
+    wb.hash[Sp + i] = i < Snew ? (hash_words(wb.newK + (size_t)i * wb.rs, W64) | 1u) : 0u;
   __syncwarp();
   if (Snew <= 32)
     mark_redundant_cpl<T, 1>(wb, S, Snew, W64, lane);
@@ -863,7 +882,7 @@ __device__ __forceinline__ bool select_merge(const WarpBuf<T> &wb, int S, int Sn
 
 // `stage` (S*W64 words, private to the warp) is required when wb.oldK aliases K_row (old states not staged in
 // shared memory): the selected rows are assembled there first, then copied over the K row.
-template <typename T>
+template <typename T, bool BATCHED = false>
 __device__ inline int select_topS(const WarpBuf<T> &wb, int S, int Snew, int W64, uint64_t *K_row, T *lpj_row,
                                   int lane, uint64_t *stage = nullptr) {
   const int M = S + Snew;
@@ -894,15 +913,38 @@ __device__ inline int select_topS(const WarpBuf<T> &wb, int S, int Snew, int W64
     }
   }
   __syncwarp();
+  // Gather the selected rows.  Loads are issued in batches of kCopyBatch before the stores: source (old states
+  // in global memory for large H*S) and destination may alias as far as the compiler knows, and a load -> store
+  // chain per word leaves one L2 round trip in flight per warp (BATCHED: the large-H*S variant of the fused kernel).
+  constexpr int kCopyBatch = BATCHED ? 4 : 1;
   uint64_t *dst = stage ? stage : K_row;
-  for (int t = lane; t < S * W64; t += 32) {
-    const int src = wb.iscr[t / W64];
-    const uint64_t *row = src < S ? wb.oldK + (size_t)src * W64 : wb.newK + (size_t)(src - S) * W64;
-    dst[t] = row[t % W64];
+  const int nw = S * W64;
+  for (int t0 = lane; t0 < nw; t0 += 32 * kCopyBatch) {
+    uint64_t v[kCopyBatch];
+#pragma unroll
+    for (int u = 0; u < kCopyBatch; ++u) {
+      const int t = t0 + 32 * u;
+      if (t < nw) {
+        const int r = t / W64, src = wb.iscr[r];
+        const uint64_t *row = src < S ? wb.oldK + (size_t)src * W64 : wb.newK + (size_t)(src - S) * wb.rs;
+        v[u] = row[t - r * W64];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kCopyBatch; ++u)
+      if (t0 + 32 * u < nw) dst[t0 + 32 * u] = v[u];
   }
   __syncwarp();
   if (stage) {
-    for (int t = lane; t < S * W64; t += 32) K_row[t] = stage[t];
+    for (int t0 = lane; t0 < nw; t0 += 32 * kCopyBatch) {
+      uint64_t v[kCopyBatch];
+#pragma unroll
+      for (int u = 0; u < kCopyBatch; ++u)
+        if (t0 + 32 * u < nw) v[u] = stage[t0 + 32 * u];
+#pragma unroll
+      for (int u = 0; u < kCopyBatch; ++u)
+        if (t0 + 32 * u < nw) K_row[t0 + 32 * u] = v[u];
+    }
     __syncwarp();
   }
   return warp_sum(nsub);

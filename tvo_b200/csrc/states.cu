@@ -89,6 +89,7 @@ int evo_params_from_cfg(const tvo_evo_config *cfg, int S, int H, EvoParams &ep, 
   dims.need_fit = ep.sel != TVO_SEL_RANDPARENTS;
   dims.need_fmask = ep.mut == TVO_MUT_CROSS_SPARSEFLIP;
   dims.old_in_global = 0;
+  dims.RS = 0;
   return TVO_OK;
 }
 
