@@ -11,7 +11,6 @@
 // per chunk so that  WpT += E^T Y  is one DGEMM (the union of active bits per datapoint is ~100 of 256,
 // so the outer product is effectively dense).
 #include <cublas_v2.h>
-#include <cstdlib>
 
 #include "bsc_device.cuh"
 
@@ -109,6 +108,33 @@ __device__ __forceinline__ int position_list(const uint64_t *st, int W64, uint16
     while (true) {
       while (m == 0 && ++w < W64) m = st[w];
       if (w >= W64) break;
+      const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+      const int pos = (w << 6) + (lo ? __ffs((int)lo) - 1 : 32 + __ffs((int)hi) - 1);
+      m &= m - 1;
+      if (n < cap) plist[n * 32] = (uint16_t)pos;
+      ++n;
+    }
+    return n;
+  }
+  if (W64 <= 32) {
+    // pass 1: which words are non-empty (four loads in flight); pass 2: ONE loop over the set bits of the state that
+    // re-reads a word (now an L1 / shared-memory hit) only when the current one is exhausted — empty words cost
+    // nothing and the warp iterates max-over-lanes |s| times
+    uint32_t nz = 0;
+    for (int w0 = 0; w0 < W64; w0 += 4) {
+      const uint64_t d0 = st[w0], d1 = w0 + 1 < W64 ? st[w0 + 1] : 0ull, d2 = w0 + 2 < W64 ? st[w0 + 2] : 0ull,
+                     d3 = w0 + 3 < W64 ? st[w0 + 3] : 0ull;
+      nz |= ((d0 ? 1u : 0u) | (d1 ? 2u : 0u) | (d2 ? 4u : 0u) | (d3 ? 8u : 0u)) << w0;
+    }
+    int w = 0;
+    uint64_t m = 0;
+    while (true) {
+      if (m == 0) {
+        if (nz == 0) break;
+        w = __ffs((int)nz) - 1;
+        nz &= nz - 1;
+        m = st[w];
+      }
       const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
       const int pos = (w << 6) + (lo ? __ffs((int)lo) - 1 : 32 + __ffs((int)hi) - 1);
       m &= m - 1;
@@ -485,14 +511,14 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   // (large H*S) leave the old states in global memory instead of staging them: more resident warps.
   if (wbytes * 8 * 4 > (size_t)kMaxSmemFast) {
     dims.old_in_global = 1;
-    if (!getenv("TVO_EXP_NOPAD")) dims.RS = dims.W64 | 1;  // conflict-free per-lane row access (see EstepDims::RS)
+    dims.RS = dims.W64 | 1;  // conflict-free per-lane row access (see EstepDims::RS); at the headline shape the
+                             // extra 1.1 kB per warp would cost the fourth CTA per SM (measured: 6 % slower)
     wbytes = warp_buf_bytes<T>(dims);
   }
   auto kern = dims.old_in_global ? estep_evo_bsc_gram_kernel<T, 1> : estep_evo_bsc_gram_kernel<T, 4>;
   // the one-CTA-per-SM variant takes as many warps as its shared memory holds (up to 12: it is latency-bound and
   // every resident warp counts; 10 at H=1024 S=128)
   int wpb = dims.old_in_global ? (int)min((size_t)kMaxWarpsLarge, (size_t)kMaxSmemFast / wbytes) : 8;
-  if (wpb > 8 && getenv("TVO_EXP_WPB")) wpb = atoi(getenv("TVO_EXP_WPB"));
   if (wpb < 1) wpb = 1;
   while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmemFast) wpb >>= 1;
   TVO_REQUIRE(wbytes * wpb <= (size_t)kMaxSmemFast, "estep_evo_bsc: per-datapoint working set %zu B exceeds shared memory",

@@ -919,13 +919,14 @@ __device__ inline int select_topS(const WarpBuf<T> &wb, int S, int Snew, int W64
   constexpr int kCopyBatch = BATCHED ? 4 : 1;
   uint64_t *dst = stage ? stage : K_row;
   const int nw = S * W64;
+  const int wsh = (W64 & (W64 - 1)) == 0 ? __ffs(W64) - 1 : -1;  // t / W64 as a shift when W64 is a power of two
   for (int t0 = lane; t0 < nw; t0 += 32 * kCopyBatch) {
     uint64_t v[kCopyBatch];
 #pragma unroll
     for (int u = 0; u < kCopyBatch; ++u) {
       const int t = t0 + 32 * u;
       if (t < nw) {
-        const int r = t / W64, src = wb.iscr[r];
+        const int r = wsh >= 0 ? (t >> wsh) : t / W64, src = wb.iscr[r];
         const uint64_t *row = src < S ? wb.oldK + (size_t)src * W64 : wb.newK + (size_t)(src - S) * wb.rs;
         v[u] = row[t - r * W64];
       }
