@@ -174,22 +174,61 @@ __device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, co
   const int n = position_list<LAT>(st, W64, plist, cap);
   if (n > cap) return bsc_gram_lpj_walk<T>(st, W64, H, a, G, prior, yy, coef);
   double f = 0.0, pr = 0.0;
+  if (LAT) {
+    // latency-oriented order: all diagonal / a / prior terms first (four rows of loads in flight), then the
+    // |s|(|s|-1)/2 off-diagonal gathers as ONE flattened pair list in batches of eight — about 1 + |s|^2/16 L2
+    // round trips per state instead of one or two per active unit.  (A state is always scored by this same
+    // function inside one kernel, so the different rounding order against the other variant is never observable.)
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+      const int h0 = plist[i * 32], h1 = plist[(i + 1) * 32], h2 = plist[(i + 2) * 32], h3 = plist[(i + 3) * 32];
+      const double g0 = __ldg(G + (size_t)h0 * H + h0), g1 = __ldg(G + (size_t)h1 * H + h1),
+                   g2 = __ldg(G + (size_t)h2 * H + h2), g3 = __ldg(G + (size_t)h3 * H + h3);
+      const double a0 = (double)__ldg(a + h0), a1 = (double)__ldg(a + h1), a2 = (double)__ldg(a + h2),
+                   a3 = (double)__ldg(a + h3);
+      const double p0 = (double)__ldg(prior + h0), p1 = (double)__ldg(prior + h1), p2 = (double)__ldg(prior + h2),
+                   p3 = (double)__ldg(prior + h3);
+      f += g0 - 2.0 * a0;
+      f += g1 - 2.0 * a1;
+      f += g2 - 2.0 * a2;
+      f += g3 - 2.0 * a3;
+      pr += p0;
+      pr += p1;
+      pr += p2;
+      pr += p3;
+    }
+    for (; i < n; ++i) {
+      const int h0 = plist[i * 32];
+      f += __ldg(G + (size_t)h0 * H + h0) - 2.0 * (double)__ldg(a + h0);
+      pr += (double)__ldg(prior + h0);
+    }
+    double g = 0.0;
+    int pi = 0, pj = 1;  // next pair (pi < pj), row-major over the strict upper triangle
+    while (pi < n - 1) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v[u] = 0.0;
+        if (pi < n - 1) {
+          v[u] = __ldg(G + (size_t)plist[pi * 32] * H + plist[pj * 32]);
+          if (++pj == n) {
+            ++pi;
+            pj = pi + 1;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) g += v[u];
+    }
+    return (T)((yy + (f + 2.0 * g)) * coef + pr);
+  }
   for (int i = 0; i < n; ++i) {
     const int h1 = plist[i * 32];
     const double *Grow = G + (size_t)h1 * H;
     f += __ldg(Grow + h1) - 2.0 * (double)__ldg(a + h1);
     pr += (double)__ldg(prior + h1);
     double g2 = 0.0;
-    int j = i + 1;
-    for (; LAT && j + 4 <= n; j += 4) {  // four gathers in flight, summed in list order (same result as the plain loop)
-      const double v0 = __ldg(Grow + plist[j * 32]), v1 = __ldg(Grow + plist[(j + 1) * 32]),
-                   v2 = __ldg(Grow + plist[(j + 2) * 32]), v3 = __ldg(Grow + plist[(j + 3) * 32]);
-      g2 += v0;
-      g2 += v1;
-      g2 += v2;
-      g2 += v3;
-    }
-    for (; j < n; ++j) g2 += __ldg(Grow + plist[j * 32]);
+    for (int j = i + 1; j < n; ++j) g2 += __ldg(Grow + plist[j * 32]);
     f += 2.0 * g2;
   }
   return (T)((yy + f) * coef + pr);
