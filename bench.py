@@ -32,6 +32,20 @@ PI_GEN = 5.0 / H
 WORKLOAD = "BSC H256 D144 S64 EVO(randparents,sparseflip,P16,C2,G2) fp64 — BASELINE configs[1] at the north-star N"
 ALG_BYTES_PER_DP = D * 8 + 2 * S * ((H + 63) // 64) * 8 + S * 8          # 5760 B (fp64, packed)
 ALG_FLOP_PER_DP = (S + P * C * G) * (2 * H * D + 3 * D + 2 * H)          # 9.56 MFLOP (dense count)
+HEADLINE = True
+
+
+def set_workload(name):
+    """`--workload c5` re-points the module constants at BASELINE configs[4] (BSC H1024 D256 S128, the data-sharded
+    multi-GPU configuration); the default is the headline configs[1].  Called before anything forks."""
+    global H, D, S, P, C, G, PI_GEN, WORKLOAD, ALG_BYTES_PER_DP, ALG_FLOP_PER_DP, HEADLINE
+    if name == "c5":
+        H, D, S, P, C, G = 1024, 256, 128, 16, 4, 2
+        PI_GEN = 8.0 / H
+        WORKLOAD = "BSC H1024 D256 S128 EVO(randparents,sparseflip,P16,C4,G2) fp64 — BASELINE configs[4]"
+        HEADLINE = False
+    ALG_BYTES_PER_DP = D * 8 + 2 * S * ((H + 63) // 64) * 8 + S * 8
+    ALG_FLOP_PER_DP = (S + P * C * G) * (2 * H * D + 3 * D + 2 * H)
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -190,7 +204,7 @@ def run_reference(args):
     vals, ems = vals[args.warmup_ref:], ems[args.warmup_ref:]
     v = statistics.mean(vals)
     line = {
-        "impl": "reference", "metric": "E-step datapoints/s (BSC H256 D144 S64); EM-iteration time in em_iter_ms",
+        "impl": "reference", "metric": f"E-step datapoints/s (BSC H{H} D{D} S{S}); EM-iteration time in em_iter_ms",
         "value": v, "unit": "datapoints/s", "n_gpus": args.gpus, "steps": args.steps_ref, "warmup": args.warmup_ref,
         "ms_per_step": statistics.mean(ems) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": last["sample"]},
@@ -344,6 +358,8 @@ def run_gpu(args):
         achieved = ALG_BYTES_PER_DP * dp_per_launch / (launch_ms * 1e-3) / 1e9
         traffic, issue = None, None
         try:
+            if not HEADLINE:
+                raise KeyError("profiles/traffic.json holds the headline shape only")
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tj["estep_evo_bsc_bytes_per_dp"] * dp_per_launch
             # second reading of the same launch: warp instructions issued per second against the scheduler peak
@@ -357,12 +373,13 @@ def run_gpu(args):
         except Exception:
             pass
         line = {
-            "metric": "E-step datapoints/s (BSC H256 D144 S64); EM-iteration time in em_iter_ms",
+            "metric": f"E-step datapoints/s (BSC H{H} D{D} S{S}); EM-iteration time in em_iter_ms",
             "value": N_total / (estep_ms * 1e-3), "unit": "datapoints/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "N_per_gpu": N, "N_total": N_total, "batch": "whole shard per launch",
-                       "l2": "inputs (Y 1.15 GB + K 2.1 GB per 1M datapoints) exceed the 126 MB L2",
+                       "l2": f"inputs (Y {N * D * 8 / 1e9:.2f} GB + K {N * S * ((H + 63) // 64) * 8 / 1e9:.2f} GB per GPU) "
+                             "exceed the 126 MB L2",
                        "parallelism": f"data-parallel x{world}, one packed NCCL all-reduce per EM iteration"},
             "estep_ms": estep_ms, "em_iter_ms": total_ms, "em_iter_datapoints_per_s": N_total / (total_ms * 1e-3),
             "free_energy_per_datapoint": F_per_dp, "subs_last_step_per_datapoint": subs / N / max(args.steps, 1),
@@ -382,9 +399,10 @@ def run_gpu(args):
                          "share_of_estep": k_ms / args.steps / estep_ms,
                          "dense_equivalent_tflops": ALG_FLOP_PER_DP * N / (estep_ms * 1e-3) / 1e12,
                          "mstep_kernel_ms_per_step": m_ms / args.steps, "issue_roofline": issue,
-                         "note": "the kernel's DRAM traffic equals its algorithmic bytes (+ the a = W^T y row), but it is "
-                                 "bound by integer-ALU issue (selection, mutation, dedup, sort: ~7.7k warp instructions "
-                                 "per datapoint, see issue_roofline), not by HBM; see DESIGN.md section 5"},
+                         "note": ("the kernel's DRAM traffic equals its algorithmic bytes (+ the a = W^T y row), but it is "
+                                  "bound by integer-ALU issue (selection, mutation, dedup, sort: ~7.7k warp instructions "
+                                  "per datapoint, see issue_roofline), not by HBM; see DESIGN.md section 5") if HEADLINE
+                         else "large-H*S variant of the kernel (one CTA per SM, latency-bound): profiles/r01j_c5.md"},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(n_per_core=args.cpu_n_per_core).items()
@@ -405,7 +423,10 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=131072)
     ap.add_argument("--cpu-n-per-core", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 = BASELINE configs[1] (the headline, default); c5 = configs[4] (H1024 D256 S128)")
     args = ap.parse_args()
+    set_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.steps_ref = max(1, min(args.steps, 3))
     args.warmup_ref = 1

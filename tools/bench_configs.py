@@ -119,4 +119,5 @@ for it in range(iters + 2):
 e, m, p = statistics.median(te), statistics.median(tm), statistics.median(tp)
 print(json.dumps({"config": name, "N": N, "estep_ms": e, "mstep_ms": m, "epoch_update_ms": p,
                   "estep_datapoints_per_s": N / e * 1e3, "em_iter_datapoints_per_s": N / (e + m + p) * 1e3,
+                  "epoch_update_ms_all": [round(x, 2) for x in tp], "estep_ms_all": [round(x, 2) for x in te],
                   "F_per_datapoint_trajectory": [round(f, 4) for f in Fs], "subs_per_datapoint_last": states._take_nsubs() / N / (iters + 2)}))

@@ -59,6 +59,27 @@ static int gemm_A(cublasHandle_t h, const float *Wt, int Dpad, const float *Y, i
   return TVO_OK;
 }
 
+// Per-device staging rows of the large-H*S E-step variant (one S x W64 row per resident warp, ~20 MB): part of the
+// per-device context, grown on demand and kept.  (A cudaMallocAsync / cudaFreeAsync pair per call hands the memory
+// back to the driver at every synchronisation with the default release threshold — measured as sporadic host-side
+// stalls of tens of ms per E-step.)  Calls on one device are serialised by the boundary's threading contract.
+static void *g_stage[64];
+static size_t g_stage_bytes[64];
+static int stage_buffer(size_t bytes, uint64_t **out) {
+  int dev = 0;
+  TVO_CUDA(cudaGetDevice(&dev));
+  TVO_REQUIRE(dev >= 0 && dev < 64, "stage buffer: device index %d out of range", dev);
+  if (g_stage_bytes[dev] < bytes) {
+    if (g_stage[dev]) TVO_CUDA(cudaFree(g_stage[dev]));  // synchronises: no kernel still uses the old rows
+    g_stage[dev] = nullptr;
+    g_stage_bytes[dev] = 0;
+    TVO_CUDA(cudaMalloc(&g_stage[dev], bytes));
+    g_stage_bytes[dev] = bytes;
+  }
+  *out = (uint64_t *)g_stage[dev];
+  return TVO_OK;
+}
+
 // ------------------------------------------------------------------------------------ Gram lpj
 // lpj of ONE state, evaluated by ONE lane.  a: shared memory (H), G: global (H x H), prior: global.
 // Bit-walk form: used when the state has more active units than the lane's position list holds.
@@ -568,8 +589,10 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
   occ = max(occ, 1);
   uint64_t *stage_rows = nullptr;
-  if (dims.old_in_global)
-    TVO_CUDA(cudaMallocAsync((void **)&stage_rows, (size_t)sm_count() * occ * wpb * S * dims.W64 * 8, st));
+  if (dims.old_in_global) {
+    rc = stage_buffer((size_t)sm_count() * occ * wpb * S * dims.W64 * 8, &stage_rows);
+    if (rc) return rc;
+  }
   T *A = (T *)scratch_a;
   if (use_tab) {
     FlipEntry *tab = (FlipEntry *)scratch;
@@ -589,7 +612,6 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
     kernel_timing_end(tok, st);
     TVO_AFTER_LAUNCH("estep_evo_bsc_gram");
   }
-  if (stage_rows) TVO_CUDA(cudaFreeAsync(stage_rows, st));
   return TVO_OK;
 }
 
