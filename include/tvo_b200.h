@@ -344,6 +344,33 @@ int tvo_sssc_mstep_f32(const float *Y, int64_t ldY, const int64_t *idx, const ui
                        int64_t scratch_bytes, int32_t *overflow, int64_t B, int32_t S, int32_t H, int32_t D,
                        int32_t with_ssz, void *stream);
 
+/* ---- TVAE (tvo/models/tvae.py): the decoder pieces that touch the packed states.  The reference casts the uint8
+ *      states to float and runs `states @ W_0 + b_0` (tvae.py:434-459, 672-701) and
+ *      `states @ log(pi/(1-pi))` (tvae.py:337, 600) as dense products.
+ *      tvo_tvae_layer0:       out (n_states x H1) = b0 + sum_{h in state} W0[h, :]   (W0: H0 x H1 row-major, b0 may
+ *                             be NULL); states: n_states x ceil(H0/64) words, contiguous.
+ *      tvo_tvae_layer0_grad:  gW0 (H0 x H1, INCREMENTED) += sum over states with unit h active of g (n_states x H1):
+ *                             the weight gradient of the first layer (what autograd's `states.T @ g` would compute).
+ *      tvo_tvae_lpj:          lpj[b, s] = sum_{h in state} prior[h] - s1 with prior = log(pi/(1-pi)),
+ *                             kind 0 (GaussianTVAE, tvae.py:335-338): s1 = nansum_d (y - out)^2 / (2 sigma2[0]);
+ *                             kind 1 (BernoulliTVAE, tvae.py:594-601): s1 = nansum_d BCE(out, y) (logs clamped at
+ *                             -100 as torch does).  Y: B x D (row stride ldY); out: (B*S) x D contiguous decoder
+ *                             output; states row b starts at states + b * st_stride_b; lpj likewise. ---- */
+int tvo_tvae_layer0_f64(const uint64_t *states, int64_t n_states, int32_t H0, const double *W0, const double *b0,
+                        int32_t H1, double *out, void *stream);
+int tvo_tvae_layer0_f32(const uint64_t *states, int64_t n_states, int32_t H0, const float *W0, const float *b0,
+                        int32_t H1, float *out, void *stream);
+int tvo_tvae_layer0_grad_f64(const uint64_t *states, int64_t n_states, int32_t H0, const double *g, int32_t H1,
+                             double *gW0, void *stream);
+int tvo_tvae_layer0_grad_f32(const uint64_t *states, int64_t n_states, int32_t H0, const float *g, int32_t H1,
+                             float *gW0, void *stream);
+int tvo_tvae_lpj_f64(int32_t kind, const double *Y, int64_t ldY, const double *out, const uint64_t *states,
+                     int64_t st_stride_b, const double *prior, const double *sigma2, double *lpj, int64_t lpj_stride_b,
+                     int64_t B, int32_t S, int32_t H0, int32_t D, void *stream);
+int tvo_tvae_lpj_f32(int32_t kind, const float *Y, int64_t ldY, const float *out, const uint64_t *states,
+                     int64_t st_stride_b, const float *prior, const float *sigma2, float *lpj, int64_t lpj_stride_b,
+                     int64_t B, int32_t S, int32_t H0, int32_t D, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

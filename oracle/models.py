@@ -4,6 +4,7 @@ numpy restatement of
   tvo/models/bsc.py:100-204        BSC
   tvo/models/noisyor.py:67-162     NoisyOR
   tvo/models/sssc.py:175-540       SSSC
+  tvo/models/tvae.py:85-701        GaussianTVAE / BernoulliTVAE (decoder, lpj, Adam + CyclicLR step)
   tvo/utils/model_protocols.py:179-193   Optimized.free_energy
   tvo/utils/sanity.py:14-86        fix_theta (clamps / non-finite replacement)
 
@@ -364,3 +365,164 @@ class PMM(_Mixture):
         th["W"] = _fix(W_new, th["W"], eps, None)
         th["pies"] = _fix(self.my_pies / N, th["pies"], eps, 1.0 - eps)
         self._zero()
+
+
+# ------------------------------------------------------------------------------------ TVAE
+def tvae_layer0(K, W0, b0):
+    """states @ W_0 + b_0 for uint8 states (..., H0) (tvae.py:457-461), as the sum of the active rows."""
+    K = np.asarray(K)
+    return K.reshape(-1, K.shape[-1]).astype(W0.dtype) @ W0 + b0
+
+
+def tvae_layer0_grad(K, g):
+    """d/dW_0 of a loss with gradient g (rows, H1) w.r.t. the first pre-activation: states^T @ g."""
+    K = np.asarray(K)
+    return K.reshape(-1, K.shape[-1]).astype(g.dtype).T @ g
+
+
+class _TVAE:
+    """numpy restatement of tvo/models/tvae.py (ReLU decoder given by W_init / b_init, analytical pi and
+    sigma2 updates, Adam + triangular CyclicLR as in tvae.py:297-309 and tvo/utils/CyclicLR.py:194-214).
+    theta keys as in the reference: W_i, b_i, pies[, sigma2]."""
+
+    kind = "gauss"
+
+    def __init__(self, W_init, b_init, pi_init, sigma2_init=None, precision=np.float64, min_lr=0.001, max_lr=0.01,
+                 cycliclr_step_size_up=400):
+        self.precision = precision
+        self.W = [np.array(w, dtype=precision) for w in W_init]
+        self.b = [np.array(x, dtype=precision) for x in b_init]
+        self.theta = {f"W_{i}": w for i, w in enumerate(self.W)}
+        self.theta.update({f"b_{i}": x for i, x in enumerate(self.b)})
+        self.theta["pies"] = np.array(pi_init, dtype=precision)
+        if self.kind == "gauss":
+            # the reference builds to.tensor([sigma2_init]) in the default dtype (float32) before casting
+            # (tvae.py:80-82): a Python float initial value passes through float32
+            self.theta["sigma2"] = np.array([np.float32(0.01 if sigma2_init is None else sigma2_init)], dtype=precision)
+            self.new_sigma2 = np.zeros(1, dtype=precision)
+        self.new_pi = np.zeros(self.W[0].shape[0], dtype=precision)
+        self.n_train = 0
+        self.min_lr, self.max_lr, self.step_up = min_lr, max_lr, cycliclr_step_size_up
+        self.lr, self.it = min_lr, 0
+        self.m = [np.zeros_like(p) for p in self.W + self.b]
+        self.v = [np.zeros_like(p) for p in self.W + self.b]
+        self.t = 0
+
+    # decoder ------------------------------------------------------------------------------------
+    def _forward_all(self, K):
+        """(pre-activations z_l, activations a_l) with a_0 = states (rows, H0)."""
+        a = [np.asarray(K).reshape(-1, np.asarray(K).shape[-1]).astype(self.precision)]
+        z = []
+        for l, (W, b) in enumerate(zip(self.W, self.b)):
+            z.append(a[-1] @ W + b)
+            a.append(np.maximum(z[-1], 0) if l < len(self.W) - 1 else self._finish(z[-1]))
+        return z, a
+
+    def _finish(self, z):
+        return z
+
+    def forward(self, K):  # tvae.py:434-467 / 672-701
+        K = np.asarray(K)
+        return self._forward_all(K)[1][-1].reshape(K.shape[:-1] + (self.W[-1].shape[1],))
+
+    def _s1(self, data, out):
+        raise NotImplementedError
+
+    def log_pseudo_joint(self, data, K):  # tvae.py:326-341 / 584-604
+        pi = self.theta["pies"]
+        out = self.forward(K)
+        s2 = np.asarray(K).astype(self.precision) @ np.log(pi / (1.0 - pi))
+        return s2 - self._s1(np.asarray(data, dtype=self.precision), out)
+
+    def free_energy(self, data, K, lpj=None):  # tvae.py:108-116
+        return float(logsumexp(self.log_joint(data, K, lpj), axis=1).sum())
+
+    # training -----------------------------------------------------------------------------------
+    def _dlpj_dz(self, data, out):
+        """d lpj_ns / d z_nsd of the output pre-activation (NaN observations carry no gradient)."""
+        raise NotImplementedError
+
+    def update_param_batch(self, data, K):  # tvae.py:118-166, 412-432
+        data = np.asarray(data, dtype=self.precision)
+        K = np.asarray(K)
+        N, S, _ = K.shape
+        z, a = self._forward_all(K)
+        out = a[-1].reshape(N, S, -1)
+        lj = self.log_joint(data, K, self.log_pseudo_joint(data, K))
+        F = float(logsumexp(lj, axis=1).sum())
+        q = lpj2pjc(lj)  # dF/d lpj_ns
+        delta = (-(q / N)[:, :, None] * self._dlpj_dz(data, out)).reshape(N * S, -1)
+        gW, gb = [None] * len(self.W), [None] * len(self.W)
+        for l in reversed(range(len(self.W))):
+            gW[l] = a[l].T @ delta
+            gb[l] = delta.sum(axis=0)
+            if l > 0:
+                delta = (delta @ self.W[l].T) * (z[l - 1] > 0)
+        # Adam (torch defaults) with the lr of the current cycle position, then the scheduler step
+        self.t += 1
+        b1, b2, eps = 0.9, 0.999, 1e-8
+        for i, (p, g) in enumerate(zip(self.W + self.b, gW + gb)):
+            self.m[i] = b1 * self.m[i] + (1 - b1) * g
+            self.v[i] = b2 * self.v[i] + (1 - b2) * g * g
+            step = self.lr / (1 - b1 ** self.t)
+            p -= step * self.m[i] / (np.sqrt(self.v[i]) / math.sqrt(1 - b2 ** self.t) + eps)
+        self.it += 1
+        cycle = math.floor(1 + self.it / (2 * self.step_up))
+        x = 1.0 + self.it / (2 * self.step_up) - cycle
+        scale = x / 0.5 if x <= 0.5 else (x - 1) / (0.5 - 1)
+        self.lr = self.min_lr + (self.max_lr - self.min_lr) * scale
+        # analytical accumulators use the decoder output from BEFORE the step and the stored lpj (= lj here)
+        self.new_pi += mean_posterior(K.astype(self.precision), lj).sum(axis=0)
+        if self.kind == "gauss":
+            sq = ((data[:, None, :] - out) ** 2).sum(axis=2)
+            self.new_sigma2 += (q * sq).sum()
+        self.n_train += N
+        return F
+
+    def update_param_epoch(self):  # tvae.py:353-391 / 615-636
+        self.theta["pies"][:] = np.clip(self.new_pi / self.n_train, 1e-5, 1 - 1e-5)
+        self.new_pi[:] = 0
+        if self.kind == "gauss":
+            self.theta["sigma2"][:] = self.new_sigma2 / (self.n_train * self.W[-1].shape[1])
+            self.new_sigma2[:] = 0
+        self.n_train = 0
+
+
+class GaussianTVAE(_TVAE):
+    kind = "gauss"
+
+    def _s1(self, data, out):
+        return np.nansum((data[:, None, :] - out) ** 2, axis=2) / (2 * self.theta["sigma2"])
+
+    def log_joint(self, data, K, lpj=None):  # tvae.py:343-351
+        data = np.asarray(data, dtype=self.precision)
+        if lpj is None:
+            lpj = self.log_pseudo_joint(data, K)
+        Dn = (data.shape[1] - np.isnan(data).sum(axis=1))[:, None]
+        pi, s2 = self.theta["pies"], self.theta["sigma2"]
+        return lpj - Dn / 2 * np.log(2 * math.pi * s2) + np.log(1 - pi).sum()
+
+    def _dlpj_dz(self, data, out):
+        d = (data[:, None, :] - out) / self.theta["sigma2"]
+        return np.where(np.isnan(d), 0.0, d)
+
+
+class BernoulliTVAE(_TVAE):
+    kind = "bern"
+
+    def _finish(self, z):
+        return 1.0 / (1.0 + np.exp(-z))
+
+    def _s1(self, data, out):
+        with np.errstate(divide="ignore"):
+            bce = -(data[:, None, :] * np.maximum(np.log(out), -100) + (1 - data[:, None, :]) * np.maximum(np.log(1 - out), -100))
+        return np.nansum(bce, axis=2)
+
+    def log_joint(self, data, K, lpj=None):  # tvae.py:606-613
+        if lpj is None:
+            lpj = self.log_pseudo_joint(data, K)
+        return lpj + np.log(1 - self.theta["pies"]).sum()
+
+    def _dlpj_dz(self, data, out):
+        d = data[:, None, :] - out
+        return np.where(np.isnan(d), 0.0, d)

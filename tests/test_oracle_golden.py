@@ -435,3 +435,45 @@ def test_golden_mixtures(name, prec, tol):
     for k in m.theta:
         assert np.allclose(m.theta[k], g["theta1_" + k], rtol=tol * 10, atol=tol * 10), k
     assert math.isclose(m.free_energy(Y, K, m.log_pseudo_joint(Y, K)), float(g["F2"]), rel_tol=max(tol * 10, 1e-12))
+
+
+# ----------------------------------------------------------------------------- TVAE
+@pytest.mark.parametrize("tag,tol", [("tvae_gauss_f64", 1e-12), ("tvae_bern_f64", 1e-12), ("tvae_gauss_f32", 2e-5)])
+def test_tvae_oracle_matches_reference_fixtures(tag, tol):
+    """tvo/models/tvae.py run by tools/make_golden.py: decoder output, lpj (with a missing observation),
+    log_joint, F, and theta after three Adam + CyclicLR steps and the analytical epoch update."""
+    g = load_golden(tag + ".npz")
+    prec = np.float32 if tag.endswith("f32") else np.float64
+    kw = dict(W_init=[g["W_0"], g["W_1"]], b_init=[g["b_0"], g["b_1"]], pi_init=g["pies"], precision=prec,
+              min_lr=0.002, max_lr=0.02, cycliclr_step_size_up=2)
+    m = om.GaussianTVAE(sigma2_init=0.6, **kw) if "gauss" in tag else om.BernoulliTVAE(**kw)
+    Y, K = g["Y"].astype(prec), g["K"]
+    assert np.allclose(m.forward(K), g["mlp_out"], rtol=tol, atol=tol)
+    assert np.allclose(m.log_pseudo_joint(Y, K), g["lpj"], rtol=tol, atol=tol)
+    assert np.allclose(m.log_joint(Y, K), g["log_joint"], rtol=tol, atol=tol)
+    assert math.isclose(m.free_energy(Y, K), float(g["F"]), rel_tol=max(tol, 1e-6 if prec == np.float32 else 0))
+    if "gauss" in tag:
+        Yn = Y.copy()
+        Yn[1, 2] = np.nan
+        assert np.allclose(m.log_pseudo_joint(Yn, K), g["lpj_nan"], rtol=tol, atol=tol)
+        assert np.allclose(m.log_joint(Yn, K), g["log_joint_nan"], rtol=tol, atol=tol)
+    Fs = [m.update_param_batch(Y, K) for _ in range(3)]
+    assert np.allclose(Fs, g["F_steps"], rtol=max(tol, 1e-6 if prec == np.float32 else 0))
+    m.update_param_epoch()
+    for k, v in m.theta.items():
+        assert np.allclose(v, g[k + "_after"], rtol=10 * tol, atol=10 * tol), k
+
+
+def test_tvae_layer0_helpers():
+    rng = np.random.default_rng(0)
+    K = (rng.random((3, 4, 70)) < 0.2).astype(np.uint8)
+    W0, b0 = rng.standard_normal((70, 9)), rng.standard_normal(9)
+    out = om.tvae_layer0(K, W0, b0)
+    ref = np.stack([b0 + W0[np.flatnonzero(s)].sum(axis=0) for s in K.reshape(-1, 70)])
+    assert np.allclose(out, ref, rtol=1e-13, atol=1e-13)
+    g = rng.standard_normal((12, 9))
+    gw = om.tvae_layer0_grad(K, g)
+    ref = np.zeros((70, 9))
+    for r, s in enumerate(K.reshape(-1, 70)):
+        ref[np.flatnonzero(s)] += g[r]
+    assert np.allclose(gw, ref, rtol=1e-13, atol=1e-13)

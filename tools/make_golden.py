@@ -290,10 +290,58 @@ def golden_trainer():
              F_after=np.array(Fs), W=np.array(Ws), pies=np.array(ps), sigma2=np.array(s2))
 
 
+def golden_tvae():
+    """GaussianTVAE / BernoulliTVAE (tvo/models/tvae.py): lpj, log_joint, F, and theta after three
+    update_param_batch steps (Adam + the reference's CyclicLR) followed by update_param_epoch."""
+    from tvo.models import GaussianTVAE, BernoulliTVAE
+    rng = np.random.default_rng(11)
+    for kind, prec in (("gauss", to.float64), ("gauss", to.float32), ("bern", to.float64)):
+        N, S, H0, H1, D = 6, 7, 9, 5, 4
+        tag = f"tvae_{kind}_{'f64' if prec == to.float64 else 'f32'}"
+        W = [rng.standard_normal((H0, H1)) * 0.7, rng.standard_normal((H1, D)) * 0.7]
+        b = [rng.standard_normal(H1) * 0.3, rng.standard_normal(D) * 0.3]
+        pies = rng.uniform(0.1, 0.5, H0)
+        K = rand_states(rng, N, S, H0, p=0.3, zero_row=True)
+        kw = dict(W_init=[to.tensor(w) for w in W], b_init=[to.tensor(x) for x in b], pi_init=to.tensor(pies),
+                  precision=prec, min_lr=0.002, max_lr=0.02, cycliclr_step_size_up=2)
+        if kind == "gauss":
+            Y = rng.standard_normal((N, D)) * 1.3
+            m = GaussianTVAE(sigma2_init=0.6, **kw)
+        else:
+            Y = (rng.random((N, D)) < 0.4).astype(np.float64)
+            m = BernoulliTVAE(**kw)
+        Yt, Kt = to.tensor(Y, dtype=prec), to.tensor(K)
+        out = dict(W_0=W[0], W_1=W[1], b_0=b[0], b_1=b[1], pies=pies, Y=Y, K=K)
+        if kind == "gauss":
+            out["sigma2"] = np.array([0.6])
+            Ynan = Yt.clone()
+            Ynan[1, 2] = float("nan")
+            out["lpj_nan"] = m._log_pseudo_joint(Ynan, Kt)
+            out["log_joint_nan"] = m.log_joint(Ynan, Kt).detach()
+        lpj = m._log_pseudo_joint(Yt, Kt)
+        out["lpj"] = lpj
+        out["log_joint"] = m.log_joint(Yt, Kt).detach()
+        out["mlp_out"] = m.forward(Kt).detach()
+        st = _States(Kt, m.log_joint(Yt, Kt).detach().clone())
+        out["F"] = np.array(m.free_energy(to.arange(N), Yt, st))
+        Fs, lrs = [], []
+        for step in range(3):
+            st.lpj[:] = m.log_joint(Yt, Kt).detach()
+            Fs.append(m.update_param_batch(to.arange(N), Yt, st))
+            lrs.append(m._optimizer.param_groups[0]["lr"])
+        m.update_param_epoch()
+        out["F_steps"] = np.array(Fs)
+        out["lr_steps"] = np.array(lrs)
+        for k, v in m.theta.items():
+            out[f"{k}_after"] = v.detach()
+        out["data_estimator"] = m.data_estimator(to.arange(N), Yt, st).detach()
+        np.savez(os.path.join(OUT, f"{tag}.npz"), **_np(out))
+
+
 if __name__ == "__main__":
     to.set_default_dtype(to.float32)
     todo = {"bsc": golden_bsc, "noisyor": golden_noisyor, "sssc": golden_sssc, "dedup_merge": golden_dedup_merge,
-            "evo_stats": golden_evo_stats, "trainer": golden_trainer, "mixtures": golden_mixtures}
+            "evo_stats": golden_evo_stats, "trainer": golden_trainer, "mixtures": golden_mixtures, "tvae": golden_tvae}
     for name in (sys.argv[1:] or list(todo)):  # python tools/make_golden.py [name ...]
         todo[name]()
     for f in sorted(os.listdir(OUT)):

@@ -94,6 +94,9 @@ for _sfx in ("f64", "f32"):
                                        _I32, _P, _P],
         f"tvo_sssc_mstep_{_sfx}": [_P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32,
                                    _P],
+        f"tvo_tvae_layer0_{_sfx}": [_P, _I64, _I32, _P, _P, _I32, _P, _P],
+        f"tvo_tvae_layer0_grad_{_sfx}": [_P, _I64, _I32, _P, _I32, _P, _P],
+        f"tvo_tvae_lpj_{_sfx}": [_I32, _P, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P],
         f"tvo_bsc_mstep_{_sfx}": [_P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P],
     })
 _RESTYPES = {
