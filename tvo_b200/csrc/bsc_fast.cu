@@ -195,7 +195,7 @@ __device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, co
   const int n = position_list<LAT>(st, W64, plist, cap);
   if (n > cap) return bsc_gram_lpj_walk<T>(st, W64, H, a, G, prior, yy, coef);
   double f = 0.0, pr = 0.0;
-  if (LAT) {
+  if constexpr (LAT) {
     // latency-oriented order: all diagonal / a / prior terms first (four rows of loads in flight), then the
     // |s|(|s|-1)/2 off-diagonal gathers as ONE flattened pair list in batches of eight — about 1 + |s|^2/16 L2
     // round trips per state instead of one or two per active unit.  (A state is always scored by this same
@@ -242,17 +242,18 @@ __device__ __forceinline__ T bsc_gram_lpj(const uint64_t *st, int W64, int H, co
       for (int u = 0; u < 8; ++u) g += v[u];
     }
     return (T)((yy + (f + 2.0 * g)) * coef + pr);
+  } else {
+    for (int i = 0; i < n; ++i) {
+      const int h1 = plist[i * 32];
+      const double *Grow = G + (size_t)h1 * H;
+      f += __ldg(Grow + h1) - 2.0 * (double)__ldg(a + h1);
+      pr += (double)__ldg(prior + h1);
+      double g2 = 0.0;
+      for (int j = i + 1; j < n; ++j) g2 += __ldg(Grow + plist[j * 32]);
+      f += 2.0 * g2;
+    }
+    return (T)((yy + f) * coef + pr);
   }
-  for (int i = 0; i < n; ++i) {
-    const int h1 = plist[i * 32];
-    const double *Grow = G + (size_t)h1 * H;
-    f += __ldg(Grow + h1) - 2.0 * (double)__ldg(a + h1);
-    pr += (double)__ldg(prior + h1);
-    double g2 = 0.0;
-    for (int j = i + 1; j < n; ++j) g2 += __ldg(Grow + plist[j * 32]);
-    f += 2.0 * g2;
-  }
-  return (T)((yy + f) * coef + pr);
 }
 
 // direct form for one state, any D, warp-cooperative, y from global memory (NaN rows only)
