@@ -94,8 +94,24 @@ elif cfg in ("gmm", "pmm"):
                     to.full((H,), 1.0 / H), precision=to.float64)
     states = FullEMSingleCauseModels(N, H, to.float64)
     name = f"{cfg.upper()} full EM, single cause, D144 C256 fp64"
+elif cfg == "tvae":
+    # GaussianTVAE with the headline's latent / observable sizes and one hidden layer; mini-batches like the
+    # reference's training loop (the M-step is one Adam step per batch)
+    from tvo_b200.models import GaussianTVAE
+    N = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
+    H, H1, D, S, P, C, G = 256, 512, 144, 64, 16, 2, 2
+    prec = to.float32
+    Wgen = to.randn(D, H, device=dev, generator=g)
+    Y = to.empty(N, D, dtype=prec, device=dev)
+    for b0, b1 in chunks(N):
+        s = (to.rand(b1 - b0, H, device=dev, generator=g) < 5.0 / H).float()
+        Y[b0:b1] = s @ Wgen.t() + to.randn(b1 - b0, D, device=dev, generator=g)
+    to.manual_seed(0)
+    model = GaussianTVAE(shape=(D, H1, H), precision=prec, sigma2_init=1.0)
+    states = EVOVariationalStates(N, H, S, prec, "randparents", "sparseflip", P, G, C, bitflip_frequency=1.0 / H, seed=5)
+    name = "GaussianTVAE D144 H1=512 H0=256 S64 EVO(randparents,sparseflip,P16,C2,G2) fp32, batches of 8192"
 else:
-    raise SystemExit("usage: bench_configs.py c3|c4|c5|gmm|pmm [N] [iters]")
+    raise SystemExit("usage: bench_configs.py c3|c4|c5|gmm|pmm|tvae [N] [iters]")
 
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 idx = to.arange(N, device=dev)
@@ -103,18 +119,38 @@ te, tm, tp, Fs = [], [], [], []
 for it in range(iters + 2):
     ev = [to.cuda.Event(enable_timing=True) for _ in range(4)]
     ev[0].record()
-    states.update_device(idx, Y, model)
-    ev[1].record()
-    model.update_param_batch(idx, Y, states)
-    ev[2].record()
+    if cfg == "tvae":  # mini-batches: E-step and the Adam step alternate per batch (Trainer.py:232-254)
+        evs = []
+        for b0 in range(0, N, 8192):
+            ib = idx[b0:b0 + 8192]
+            e3 = [to.cuda.Event(enable_timing=True) for _ in range(3)]
+            e3[0].record()
+            states.update_device(ib, Y[ib], model)
+            e3[1].record()
+            model.update_param_batch(ib, Y[ib], states)
+            e3[2].record()
+            evs.append(e3)
+        ev[1].record()
+        ev[2].record()
+    else:
+        states.update_device(idx, Y, model)
+        ev[1].record()
+        model.update_param_batch(idx, Y, states)
+        ev[2].record()
     model.update_param_epoch()
     ev[3].record()
     to.cuda.synchronize()
-    if it >= 2:
+    if it >= 2 and cfg == "tvae":
+        te.append(sum(e[0].elapsed_time(e[1]) for e in evs))
+        tm.append(sum(e[1].elapsed_time(e[2]) for e in evs))
+        tp.append(ev[2].elapsed_time(ev[3]))
+    elif it >= 2:
         te.append(ev[0].elapsed_time(ev[1]))
         tm.append(ev[1].elapsed_time(ev[2]))
         tp.append(ev[2].elapsed_time(ev[3]))
     F = getattr(model, "_last_F", None)
+    if cfg == "tvae":
+        F = to.logsumexp(states.lpj, dim=1).sum()
     Fs.append(float(F) / N if F is not None else float("nan"))
 e, m, p = statistics.median(te), statistics.median(tm), statistics.median(tp)
 print(json.dumps({"config": name, "N": N, "estep_ms": e, "mstep_ms": m, "epoch_update_ms": p,
