@@ -67,45 +67,79 @@ __global__ void nor_prepare_kernel(const T *__restrict__ W, const T *__restrict_
   }
 }
 
-// lpj of ONE state, warp-cooperative (lanes over d).  ybits: bit i of lane l = y[l + 32 i] != 0.
+// eight consecutive values, 32-byte aligned
+__device__ __forceinline__ void ldg8(const float *p, float (&v)[8]) {
+  const float4 t = __ldg(reinterpret_cast<const float4 *>(p)), u = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+  v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w, v[4] = u.x, v[5] = u.y, v[6] = u.z, v[7] = u.w;
+}
+__device__ __forceinline__ void ldg8(const double *p, double (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double2 t = __ldg(reinterpret_cast<const double2 *>(p) + i);
+    v[2 * i] = t.x, v[2 * i + 1] = t.y;
+  }
+}
+
+// lpj of TWO states per pass: lanes 0-15 score state s, lanes 16-31 state s + 1.  Within a group of 128
+// observables half-lane hl owns the eight CONSECUTIVE columns 8 hl .. 8 hl + 7, so one active unit costs two (fp32)
+// vector loads and eight multiplies per lane for two states, and the reduction over d is four shuffles.
+// (One warp per state with one column per lane and chunk spent ~225 warp instructions per state, 74 % of the fused
+// E-step; the kernel issues at 75 % of peak, so instructions are what it is made of.)
+// ybits: bit 8 g + q of half-lane hl = y[128 g + 8 hl + q] != 0 (same in both halves).
+// sum_d log t_d is taken as one log per four columns: every term is clamped to [1e-7, 1 - 1e-7], so a product of
+// four stays above 1e-28 (eight would underflow fp32).
 template <typename T>
-__device__ inline T nor_state_lpj(const uint64_t *st, int W64, const NorTheta<T> &th, const uint32_t *ybits, bool any_y,
-                                  int D, int lane) {
-  uint64_t any = 0;
-  for (int w = 0; w < W64; ++w) any |= st[w];
-  if (!any) return any_y ? T(-1e30) : T(0);  // noisyor.py:83-86,102
+__device__ inline void nor_score_pair(const uint64_t *states, int s, int count, int W64, const NorTheta<T> &th,
+                                      const uint32_t *ybits, bool any_y, int D, T *out, int lane) {
+  const int half = lane >> 4, hl = lane & 15;
+  const int ms = s + half;
+  const bool valid = ms < count;
+  const uint64_t *st = states + (size_t)(valid ? ms : s) * W64;
   const T lo = (T)kNorEps, hi = T(1) - (T)kNorEps;
+  uint64_t any = 0;
   T acc = T(0), pr = T(0);
-  // the set bits are walked once per group of 4 column chunks (128 observables), products in registers;
-  // sum_d log t_d is taken as ONE log per lane and group: every term is clamped to [1e-7, 1 - 1e-7], so the
-  // product of a lane's four terms stays above 1e-28 (E-step 29.5 -> 23.4 ms at C4)
-  for (int c0 = 0, ci0 = 0; c0 < th.Dpad; c0 += 128, ci0 += 4) {
-    T P[4] = {T(1), T(1), T(1), T(1)};
+  for (int c0 = 0, g = 0; c0 < th.Dpad; c0 += 128, ++g) {
+    T P[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) P[q] = T(1);
+    const bool colok = c0 + 8 * hl < th.Dpad;  // Dpad is a multiple of 32: the eight columns are inside the row
     for (int w = 0; w < W64; ++w) {
       uint64_t word = st[w];
-      while (word) {
+      if (c0 == 0) any |= word;
+      while (word) {  // per-lane trip count: the halves walk different states
         const int h = (w << 6) + __ffsll((long long)word) - 1;
         word &= word - 1;
-        const T *row = th.W1mT + (size_t)h * th.Dpad + c0 + lane;
+        if (colok) {
+          T v[8];
+          ldg8(th.W1mT + (size_t)h * th.Dpad + c0 + 8 * hl, v);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (c0 + 32 * q < th.Dpad) P[q] *= __ldg(row + 32 * q);
+          for (int q = 0; q < 8; ++q) P[q] *= v[q];
+        }
         if (c0 == 0) pr += __ldg(th.prior + h);
       }
     }
-    T prod = T(1);
-    const uint32_t yb = (ci0 < 32 ? ybits[0] >> ci0 : ybits[1] >> (ci0 - 32)) & 0xFu;  // ci0 is a multiple of 4
+    // static indices only: the four words stay in registers
+    const uint32_t yw = g < 4 ? ybits[0] : (g < 8 ? ybits[1] : (g < 12 ? ybits[2] : ybits[3]));
+    const uint32_t yb = (yw >> (8 * (g & 3))) & 0xFFu;
+    T prod0 = T(1), prod1 = T(1);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (c0 + 32 * q + lane < D) {
-        T Pc = P[q] < lo ? lo : (P[q] > hi ? hi : P[q]);  // to.clamp (noisyor.py:89)
+    for (int q = 0; q < 8; ++q) {
+      if (c0 + 8 * hl + q < D) {
+        const T Pc = P[q] < lo ? lo : (P[q] > hi ? hi : P[q]);  // to.clamp (noisyor.py:89)
         // y log(1/P - 1) + log P  ==  y ? log(1 - P) : log P   (noisyor.py:91-97)
-        prod *= ((yb >> q) & 1u) ? T(1) - Pc : Pc;
+        const T t = ((yb >> q) & 1u) ? T(1) - Pc : Pc;
+        if (q < 4)
+          prod0 *= t;
+        else
+          prod1 *= t;
       }
     }
-    acc += log(prod);
+    acc += log(prod0) + log(prod1);
   }
-  return pr + warp_sum(acc);
+  __syncwarp();
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);  // stays inside the 16-lane half
+  if (hl == 0 && valid) out[ms] = any ? pr + acc : (any_y ? T(-1e30) : T(0));  // all-zero state: noisyor.py:83-86,102
 }
 
 // model adapter for the generic fused E-step kernel
@@ -119,21 +153,32 @@ struct NorModel {
   };
   static size_t smem_bytes(const Params &) { return 0; }
   struct Ctx {
-    uint32_t ybits[2];  // D <= 2048
+    uint32_t ybits[4];  // D <= 2048: 16 groups of 128 observables x 8 columns per half-lane
     bool any_y;
     __device__ void load(const Params &p, int64_t b, unsigned char *, int lane) {
       const uint8_t *y = p.Y + b * p.ldY;
-      ybits[0] = ybits[1] = 0;
-      for (int d = lane, i = 0; d < p.D; d += 32, ++i)
-        if (y[d]) ybits[i >> 5] |= 1u << (i & 31);
-      any_y = __any_sync(FULL, (ybits[0] | ybits[1]) != 0);
+      const int hl = lane & 15;
+      ybits[0] = ybits[1] = ybits[2] = ybits[3] = 0;
+      for (int c0 = 0, g = 0; c0 < p.D; c0 += 128, ++g)
+        for (int q = 0; q < 8; ++q) {
+          const int d = c0 + 8 * hl + q;
+          if (d < p.D && y[d]) {
+            const uint32_t bit = 1u << (8 * (g & 3) + q);
+            if (g < 4)
+              ybits[0] |= bit;
+            else if (g < 8)
+              ybits[1] |= bit;
+            else if (g < 12)
+              ybits[2] |= bit;
+            else
+              ybits[3] |= bit;
+          }
+        }
+      any_y = __any_sync(FULL, (ybits[0] | ybits[1] | ybits[2] | ybits[3]) != 0);
     }
     __device__ void score(const Params &p, const uint64_t *states, int count, int W64, T *out, int lane) {
       const NorTheta<T> th = nor_theta_view<T>(p.ws, p.H, p.D);
-      for (int s = 0; s < count; ++s) {
-        const T v = nor_state_lpj<T>(states + (size_t)s * W64, W64, th, ybits, any_y, p.D, lane);
-        if (lane == 0) out[s] = v;
-      }
+      for (int s = 0; s < count; s += 2) nor_score_pair<T>(states, s, count, W64, th, ybits, any_y, p.D, out, lane);
       __syncwarp();
     }
   };
