@@ -469,6 +469,168 @@ nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *
   }
 }
 
+// M-step, slot form (fp32 mode).  The (state, active unit) pairs of a datapoint are what the work is made of
+// (S |s| of them, |s| ~ 2-3 of H); the register-stationary kernel above visits them with 8 predicated h per thread
+// and one h-tile per CTA (ncu at C4: 69.6 k warp instructions per datapoint, barrier the top stall).  Here a CTA of
+// 512 threads holds Btilde / Ctilde for ALL h in shared memory ([h][d], fp32) and is split into 512 / Dpad slots of
+// Dpad threads (thread = slot, column d): slot k owns the units h = k (mod slots), so within a datapoint no two
+// threads ever touch the same accumulator and the updates are plain shared-memory read-modify-writes — no atomics,
+// no predicated-off lanes.  Every kNorFlush datapoints the fp32 partial sums are added to the fp64 statistics in
+// global memory (REDs) and cleared, which bounds the fp32 accumulation error (a few hundred terms per flush).
+constexpr int kNorFlush = 256;
+__global__ void __launch_bounds__(512, 2)
+nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx,
+                      const uint64_t *__restrict__ K, int64_t k_stride_n, const float *__restrict__ lpj,
+                      int64_t lpj_stride_n, const float *__restrict__ W1mT, const double *__restrict__ prior_sum,
+                      double *__restrict__ stats, int64_t B, int S, int H, int D, int W64, int Dpad, int q_off, int k_off,
+                      int acc_off) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nslots = 512 / Dpad;  // power of two, <= 16
+  const int d = tid % Dpad, slot = tid / Dpad;
+  float *Qsm = (float *)smem_raw;                        // S x Dpad
+  float *q = (float *)(smem_raw + q_off);                // S
+  uint64_t *Ksm = (uint64_t *)(smem_raw + k_off);        // S x W64
+  float *accB = (float *)(smem_raw + acc_off);           // H x Dpad
+  float *accC = accB + (size_t)H * Dpad;                 // H x Dpad
+  __shared__ double red;
+  // bits h with h % nslots == slot, replicated over a 64-bit word (64 % nslots == 0)
+  uint64_t slotmask = 0;
+  for (int h = slot; h < 64; h += nslots) slotmask |= 1ull << h;
+  for (int t = tid; t < 2 * H * Dpad; t += 512) accB[t] = 0.f;
+  double pi_acc = 0.0, accF = 0.0, accN = 0.0;  // pi: thread tid < H owns unit tid (H <= 512)
+  const float eps = (float)kNorEps;
+  const size_t HD = (size_t)H * D;
+  int since_flush = 0;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const int64_t row = idx ? idx[b] : b;
+    const float *l = lpj + row * lpj_stride_n;
+    __syncthreads();  // previous datapoint fully consumed
+    for (int t = tid; t < S * W64; t += 512) Ksm[t] = K[row * k_stride_n + t];
+    const float ym1 = (d < D ? (float)Y[b * ldY + d] : 1.f) - 1.f;
+    if (tid < 32) {  // softmax weights (lpj2pjc, _utils.py:182-191)
+      double mx = -INFINITY;
+      for (int s = lane; s < S; s += 32) mx = fmax(mx, (double)l[s]);
+      mx = warp_max(mx);
+      double se = 0.0;
+      for (int s = lane; s < S; s += 32) se += exp((double)l[s] - mx);
+      se = warp_sum(se);
+      for (int s = lane; s < S; s += 32) q[s] = (float)(exp((double)l[s] - mx) / se);
+      if (lane == 0) red = mx + log(se);
+    }
+    __syncthreads();
+    // phase 1: Q_sd over ALL active h of the state (noisyor.py:123-124), ascending h
+    for (int s = slot; s < S; s += nslots) {
+      const uint64_t *st = Ksm + s * W64;
+      float Q = 1.f;
+      for (int w = 0; w < W64; ++w) {
+        uint64_t word = st[w];
+        while (word) {
+          const int h = (w << 6) + __ffsll((long long)word) - 1;
+          word &= word - 1;
+          Q *= __ldg(W1mT + (size_t)h * Dpad + d);
+        }
+      }
+      Qsm[s * Dpad + d] = Q;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      accF += red + *prior_sum;
+      accN += 1.0;
+    }
+    if (tid < H) {  // new_pi += <s_h>  (noisyor.py:117)
+      double e = 0.0;
+      for (int s = 0; s < S; ++s)
+        if ((Ksm[s * W64 + (tid >> 6)] >> (tid & 63)) & 1ull) e += (double)q[s];
+      pi_acc += e;
+    }
+    // phase 2: Btilde, Ctilde (noisyor.py:121-132): this slot's units of every state, column d
+    for (int w = 0; w < W64; ++w) {
+      for (int s0 = 0; s0 < S; s0 += 32) {  // 32 states tested at once, one per lane (the slot is warp-uniform)
+        const int sl = s0 + lane;
+        const uint64_t ml = sl < S ? (Ksm[sl * W64 + w] & slotmask) : 0ull;
+        unsigned act = __ballot_sync(FULL, ml != 0ull);
+        while (act) {
+          const int src = __ffs((int)act) - 1;
+          act &= act - 1;
+          uint64_t m = __shfl_sync(FULL, ml, src);
+          const int s = s0 + src;
+          const float qs = q[s];
+          const float Q = Qsm[s * Dpad + d];
+          const float omq = 1.f - Q;
+          while (m) {
+            const int h = (w << 6) + __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const float Ws = __ldg(W1mT + (size_t)h * Dpad + d);
+            const float Bv = __fdividef(1.f, Ws * omq + eps);
+            const float Cv = __fdividef(Bv * Q, Ws);
+            accB[h * Dpad + d] += qs * (Bv * ym1);
+            accC[h * Dpad + d] += qs * Cv;
+          }
+        }
+      }
+    }
+    if (++since_flush == kNorFlush) {
+      since_flush = 0;
+      __syncthreads();
+      for (int t = tid; t < H * Dpad; t += 512) {
+        const int h = t / Dpad, dd = t - h * Dpad;
+        const float vb = accB[t], vc = accC[t];
+        if (dd < D) {
+          if (vb != 0.f) atomicAdd(stats + (size_t)h * D + dd, (double)vb);
+          if (vc != 0.f) atomicAdd(stats + HD + (size_t)h * D + dd, (double)vc);
+        }
+        accB[t] = 0.f;
+        accC[t] = 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < H * Dpad; t += 512) {
+    const int h = t / Dpad, dd = t - h * Dpad;
+    const float vb = accB[t], vc = accC[t];
+    if (dd < D) {
+      if (vb != 0.f) atomicAdd(stats + (size_t)h * D + dd, (double)vb);
+      if (vc != 0.f) atomicAdd(stats + HD + (size_t)h * D + dd, (double)vc);
+    }
+  }
+  if (tid < H && pi_acc != 0.0) atomicAdd(stats + 2 * HD + tid, pi_acc);
+  if (tid == 0 && accN != 0.0) {
+    atomicAdd(stats + 2 * HD + H, accN);
+    atomicAdd(stats + 2 * HD + H + 1, accF);
+  }
+}
+
+template <typename T>
+static int nor_mstep_slot(const uint8_t *, int64_t, const int64_t *, const uint64_t *, int64_t, const T *, int64_t,
+                          const void *, double *, int64_t, int, int, int, void *, bool &done) {
+  done = false;  // fp64 mode keeps the register-stationary kernel (fp64 accumulators, IEEE division)
+  return TVO_OK;
+}
+template <>
+int nor_mstep_slot<float>(const uint8_t *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, int64_t k_stride_n,
+                          const float *lpj, int64_t lpj_stride_n, const void *ws, double *stats, int64_t B, int S, int H,
+                          int D, void *stream, bool &done) {
+  done = false;
+  const int Dpad = nor_dpad(D), W64 = n_words(H);
+  if (!(Dpad <= 256 && 512 % Dpad == 0 && H <= 512)) return TVO_OK;
+  const int q_off = (int)align16((size_t)S * Dpad * 4), k_off = q_off + (int)align16((size_t)S * 4),
+            acc_off = k_off + (int)align16((size_t)S * W64 * 8);
+  const size_t smem = (size_t)acc_off + (size_t)2 * H * Dpad * 4;
+  if (smem > 110 * 1024) return TVO_OK;  // two CTAs per SM
+  auto kern = nor_mstep_slot_kernel;
+  TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 512, smem));
+  const int gx = (int)max((int64_t)1, min(B, (int64_t)sm_count() * max(occ, 1)));
+  const NorTheta<float> th = nor_theta_view<float>(ws, H, D);
+  kern<<<gx, 512, smem, (cudaStream_t)stream>>>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, th.W1mT, &th.hdr->prior_sum,
+                                                stats, B, S, H, D, W64, Dpad, q_off, k_off, acc_off);
+  TVO_AFTER_LAUNCH("noisyor_mstep_slot");
+  done = true;
+  return TVO_OK;
+}
+
 // ------------------------------------------------------------------------------------ host side
 template <typename T>
 int nor_prepare(const T *W, const T *pies, int H, int D, void *ws, void *stream) {
@@ -514,6 +676,11 @@ int nor_mstep(const uint8_t *Y, int64_t ldY, const int64_t *idx, const uint64_t 
   TVO_REQUIRE(B >= 0 && S > 0 && H > 0 && D > 0, "noisyor_mstep: bad sizes");
   if (B == 0) return TVO_OK;
   const int Dpad = nor_dpad(D), W64 = n_words(H);
+  {
+    bool done = false;  // fp32 mode: shared-memory accumulators, one unit class per thread slot
+    int rc = nor_mstep_slot<T>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, ws, stats, B, S, H, D, stream, done);
+    if (rc || done) return rc;
+  }
   if (Dpad <= 256 && 512 % Dpad == 0) {  // register-stationary accumulators
     const size_t smem2 = align16((size_t)S * Dpad * sizeof(T)) + (size_t)S * 8 + (size_t)S * W64 * 8;
     if (smem2 <= 100 * 1024) {
