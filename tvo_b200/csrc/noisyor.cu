@@ -508,17 +508,22 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
     __syncthreads();  // previous datapoint fully consumed
     for (int t = tid; t < S * W64; t += 512) Ksm[t] = K[row * k_stride_n + t];
     const float ym1 = (d < D ? (float)Y[b * ldY + d] : 1.f) - 1.f;
-    if (tid < 32) {  // softmax weights (lpj2pjc, _utils.py:182-191)
-      double mx = -INFINITY;
-      for (int s = lane; s < S; s += 32) mx = fmax(mx, (double)l[s]);
-      mx = warp_max(mx);
-      double se = 0.0;
-      for (int s = lane; s < S; s += 32) se += exp((double)l[s] - mx);
-      se = warp_sum(se);
-      for (int s = lane; s < S; s += 32) q[s] = (float)(exp((double)l[s] - mx) / se);
-      if (lane == 0) red = mx + log(se);
-    }
     __syncthreads();
+    if (tid >= 512 - 32) {  // softmax weights (lpj2pjc, _utils.py:182-191) by the LAST warp, which then joins phase 1
+      float mx = -INFINITY;
+      for (int s = lane; s < S; s += 32) mx = fmaxf(mx, l[s]);
+      mx = warp_max(mx);
+      float se = 0.f;
+      for (int s = lane; s < S; s += 32) {
+        const float e = expf(l[s] - mx);
+        q[s] = e;
+        se += e;
+      }
+      se = warp_sum(se);
+      const float inv = 1.f / se;
+      for (int s = lane; s < S; s += 32) q[s] *= inv;
+      if (lane == 0) red = (double)mx + log((double)se);
+    }
     // phase 1: Q_sd over ALL active h of the state (noisyor.py:123-124), ascending h
     for (int s = slot; s < S; s += nslots) {
       const uint64_t *st = Ksm + s * W64;
