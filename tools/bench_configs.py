@@ -157,3 +157,8 @@ print(json.dumps({"config": name, "N": N, "estep_ms": e, "mstep_ms": m, "epoch_u
                   "estep_datapoints_per_s": N / e * 1e3, "em_iter_datapoints_per_s": N / (e + m + p) * 1e3,
                   "epoch_update_ms_all": [round(x, 2) for x in tp], "estep_ms_all": [round(x, 2) for x in te],
                   "F_per_datapoint_trajectory": [round(f, 4) for f in Fs], "subs_per_datapoint_last": states._take_nsubs() / N / (iters + 2)}))
+if os.environ.get("TVO_STATE_STATS"):  # sparsity of the final K (diagnostic)
+    from tvo_b200.variational._packed import unpack
+    pc = unpack(states._Kp[:20000], H).sum(dim=2)
+    print(json.dumps({"mean_active_units": float(pc.float().mean()), "max_active_units": int(pc.max()),
+                      "frac_datapoints_with_state_over_7": float((pc.max(dim=1).values > 7).float().mean())}))

@@ -478,6 +478,10 @@ nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *
 // no predicated-off lanes.  Every kNorFlush datapoints the fp32 partial sums are added to the fp64 statistics in
 // global memory (REDs) and cleared, which bounds the fp32 accumulation error (a few hundred terms per flush).
 constexpr int kNorFlush = 256;
+// V columns per thread: V = 4 (Dpad >= 128) makes a slot ONE warp — 4 consecutive columns per lane, vector loads of
+// 1 - W, Q and the accumulators — so the per-(state, unit) control work (ballot, shuffle, bit walk) is paid once
+// per 128 columns instead of once per 32, and 16 slots share the units of a datapoint; V = 1 for narrower D.
+template <int V>
 __global__ void __launch_bounds__(512, 2)
 nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx,
                       const uint64_t *__restrict__ K, int64_t k_stride_n, const float *__restrict__ lpj,
@@ -486,8 +490,9 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
                       int acc_off) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int nslots = 512 / Dpad;  // power of two, <= 16
-  const int d = tid % Dpad, slot = tid / Dpad;
+  const int tps = Dpad / V;        // threads per slot (a multiple of 32)
+  const int nslots = 512 / tps;    // power of two, <= 16
+  const int d = (tid % tps) * V, slot = tid / tps;
   float *Qsm = (float *)smem_raw;                        // S x Dpad
   float *q = (float *)(smem_raw + q_off);                // S
   uint64_t *Ksm = (uint64_t *)(smem_raw + k_off);        // S x W64
@@ -507,7 +512,9 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
     const float *l = lpj + row * lpj_stride_n;
     __syncthreads();  // previous datapoint fully consumed
     for (int t = tid; t < S * W64; t += 512) Ksm[t] = K[row * k_stride_n + t];
-    const float ym1 = (d < D ? (float)Y[b * ldY + d] : 1.f) - 1.f;
+    float ym1[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) ym1[v] = (d + v < D ? (float)Y[b * ldY + d + v] : 1.f) - 1.f;
     __syncthreads();
     if (tid >= 512 - 32) {  // softmax weights (lpj2pjc, _utils.py:182-191) by the LAST warp, which then joins phase 1
       float mx = -INFINITY;
@@ -527,16 +534,27 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
     // phase 1: Q_sd over ALL active h of the state (noisyor.py:123-124), ascending h
     for (int s = slot; s < S; s += nslots) {
       const uint64_t *st = Ksm + s * W64;
-      float Q = 1.f;
+      float Q[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) Q[v] = 1.f;
       for (int w = 0; w < W64; ++w) {
         uint64_t word = st[w];
         while (word) {
           const int h = (w << 6) + __ffsll((long long)word) - 1;
           word &= word - 1;
-          Q *= __ldg(W1mT + (size_t)h * Dpad + d);
+          const float *wr = W1mT + (size_t)h * Dpad + d;
+          if (V == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(wr));
+            Q[0] *= t.x, Q[V > 1 ? 1 : 0] *= t.y, Q[V > 2 ? 2 : 0] *= t.z, Q[V > 3 ? 3 : 0] *= t.w;
+          } else {
+            Q[0] *= __ldg(wr);
+          }
         }
       }
-      Qsm[s * Dpad + d] = Q;
+      if (V == 4)
+        *reinterpret_cast<float4 *>(Qsm + s * Dpad + d) = make_float4(Q[0], Q[V > 1 ? 1 : 0], Q[V > 2 ? 2 : 0], Q[V > 3 ? 3 : 0]);
+      else
+        Qsm[s * Dpad + d] = Q[0];
     }
     __syncthreads();
     if (tid == 0) {
@@ -549,7 +567,7 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
         if ((Ksm[s * W64 + (tid >> 6)] >> (tid & 63)) & 1ull) e += (double)q[s];
       pi_acc += e;
     }
-    // phase 2: Btilde, Ctilde (noisyor.py:121-132): this slot's units of every state, column d
+    // phase 2: Btilde, Ctilde (noisyor.py:121-132): this slot's units of every state, columns d .. d + V - 1
     for (int w = 0; w < W64; ++w) {
       for (int s0 = 0; s0 < S; s0 += 32) {  // 32 states tested at once, one per lane (the slot is warp-uniform)
         const int sl = s0 + lane;
@@ -561,16 +579,45 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
           uint64_t m = __shfl_sync(FULL, ml, src);
           const int s = s0 + src;
           const float qs = q[s];
-          const float Q = Qsm[s * Dpad + d];
-          const float omq = 1.f - Q;
+          float Q[V], omq[V];
+          if (V == 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(Qsm + s * Dpad + d);
+            Q[0] = t.x, Q[V > 1 ? 1 : 0] = t.y, Q[V > 2 ? 2 : 0] = t.z, Q[V > 3 ? 3 : 0] = t.w;
+          } else {
+            Q[0] = Qsm[s * Dpad + d];
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) omq[v] = 1.f - Q[v];
           while (m) {
             const int h = (w << 6) + __ffsll((long long)m) - 1;
             m &= m - 1;
-            const float Ws = __ldg(W1mT + (size_t)h * Dpad + d);
-            const float Bv = __fdividef(1.f, Ws * omq + eps);
-            const float Cv = __fdividef(Bv * Q, Ws);
-            accB[h * Dpad + d] += qs * (Bv * ym1);
-            accC[h * Dpad + d] += qs * Cv;
+            float Ws[V], ab[V], ac[V];
+            float *pb = accB + h * Dpad + d, *pc = accC + h * Dpad + d;
+            if (V == 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4 *>(W1mT + (size_t)h * Dpad + d));
+              Ws[0] = t.x, Ws[V > 1 ? 1 : 0] = t.y, Ws[V > 2 ? 2 : 0] = t.z, Ws[V > 3 ? 3 : 0] = t.w;
+              const float4 u = *reinterpret_cast<const float4 *>(pb), x = *reinterpret_cast<const float4 *>(pc);
+              ab[0] = u.x, ab[V > 1 ? 1 : 0] = u.y, ab[V > 2 ? 2 : 0] = u.z, ab[V > 3 ? 3 : 0] = u.w;
+              ac[0] = x.x, ac[V > 1 ? 1 : 0] = x.y, ac[V > 2 ? 2 : 0] = x.z, ac[V > 3 ? 3 : 0] = x.w;
+            } else {
+              Ws[0] = __ldg(W1mT + (size_t)h * Dpad + d);
+              ab[0] = *pb;
+              ac[0] = *pc;
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float Bv = __fdividef(1.f, Ws[v] * omq[v] + eps);
+              const float Cv = __fdividef(Bv * Q[v], Ws[v]);
+              ab[v] += qs * (Bv * ym1[v]);
+              ac[v] += qs * Cv;
+            }
+            if (V == 4) {
+              *reinterpret_cast<float4 *>(pb) = make_float4(ab[0], ab[V > 1 ? 1 : 0], ab[V > 2 ? 2 : 0], ab[V > 3 ? 3 : 0]);
+              *reinterpret_cast<float4 *>(pc) = make_float4(ac[0], ac[V > 1 ? 1 : 0], ac[V > 2 ? 2 : 0], ac[V > 3 ? 3 : 0]);
+            } else {
+              *pb = ab[0];
+              *pc = ac[0];
+            }
           }
         }
       }
@@ -623,7 +670,7 @@ int nor_mstep_slot<float>(const uint8_t *Y, int64_t ldY, const int64_t *idx, con
             acc_off = k_off + (int)align16((size_t)S * W64 * 8);
   const size_t smem = (size_t)acc_off + (size_t)2 * H * Dpad * 4;
   if (smem > 110 * 1024) return TVO_OK;  // two CTAs per SM
-  auto kern = nor_mstep_slot_kernel;
+  auto kern = Dpad >= 128 ? nor_mstep_slot_kernel<4> : nor_mstep_slot_kernel<1>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 512, smem));
