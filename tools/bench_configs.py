@@ -160,5 +160,7 @@ print(json.dumps({"config": name, "N": N, "estep_ms": e, "mstep_ms": m, "epoch_u
 if os.environ.get("TVO_STATE_STATS"):  # sparsity of the final K (diagnostic)
     from tvo_b200.variational._packed import unpack
     pc = unpack(states._Kp[:20000], H).sum(dim=2)
-    print(json.dumps({"mean_active_units": float(pc.float().mean()), "max_active_units": int(pc.max()),
+    hist = to.bincount(pc.flatten().long(), minlength=12)[:12].float()
+    print(json.dumps({"hist_active_units_0_11": [round(float(x), 5) for x in hist / hist.sum()],
+                      "mean_active_units": float(pc.float().mean()), "max_active_units": int(pc.max()),
                       "frac_datapoints_with_state_over_7": float((pc.max(dim=1).values > 7).float().mean())}))

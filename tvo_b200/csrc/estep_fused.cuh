@@ -15,10 +15,13 @@
 
 namespace tvo {
 
-// MAXW = 8: CTAs of 8 warps, up to 3 per SM (80 registers);  MAXW = 12: working sets that allow only ONE CTA per SM
-// (e.g. SSSC: 21 kB per warp) run it with as many warps as its shared memory holds — every resident warp counts there.
-template <typename T, typename Model, int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, MAXW == 8 ? 3 : 1)
+// Three register / residency tiers, picked by how many 8-warp CTAs the working set allows per SM:
+//   <8, 3>  three or more CTAs of 8 warps (80 registers; NoisyOR);
+//   <8, 2>  two CTAs of 8 warps with 128 registers (SSSC at H = 256: 10.4 kB per warp; its fp64 Cholesky scorer spills
+//           at 80 registers — 17.9 ms against 13.x ms at C3);
+//   <12, 1> one CTA per SM with as many warps as its shared memory holds (up to 12) and no register cap.
+template <typename T, typename Model, int MAXW, int MINB>
+__global__ void __launch_bounds__(32 * MAXW, MINB)
 estep_evo_fused_kernel(typename Model::Params mp, const int64_t *__restrict__ idx, int64_t row0,
                        uint64_t *__restrict__ K, T *__restrict__ lpj, EvoParams ep,
                        const double *__restrict__ sparsity_p, EstepDims dims, size_t model_smem, int64_t B, int H,
@@ -90,17 +93,21 @@ int launch_estep_evo_fused(const typename Model::Params &mp, const int64_t *idx,
   while (wpb > 1 && wbytes * wpb > (size_t)227 * 1024) wpb >>= 1;
   TVO_REQUIRE(wbytes * wpb <= (size_t)227 * 1024, "%s: per-datapoint working set %zu B exceeds shared memory", who, wbytes);
   size_t smem = wbytes * wpb;
-  auto kern = estep_evo_fused_kernel<T, Model, 8>;
+  auto kern = estep_evo_fused_kernel<T, Model, 8, 3>;
+  const size_t fit8 = wpb == 8 ? ((size_t)227 * 1024) / (smem + 1024) : 0;  // 8-warp CTAs per SM by shared memory
+  if (wpb == 8 && fit8 == 2) {
+    kern = estep_evo_fused_kernel<T, Model, 8, 2>;
+  } else if (wpb == 8 && fit8 <= 1 && wbytes * 9 <= (size_t)227 * 1024) {  // one CTA per SM: widen it
+    wpb = (int)min((size_t)12, (size_t)227 * 1024 / wbytes);
+    smem = wbytes * wpb;
+    kern = estep_evo_fused_kernel<T, Model, 12, 1>;
+  } else if (wpb < 8 || fit8 <= 1) {
+    kern = estep_evo_fused_kernel<T, Model, 12, 1>;  // a single narrow CTA: no reason to cap its registers
+  }
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
   occ = max(occ, 1);
-  if (wpb == 8 && occ == 1 && wbytes * 9 <= (size_t)227 * 1024) {  // one CTA per SM: widen it
-    wpb = (int)min((size_t)12, (size_t)227 * 1024 / wbytes);
-    smem = wbytes * wpb;
-    kern = estep_evo_fused_kernel<T, Model, 12>;
-    TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
   const int grid = (int)max((int64_t)1, min((B + wpb - 1) / wpb, (int64_t)sm_count() * occ));
   kern<<<grid, wpb * 32, smem, stream>>>(mp, idx, row0, K, lpj, ep, sparsity, dims, msm, B, H,
                                          (unsigned long long *)nsubs);
