@@ -19,7 +19,9 @@ namespace tvo {
 //   <8, 3>  three or more CTAs of 8 warps (80 registers; NoisyOR);
 //   <8, 2>  two CTAs of 8 warps with 128 registers (SSSC at H = 256: 10.4 kB per warp; its fp64 Cholesky scorer spills
 //           at 80 registers — 17.9 ms against 13.x ms at C3);
-//   <12, 1> one CTA per SM with as many warps as its shared memory holds (up to 12) and no register cap.
+//   <16, 1> one CTA per SM with as many warps as its shared memory holds (up to 16; 14 for SSSC at H = 256).
+// Measured at C3 (E-step per 200k): 8 warps 19.1 ms, 10 warps 14.9, 12 warps 12.6, 14 warps 11.1; two CTAs of 8 warps at
+// 128 registers with a smaller sub-warp scratch (4 units) 15.9.
 template <typename T, typename Model, int MAXW, int MINB>
 __global__ void __launch_bounds__(32 * MAXW, MINB)
 estep_evo_fused_kernel(typename Model::Params mp, const int64_t *__restrict__ idx, int64_t row0,
@@ -98,11 +100,11 @@ int launch_estep_evo_fused(const typename Model::Params &mp, const int64_t *idx,
   if (wpb == 8 && fit8 == 2) {
     kern = estep_evo_fused_kernel<T, Model, 8, 2>;
   } else if (wpb == 8 && fit8 <= 1 && wbytes * 9 <= (size_t)227 * 1024) {  // one CTA per SM: widen it
-    wpb = (int)min((size_t)12, (size_t)227 * 1024 / wbytes);
+    wpb = (int)min((size_t)16, (size_t)227 * 1024 / wbytes);
     smem = wbytes * wpb;
-    kern = estep_evo_fused_kernel<T, Model, 12, 1>;
+    kern = estep_evo_fused_kernel<T, Model, 16, 1>;
   } else if (wpb < 8 || fit8 <= 1) {
-    kern = estep_evo_fused_kernel<T, Model, 12, 1>;  // a single narrow CTA: no reason to cap its registers
+    kern = estep_evo_fused_kernel<T, Model, 16, 1>;  // a single narrow CTA: no reason to cap its registers
   }
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;

@@ -461,7 +461,7 @@ sssc_lpj_kernel(typename SsscModel<T>::Params p, const uint64_t *__restrict__ K,
 // The kernel accumulates szszT, ssT, s, sz, diag_yyT, N, F and writes X = <kappa>_q (B x H) and
 // E = <s>_q (B x H); the three outer-product sums are GEMMs on X, E, Y done by the host wrapper.
 template <typename T>
-__global__ void __launch_bounds__(384)  // up to 12 warps: one CTA per SM at H = 256 (23 kB per warp), see the launcher
+__global__ void __launch_bounds__(512)  // up to 16 warps: one CTA per SM at H = 256 (17 kB per warp), see the launcher
 sssc_mstep_kernel(typename SsscModel<T>::Params p, const int64_t *__restrict__ idx, int64_t row0,
                   const uint64_t *__restrict__ K, int64_t k_stride_n, const T *__restrict__ lpj, int64_t lpj_stride_n,
                   double *__restrict__ stats, double *__restrict__ X_out, double *__restrict__ E_out,
@@ -714,8 +714,8 @@ int sssc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, i
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wbytes * wpb)));
   int occ = 1;
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, wbytes * wpb));
-  if (wpb == 8 && occ <= 1 && wbytes * 9 <= (size_t)227 * 1024) {  // one CTA per SM: as many warps as fit (<= 12)
-    wpb = (int)min((size_t)12, (size_t)227 * 1024 / wbytes);
+  if (wpb == 8 && occ <= 1 && wbytes * 9 <= (size_t)227 * 1024) {  // one CTA per SM: as many warps as fit (<= 16)
+    wpb = (int)min((size_t)16, (size_t)227 * 1024 / wbytes);
     TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wbytes * wpb)));
     occ = 1;
   }
