@@ -15,13 +15,12 @@
 
 namespace tvo {
 
-// Three register / residency tiers, picked by how many 8-warp CTAs the working set allows per SM:
+// Two register / residency tiers, picked by how many 8-warp CTAs the working set allows per SM:
 //   <8, 3>  three or more CTAs of 8 warps (80 registers; NoisyOR);
-//   <8, 2>  two CTAs of 8 warps with 128 registers (SSSC at H = 256: 10.4 kB per warp; its fp64 Cholesky scorer spills
-//           at 80 registers — 17.9 ms against 13.x ms at C3);
-//   <16, 1> one CTA per SM with as many warps as its shared memory holds (up to 16; 14 for SSSC at H = 256).
-// Measured at C3 (E-step per 200k): 8 warps 19.1 ms, 10 warps 14.9, 12 warps 12.6, 14 warps 11.1; two CTAs of 8 warps at
-// 128 registers with a smaller sub-warp scratch (4 units) 15.9.
+//   <16, 1> ONE CTA per SM with as many warps as its shared memory holds (up to 16; 128 registers): SSSC at H = 256.
+// Measured at C3 (E-step per 200k datapoints): 8 warps 19.1 ms, 10 warps 14.9, 12 warps 12.6, 14 warps 11.1; two CTAs
+// of 8 warps at 128 registers were slower than one wide CTA with fewer warps (13.3 ms with 16 warps against 11.1 ms
+// with 14), so there is no two-CTA tier.
 template <typename T, typename Model, int MAXW, int MINB>
 __global__ void __launch_bounds__(32 * MAXW, MINB)
 estep_evo_fused_kernel(typename Model::Params mp, const int64_t *__restrict__ idx, int64_t row0,
@@ -97,14 +96,10 @@ int launch_estep_evo_fused(const typename Model::Params &mp, const int64_t *idx,
   size_t smem = wbytes * wpb;
   auto kern = estep_evo_fused_kernel<T, Model, 8, 3>;
   const size_t fit8 = wpb == 8 ? ((size_t)227 * 1024) / (smem + 1024) : 0;  // 8-warp CTAs per SM by shared memory
-  if (wpb == 8 && fit8 == 2) {
-    kern = estep_evo_fused_kernel<T, Model, 8, 2>;
-  } else if (wpb == 8 && fit8 <= 1 && wbytes * 9 <= (size_t)227 * 1024) {  // one CTA per SM: widen it
-    wpb = (int)min((size_t)16, (size_t)227 * 1024 / wbytes);
+  if (fit8 < 3) {  // fewer than three 8-warp CTAs per SM: ONE wide CTA with as many warps as fit (up to 16)
+    wpb = (int)max((size_t)1, min((size_t)16, (size_t)227 * 1024 / wbytes));
     smem = wbytes * wpb;
     kern = estep_evo_fused_kernel<T, Model, 16, 1>;
-  } else if (wpb < 8 || fit8 <= 1) {
-    kern = estep_evo_fused_kernel<T, Model, 16, 1>;  // a single narrow CTA: no reason to cap its registers
   }
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;

@@ -352,17 +352,19 @@ struct SsscModel {
     unsigned char *big;  // global scratch, one sssc_scratch_bytes(kSsscAB) row per warp of the grid (or nullptr)
     int *overflow;       // set when a state has more active units than can be evaluated
   };
-  __host__ __device__ static size_t smem_bytes(const Params &p) { return (size_t)p.H * 8 + sssc_warp_scratch_bytes(); }
+  // fp64: the a = W^T y row is read where the GEMM left it (global scratch, through L1/L2) — 2 kB per warp less
+  // shared memory, i.e. two more resident warps per SM at H = 256; fp32 keeps a converted fp64 copy in shared memory
+  __host__ __device__ static size_t a_row_bytes(const Params &p) { return sizeof(T) == 8 ? 0 : (size_t)p.H * 8; }
+  __host__ __device__ static size_t smem_bytes(const Params &p) { return a_row_bytes(p) + sssc_warp_scratch_bytes(); }
   struct Ctx {
     double yy;
     bool has_nan;
     const T *y;
-    double *a_sm;
+    const double *a_sm;
     unsigned char *scr;  // the warp's shared scratch
     __device__ void load(const Params &p, int64_t b, unsigned char *smem, int lane) {
       y = p.Y + b * p.ldY;
-      a_sm = (double *)smem;
-      scr = smem + (size_t)p.H * 8;
+      scr = smem + a_row_bytes(p);
       double t = 0.0;
       bool nan = false;
       for (int d = lane; d < p.D; d += 32) {
@@ -372,7 +374,13 @@ struct SsscModel {
       }
       yy = warp_sum(t);
       has_nan = __any_sync(FULL, nan);
-      for (int h = lane; h < p.H; h += 32) a_sm[h] = (double)p.A[b * (int64_t)p.H + h];
+      if (sizeof(T) == 8) {
+        a_sm = reinterpret_cast<const double *>(p.A) + b * (int64_t)p.H;
+      } else {
+        double *a_w = (double *)smem;
+        for (int h = lane; h < p.H; h += 32) a_w[h] = (double)p.A[b * (int64_t)p.H + h];
+        a_sm = a_w;
+      }
     }
     // Evaluate `count` states.  `sink(s, value, n_active, scratch, amax, gl, GS-lane-count, gmask)` is called by
     // every lane of the group that solved state s (want_moments: scratch holds kappa and Lambda + kappa kappa^T).
