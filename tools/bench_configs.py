@@ -31,7 +31,21 @@ def chunks(N, step=65536):
         yield b0, min(N, b0 + step)
 
 
-if cfg == "c5":
+if cfg in ("c2", "c2f32"):
+    # the headline shape through this tool, fp64 and the stated fp32 mode (bench.py is the fp64 measurement of record)
+    N = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+    H, D, S, P, C, G = 256, 144, 64, 16, 2, 2
+    prec = to.float64 if cfg == "c2" else to.float32
+    Wgen = to.randn(D, H, dtype=to.float64, device=dev, generator=g)
+    Y = to.empty(N, D, dtype=prec, device=dev)
+    for b0, b1 in chunks(N):
+        s = (to.rand(b1 - b0, H, device=dev, generator=g) < 5.0 / H).double()
+        Y[b0:b1] = (s @ Wgen.t() + to.randn(b1 - b0, D, dtype=to.float64, device=dev, generator=g)).to(prec)
+    model = BSC(H, D, (Wgen + 0.5 * to.randn(D, H, dtype=to.float64, device=dev, generator=g)).to(prec),
+                to.tensor([1.0], dtype=prec), to.full((H,), 1.0 / H, dtype=prec), precision=prec)
+    states = EVOVariationalStates(N, H, S, prec, "randparents", "sparseflip", P, G, C, bitflip_frequency=1.0 / H, seed=5)
+    name = f"C2 BSC H256 D144 S64 EVO(randparents,sparseflip,P16,C2,G2) {'fp64' if cfg == 'c2' else 'fp32'}"
+elif cfg == "c5":
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
     H, D, S, P, C, G = 1024, 256, 128, 16, 4, 2
     Wgen = to.randn(D, H, dtype=to.float64, device=dev, generator=g)
