@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """Device timing of the EM iteration at the other BASELINE.json configurations:
-C3 SSSC D64 H256 S32, C4 NoisyOR D100 H64 S64 crossover fp32, C5 BSC H1024 D256 S128.
-Development / reporting aid (bench.py stays on the headline workload).
+C3 SSSC D64 H256 S32, C4 NoisyOR D100 H64 S64 crossover fp32, C5 BSC H1024 D256 S128 — plus the headline shape in
+fp64 / the stated fp32 mode (c2, c2f32), the single-cause mixtures (gmm, pmm) and a GaussianTVAE (tvae).
+Development / reporting aid (bench.py stays the measurement of record for the headline workload).
 
-    python tools/bench_configs.py c3|c4|c5 [N] [iters]
-prints one JSON line with E-step / M-step / epoch times (CUDA events, median of the timed iterations).
+    python tools/bench_configs.py c2|c2f32|c3|c4|c5|gmm|pmm|tvae [N] [iters]
+prints one JSON line with E-step / M-step / epoch times (CUDA events, median of the timed iterations);
+TVO_STATE_STATS=1 adds the active-unit histogram of the final K.
 """
 import json
 import os
@@ -125,7 +127,7 @@ elif cfg == "tvae":
     states = EVOVariationalStates(N, H, S, prec, "randparents", "sparseflip", P, G, C, bitflip_frequency=1.0 / H, seed=5)
     name = "GaussianTVAE D144 H1=512 H0=256 S64 EVO(randparents,sparseflip,P16,C2,G2) fp32, batches of 8192"
 else:
-    raise SystemExit("usage: bench_configs.py c3|c4|c5|gmm|pmm|tvae [N] [iters]")
+    raise SystemExit("usage: bench_configs.py c2|c2f32|c3|c4|c5|gmm|pmm|tvae [N] [iters]")
 
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 idx = to.arange(N, device=dev)
