@@ -183,3 +183,35 @@ def test_noisyor_rollback_with_fullem():
     F = [tr.em_step()["train_F"] for _ in range(30)]
     assert np.all(np.isfinite(F))
     assert np.all(np.diff(F) >= -eps)
+
+
+def test_noisyor_mstep_c4_shape_cross_kernel_and_linearity():
+    """BASELINE configs[3] shape (D=100, H=64, S=64), 100k datapoints: every CTA of the fp32 slot-form kernel walks
+    hundreds of datapoints and flushes its shared-memory partial sums more than once.  Its statistics must agree
+    (a) with the fp64 register-stationary kernel on the same inputs (two independent kernels) and (b) with the sum of
+    two calls on the two halves of the data (linearity)."""
+    rng = np.random.default_rng(7)
+    N, H, D, S = 100_000, 64, 100, 64
+    tvo_b200._set_device(to.device(DEV))
+    g = to.Generator(device=DEV).manual_seed(3)
+    W = to.rand(D, H, device=DEV, generator=g, dtype=to.float64) * 0.96 + 0.02
+    pies = to.full((H,), 1.0 / H, dtype=to.float64, device=DEV)
+    Y = (to.rand(N, D, device=DEV, generator=g) < 0.25).to(to.uint8)
+    K = (to.rand(N, S, H, device=DEV, generator=g) < 1.5 / H).to(to.uint8)
+    K[:, 0] = 0
+    res = {}
+    for dtype in (to.float64, to.float32):
+        m = NoisyOR(H, D, W.to(dtype), pies.to(dtype), precision=dtype)
+        st = EVOVariationalStates(N, H, S, dtype, "randparents", "randflip", 2, 1, 1, K_init=K)
+        idx = to.arange(N, device=DEV)
+        st.lpj[:] = m.log_pseudo_joint(Y, st.K)
+        m.update_param_batch(idx, Y, st)
+        res[dtype] = (m.Btilde.double().clone(), m.Ctilde.double().clone(), m.new_pi.double().clone())
+        if dtype == to.float32:
+            m2 = NoisyOR(H, D, W.to(dtype), pies.to(dtype), precision=dtype)
+            m2.update_param_batch(idx[: N // 2], Y[: N // 2], st)
+            m2.update_param_batch(idx[N // 2:], Y[N // 2:], st)
+            for a, b in zip(res[dtype], (m2.Btilde.double(), m2.Ctilde.double(), m2.new_pi.double())):
+                assert to.allclose(a, b, rtol=1e-6, atol=1e-6 * float(a.abs().max()))
+    for a, b in zip(res[to.float64], res[to.float32]):
+        assert to.allclose(a, b, rtol=2e-4, atol=2e-4 * float(a.abs().max()))
