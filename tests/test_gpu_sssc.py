@@ -160,7 +160,7 @@ def test_sssc_fullem_train_increases_F():
 
 
 def test_sssc_dense_states_all_solver_levels_and_overflow():
-    """States with 0..8 active units run in sub-warp groups, 9..16 with the full warp in shared memory,
+    """States with 0..6 active units run in sub-warp groups, 7..16 with the full warp in shared memory,
     17..32 in the warp's global scratch row, more than 32 set the overflow flag (finfo.min, raise at epoch
     end): lpj and the M-step statistics against the oracle for a K that mixes all levels."""
     rng = np.random.default_rng(21)
@@ -203,3 +203,41 @@ def test_sssc_dense_states_all_solver_levels_and_overflow():
     assert np.allclose(got2[mask], want[mask], rtol=1e-9, atol=1e-9 * np.abs(want).max())
     with pytest.raises(RuntimeError):
         m._check_overflow()
+
+
+def test_sssc_c3_shape_properties():
+    """BASELINE configs[2] shape (D=64, H=256, S=32), 20k datapoints: the fused E-step runs as ONE wide CTA per SM
+    (16 warps, several datapoints per warp) and the M-step likewise.  Size-independent properties: the stored lpj
+    equal a stand-alone re-score of the final K, rows are sorted ascending with pairwise distinct states, F does
+    not decrease, and the M-step statistics are additive over the two halves of the data."""
+    tvo_b200._set_device(to.device(DEV))
+    g = to.Generator(device=DEV).manual_seed(11)
+    N, H, D, S = 20_000, 256, 64, 32
+    Wg = to.randn(D, H, dtype=to.float64, device=DEV, generator=g)
+    s = (to.rand(N, H, device=DEV, generator=g) < 4.0 / H).double()
+    z = to.randn(N, H, dtype=to.float64, device=DEV, generator=g)
+    Y = (s * z) @ Wg.t() + (0.1 ** 0.5) * to.randn(N, D, dtype=to.float64, device=DEV, generator=g)
+    mk = lambda: SSSC(H, D, Wg + 0.1 * to.randn(D, H, dtype=to.float64, device=DEV, generator=to.Generator(device=DEV).manual_seed(5)),  # noqa: E731
+                      to.tensor([0.1]), to.zeros(H), to.eye(H), to.full((H,), 4.0 / H), precision=to.float64)
+    m = mk()
+    np.random.seed(0)
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", 8, 1, 4, bitflip_frequency=1.0 / H, seed=5)
+    idx = to.arange(N, device=DEV)
+    st.lpj[:] = m.log_pseudo_joint(Y, st.K)
+    F0 = m.free_energy(idx, Y, st)
+    for _ in range(2):
+        st.update(idx, Y, m)
+    again = m.log_pseudo_joint(Y, st.K)
+    assert to.allclose(st.lpj, again, rtol=1e-9, atol=1e-9 * float(again.abs().max()))
+    assert bool((st.lpj[:, 1:] >= st.lpj[:, :-1]).all())
+    Kp = st._Kp[:2000]
+    same = (Kp[:, :, None, :] == Kp[:, None, :, :]).all(dim=3)
+    assert int(same.sum()) == Kp.shape[0] * S  # only the diagonal: no duplicate states in a row
+    assert m.free_energy(idx, Y, st) >= F0
+    m.update_param_batch(idx, Y, st)
+    full = m._stats.clone()
+    m2 = mk()
+    m2.update_param_batch(idx[: N // 2], Y[: N // 2], st)
+    m2.update_param_batch(idx[N // 2:], Y[N // 2:], st)
+    assert to.allclose(full, m2._stats, rtol=1e-9, atol=1e-9 * float(full.abs().max()))
+    m._check_overflow()
