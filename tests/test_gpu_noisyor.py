@@ -215,3 +215,34 @@ def test_noisyor_mstep_c4_shape_cross_kernel_and_linearity():
                 assert to.allclose(a, b, rtol=1e-6, atol=1e-6 * float(a.abs().max()))
     for a, b in zip(res[to.float64], res[to.float32]):
         assert to.allclose(a, b, rtol=2e-4, atol=2e-4 * float(a.abs().max()))
+
+
+def test_noisyor_estep_c4_shape_properties():
+    """BASELINE configs[3] shape (D=100, H=64, S=64, crossover, fp32), 50k datapoints, several datapoints per warp:
+    stored lpj equal a re-score of the final K, rows are sorted ascending with pairwise distinct states, F does not
+    decrease; the fp32 lpj agree with an fp64 re-score of the same states within the fp32 tolerance."""
+    tvo_b200._set_device(to.device(DEV))
+    g = to.Generator(device=DEV).manual_seed(13)
+    N, H, D, S = 50_000, 64, 100, 64
+    W = to.rand(D, H, device=DEV, generator=g) * 0.9 + 0.05
+    pies = to.full((H,), 2.0 / H, device=DEV)
+    Y = (to.rand(N, D, device=DEV, generator=g) < 0.2).to(to.uint8)
+    m = NoisyOR(H, D, W, pies, precision=to.float32)
+    np.random.seed(1)
+    st = EVOVariationalStates(N, H, S, to.float32, "fitparents_fixed", "randflip", 8, 1, crossover=True, seed=3)
+    idx = to.arange(N, device=DEV)
+    st.lpj[:] = m.log_pseudo_joint(Y, st.K)
+    F0 = m.free_energy(idx, Y, st)
+    for _ in range(2):
+        st.update(idx, Y, m)
+    again = m.log_pseudo_joint(Y, st.K)
+    assert to.equal(st.lpj, again)  # same scorer, same states: bit-identical
+    assert bool((st.lpj[:, 1:] >= st.lpj[:, :-1]).all())
+    Kp = st._Kp[:4000]
+    same = (Kp[:, :, None, :] == Kp[:, None, :, :]).all(dim=3)
+    assert int(same.sum()) == Kp.shape[0] * S
+    assert m.free_energy(idx, Y, st) >= F0
+    m64 = NoisyOR(H, D, W.double(), pies.double(), precision=to.float64)
+    ref = m64.log_pseudo_joint(Y[:5000], st.K[:5000])
+    ok = ref > -1e29
+    assert to.allclose(st.lpj[:5000][ok].double(), ref[ok], rtol=1e-4, atol=1e-4 * float(ref[ok].abs().max()))
