@@ -470,121 +470,107 @@ nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *
 }
 
 // M-step, slot form (fp32 mode).  The (state, active unit) pairs of a datapoint are what the work is made of
-// (S |s| of them, |s| ~ 2-3 of H); the register-stationary kernel above visits them with 8 predicated h per thread
+// (S |s| of them, |s| ~ 1-3 of H); the register-stationary kernel above visits them with 8 predicated h per thread
 // and one h-tile per CTA (ncu at C4: 69.6 k warp instructions per datapoint, barrier the top stall).  Here a CTA of
-// 512 threads holds Btilde / Ctilde for ALL h in shared memory ([h][d], fp32) and is split into 512 / Dpad slots of
-// Dpad threads (thread = slot, column d): slot k owns the units h = k (mod slots), so within a datapoint no two
-// threads ever touch the same accumulator and the updates are plain shared-memory read-modify-writes — no atomics,
-// no predicated-off lanes.  Every kNorFlush datapoints the fp32 partial sums are added to the fp64 statistics in
-// global memory (REDs) and cleared, which bounds the fp32 accumulation error (a few hundred terms per flush).
+// 512 threads holds Btilde / Ctilde for ALL h in shared memory ([h][d], fp32) and is split into slots of Dpad / V
+// threads (thread = slot, columns d .. d + V - 1): slot k owns the units h = k (mod slots), so no two warps ever
+// touch the same accumulator and the updates are plain shared-memory read-modify-writes.
+// Nothing else is shared: every warp computes the 64 softmax weights of the datapoint itself (registers, handed out
+// by shuffle), reads the states straight from global memory (one word per lane, L1) and rebuilds Q_sd for the states
+// it visits from 1 - W (|s| vector loads; Q_sd == 1 - W_dh for the single-unit states that dominate) — so the
+// datapoint loop has NO barrier and the warps drift apart freely (the first slot version staged Q in shared memory
+// behind three barriers per datapoint: ncu showed 6.2 warps per issue slot waiting there).  Every kNorFlush
+// datapoints the fp32 partial sums are added to the fp64 statistics in global memory (REDs) and cleared, which bounds
+// the fp32 accumulation error (a few hundred terms per flush).
+// V = 4 (Dpad >= 128): a slot is ONE warp — 4 consecutive columns per lane, vector loads; V = 1 for narrower D.
 constexpr int kNorFlush = 256;
-// V columns per thread: V = 4 (Dpad >= 128) makes a slot ONE warp — 4 consecutive columns per lane, vector loads of
-// 1 - W, Q and the accumulators — so the per-(state, unit) control work (ballot, shuffle, bit walk) is paid once
-// per 128 columns instead of once per 32, and 16 slots share the units of a datapoint; V = 1 for narrower D.
+constexpr int kNorQR = 4;  // softmax weights per lane: S <= 128
 template <int V>
 __global__ void __launch_bounds__(512, 2)
 nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx,
                       const uint64_t *__restrict__ K, int64_t k_stride_n, const float *__restrict__ lpj,
                       int64_t lpj_stride_n, const float *__restrict__ W1mT, const double *__restrict__ prior_sum,
-                      double *__restrict__ stats, int64_t B, int S, int H, int D, int W64, int Dpad, int q_off, int k_off,
-                      int acc_off) {
+                      double *__restrict__ stats, int64_t B, int S, int H, int D, int W64, int Dpad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int tps = Dpad / V;        // threads per slot (a multiple of 32)
   const int nslots = 512 / tps;    // power of two, <= 16
   const int d = (tid % tps) * V, slot = tid / tps;
-  float *Qsm = (float *)smem_raw;                        // S x Dpad
-  float *q = (float *)(smem_raw + q_off);                // S
-  uint64_t *Ksm = (uint64_t *)(smem_raw + k_off);        // S x W64
-  float *accB = (float *)(smem_raw + acc_off);           // H x Dpad
+  const bool pi_owner = (tid % tps) < 32;  // first warp of the slot keeps its units' share of new_pi
+  float *accB = (float *)smem_raw;                       // H x Dpad
   float *accC = accB + (size_t)H * Dpad;                 // H x Dpad
-  __shared__ double red;
+  float *pi_sm = accC + (size_t)H * Dpad;                // H
   // bits h with h % nslots == slot, replicated over a 64-bit word (64 % nslots == 0)
   uint64_t slotmask = 0;
   for (int h = slot; h < 64; h += nslots) slotmask |= 1ull << h;
-  for (int t = tid; t < 2 * H * Dpad; t += 512) accB[t] = 0.f;
-  double pi_acc = 0.0, accF = 0.0, accN = 0.0;  // pi: thread tid < H owns unit tid (H <= 512)
+  for (int t = tid; t < 2 * H * Dpad + H; t += 512) accB[t] = 0.f;
+  __syncthreads();
+  double accF = 0.0, accN = 0.0;
   const float eps = (float)kNorEps;
   const size_t HD = (size_t)H * D;
   int since_flush = 0;
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
     const int64_t row = idx ? idx[b] : b;
     const float *l = lpj + row * lpj_stride_n;
-    __syncthreads();  // previous datapoint fully consumed
-    for (int t = tid; t < S * W64; t += 512) Ksm[t] = K[row * k_stride_n + t];
+    const uint64_t *Kn = K + row * k_stride_n;
+    // softmax weights (lpj2pjc, _utils.py:182-191): q of state 32 r + lane in qreg[r]
+    float qreg[kNorQR], mx = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < kNorQR; ++r) {
+      qreg[r] = 32 * r + lane < S ? l[32 * r + lane] : -INFINITY;
+      mx = fmaxf(mx, qreg[r]);
+    }
+    mx = warp_max(mx);
+    float se = 0.f;
+#pragma unroll
+    for (int r = 0; r < kNorQR; ++r) {
+      qreg[r] = 32 * r + lane < S ? expf(qreg[r] - mx) : 0.f;
+      se += qreg[r];
+    }
+    se = warp_sum(se);
+    const float inv = 1.f / se;
+#pragma unroll
+    for (int r = 0; r < kNorQR; ++r) qreg[r] *= inv;
+    if (tid == 0) {
+      accF += (double)mx + log((double)se) + *prior_sum;
+      accN += 1.0;
+    }
     float ym1[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) ym1[v] = (d + v < D ? (float)Y[b * ldY + d + v] : 1.f) - 1.f;
-    __syncthreads();
-    if (tid >= 512 - 32) {  // softmax weights (lpj2pjc, _utils.py:182-191) by the LAST warp, which then joins phase 1
-      float mx = -INFINITY;
-      for (int s = lane; s < S; s += 32) mx = fmaxf(mx, l[s]);
-      mx = warp_max(mx);
-      float se = 0.f;
-      for (int s = lane; s < S; s += 32) {
-        const float e = expf(l[s] - mx);
-        q[s] = e;
-        se += e;
-      }
-      se = warp_sum(se);
-      const float inv = 1.f / se;
-      for (int s = lane; s < S; s += 32) q[s] *= inv;
-      if (lane == 0) red = (double)mx + log((double)se);
-    }
-    // phase 1: Q_sd over ALL active h of the state (noisyor.py:123-124), ascending h
-    for (int s = slot; s < S; s += nslots) {
-      const uint64_t *st = Ksm + s * W64;
-      float Q[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) Q[v] = 1.f;
-      for (int w = 0; w < W64; ++w) {
-        uint64_t word = st[w];
-        while (word) {
-          const int h = (w << 6) + __ffsll((long long)word) - 1;
-          word &= word - 1;
-          const float *wr = W1mT + (size_t)h * Dpad + d;
-          if (V == 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(wr));
-            Q[0] *= t.x, Q[V > 1 ? 1 : 0] *= t.y, Q[V > 2 ? 2 : 0] *= t.z, Q[V > 3 ? 3 : 0] *= t.w;
-          } else {
-            Q[0] *= __ldg(wr);
-          }
-        }
-      }
-      if (V == 4)
-        *reinterpret_cast<float4 *>(Qsm + s * Dpad + d) = make_float4(Q[0], Q[V > 1 ? 1 : 0], Q[V > 2 ? 2 : 0], Q[V > 3 ? 3 : 0]);
-      else
-        Qsm[s * Dpad + d] = Q[0];
-    }
-    __syncthreads();
-    if (tid == 0) {
-      accF += red + *prior_sum;
-      accN += 1.0;
-    }
-    if (tid < H) {  // new_pi += <s_h>  (noisyor.py:117)
-      double e = 0.0;
-      for (int s = 0; s < S; ++s)
-        if ((Ksm[s * W64 + (tid >> 6)] >> (tid & 63)) & 1ull) e += (double)q[s];
-      pi_acc += e;
-    }
-    // phase 2: Btilde, Ctilde (noisyor.py:121-132): this slot's units of every state, columns d .. d + V - 1
+    // Btilde, Ctilde (noisyor.py:121-132) and new_pi (:117): this slot's units of every state, columns d .. d + V - 1
     for (int w = 0; w < W64; ++w) {
-      for (int s0 = 0; s0 < S; s0 += 32) {  // 32 states tested at once, one per lane (the slot is warp-uniform)
-        const int sl = s0 + lane;
-        const uint64_t ml = sl < S ? (Ksm[sl * W64 + w] & slotmask) : 0ull;
+#pragma unroll
+      for (int r = 0; r < kNorQR; ++r) {  // 32 states tested at once, one per lane (the slot is warp-uniform)
+        const int s0 = 32 * r, sl = s0 + lane;
+        if (s0 >= S) break;
+        const uint64_t word = sl < S ? __ldg(Kn + (size_t)sl * W64 + w) : 0ull;
+        const uint64_t ml = word & slotmask;
         unsigned act = __ballot_sync(FULL, ml != 0ull);
         while (act) {
           const int src = __ffs((int)act) - 1;
           act &= act - 1;
           uint64_t m = __shfl_sync(FULL, ml, src);
+          const uint64_t full_w = __shfl_sync(FULL, word, src);
           const int s = s0 + src;
-          const float qs = q[s];
+          const float qs = __shfl_sync(FULL, qreg[r], src);
+          // Q_sd over ALL active units of the state, ascending h (noisyor.py:123-124)
           float Q[V], omq[V];
-          if (V == 4) {
-            const float4 t = *reinterpret_cast<const float4 *>(Qsm + s * Dpad + d);
-            Q[0] = t.x, Q[V > 1 ? 1 : 0] = t.y, Q[V > 2 ? 2 : 0] = t.z, Q[V > 3 ? 3 : 0] = t.w;
-          } else {
-            Q[0] = Qsm[s * Dpad + d];
+#pragma unroll
+          for (int v = 0; v < V; ++v) Q[v] = 1.f;
+          for (int w2 = 0; w2 < W64; ++w2) {
+            uint64_t f = w2 == w ? full_w : __ldg(Kn + (size_t)s * W64 + w2);
+            while (f) {
+              const int h2 = (w2 << 6) + __ffsll((long long)f) - 1;
+              f &= f - 1;
+              const float *wr = W1mT + (size_t)h2 * Dpad + d;
+              if (V == 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(wr));
+                Q[0] *= t.x, Q[V > 1 ? 1 : 0] *= t.y, Q[V > 2 ? 2 : 0] *= t.z, Q[V > 3 ? 3 : 0] *= t.w;
+              } else {
+                Q[0] *= __ldg(wr);
+              }
+            }
           }
 #pragma unroll
           for (int v = 0; v < V; ++v) omq[v] = 1.f - Q[v];
@@ -618,11 +604,12 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
               *pb = ab[0];
               *pc = ac[0];
             }
+            if (pi_owner && lane == 0) pi_sm[h] += qs;  // new_pi += <s_h>: this slot is the only writer of unit h
           }
         }
       }
     }
-    if (++since_flush == kNorFlush) {
+    if (++since_flush == kNorFlush || b + gridDim.x >= B) {  // every CTA iteration count is uniform within the CTA
       since_flush = 0;
       __syncthreads();
       for (int t = tid; t < H * Dpad; t += 512) {
@@ -635,18 +622,13 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
         accB[t] = 0.f;
         accC[t] = 0.f;
       }
+      for (int h = tid; h < H; h += 512) {
+        if (pi_sm[h] != 0.f) atomicAdd(stats + 2 * HD + h, (double)pi_sm[h]);
+        pi_sm[h] = 0.f;
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
-  for (int t = tid; t < H * Dpad; t += 512) {
-    const int h = t / Dpad, dd = t - h * Dpad;
-    const float vb = accB[t], vc = accC[t];
-    if (dd < D) {
-      if (vb != 0.f) atomicAdd(stats + (size_t)h * D + dd, (double)vb);
-      if (vc != 0.f) atomicAdd(stats + HD + (size_t)h * D + dd, (double)vc);
-    }
-  }
-  if (tid < H && pi_acc != 0.0) atomicAdd(stats + 2 * HD + tid, pi_acc);
   if (tid == 0 && accN != 0.0) {
     atomicAdd(stats + 2 * HD + H, accN);
     atomicAdd(stats + 2 * HD + H + 1, accF);
@@ -665,10 +647,8 @@ int nor_mstep_slot<float>(const uint8_t *Y, int64_t ldY, const int64_t *idx, con
                           int D, void *stream, bool &done) {
   done = false;
   const int Dpad = nor_dpad(D), W64 = n_words(H);
-  if (!(Dpad <= 256 && 512 % Dpad == 0 && H <= 512)) return TVO_OK;
-  const int q_off = (int)align16((size_t)S * Dpad * 4), k_off = q_off + (int)align16((size_t)S * 4),
-            acc_off = k_off + (int)align16((size_t)S * W64 * 8);
-  const size_t smem = (size_t)acc_off + (size_t)2 * H * Dpad * 4;
+  if (!(Dpad <= 256 && 512 % Dpad == 0 && S <= 32 * kNorQR)) return TVO_OK;
+  const size_t smem = ((size_t)2 * H * Dpad + H) * 4;
   if (smem > 110 * 1024) return TVO_OK;  // two CTAs per SM
   auto kern = Dpad >= 128 ? nor_mstep_slot_kernel<4> : nor_mstep_slot_kernel<1>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -677,7 +657,7 @@ int nor_mstep_slot<float>(const uint8_t *Y, int64_t ldY, const int64_t *idx, con
   const int gx = (int)max((int64_t)1, min(B, (int64_t)sm_count() * max(occ, 1)));
   const NorTheta<float> th = nor_theta_view<float>(ws, H, D);
   kern<<<gx, 512, smem, (cudaStream_t)stream>>>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, th.W1mT, &th.hdr->prior_sum,
-                                                stats, B, S, H, D, W64, Dpad, q_off, k_off, acc_off);
+                                                stats, B, S, H, D, W64, Dpad);
   TVO_AFTER_LAUNCH("noisyor_mstep_slot");
   done = true;
   return TVO_OK;
