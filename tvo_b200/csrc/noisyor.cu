@@ -490,7 +490,8 @@ __global__ void __launch_bounds__(512, 2)
 nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx,
                       const uint64_t *__restrict__ K, int64_t k_stride_n, const float *__restrict__ lpj,
                       int64_t lpj_stride_n, const float *__restrict__ W1mT, const double *__restrict__ prior_sum,
-                      double *__restrict__ stats, int64_t B, int S, int H, int D, int W64, int Dpad) {
+                      const float *__restrict__ prior, double *__restrict__ stats, int64_t B, int S, int H, int D, int W64,
+                      int Dpad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int tps = Dpad / V;        // threads per slot (a multiple of 32)
@@ -500,10 +501,47 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
   float *accB = (float *)smem_raw;                       // H x Dpad
   float *accC = accB + (size_t)H * Dpad;                 // H x Dpad
   float *pi_sm = accC + (size_t)H * Dpad;                // H
-  // bits h with h % nslots == slot, replicated over a 64-bit word (64 % nslots == 0)
-  uint64_t slotmask = 0;
-  for (int h = slot; h < 64; h += nslots) slotmask |= 1ull << h;
+  uint64_t *masks = (uint64_t *)(pi_sm + ((H + 3) & ~3));  // nslots x W64: the units owned by each slot
+  unsigned char *slot_of = (unsigned char *)(masks + (size_t)nslots * W64);  // H
+  // Which slot owns which unit.  No barrier means a slot's warp is as slow as its units are popular, and learned
+  // units are anything but equally popular: h mod nslots left the warps of the rare units idle at the flush barrier.
+  // Longest-processing-time-first on the prior activity pi_h (the model's own estimate of how often unit h is on):
+  // units by descending pi_h, each to the least loaded slot.  Any assignment gives the same sums (one owner per
+  // accumulator, datapoints in the same order), so this only moves work around.
+  if (tid == 0) {
+    float load[16];
+    for (int k = 0; k < nslots; ++k) load[k] = 0.f;
+    for (int h = 0; h < H; ++h) slot_of[h] = 255;
+    if (H <= 256) {
+      for (int it = 0; it < H; ++it) {
+        int best = -1;
+        float bp = -INFINITY;
+        for (int h = 0; h < H; ++h) {
+          const float ph = __ldg(prior + h);  // log-odds: monotone in pi_h
+          if (slot_of[h] == 255 && ph > bp) {
+            bp = ph;
+            best = h;
+          }
+        }
+        int ks = 0;
+        for (int k = 1; k < nslots; ++k)
+          if (load[k] < load[ks]) ks = k;
+        slot_of[best] = (unsigned char)ks;
+        load[ks] += 1.f / (1.f + expf(-bp)) + 1e-3f;
+      }
+    } else {
+      for (int h = 0; h < H; ++h) slot_of[h] = (unsigned char)(h % nslots);
+    }
+  }
   for (int t = tid; t < 2 * H * Dpad + H; t += 512) accB[t] = 0.f;
+  __syncthreads();
+  for (int t = tid; t < nslots * W64; t += 512) {
+    const int k = t / W64, w = t - k * W64;
+    uint64_t mk = 0;
+    for (int j = 0; j < 64 && (w << 6) + j < H; ++j)
+      if (slot_of[(w << 6) + j] == k) mk |= 1ull << j;
+    masks[t] = mk;
+  }
   __syncthreads();
   double accF = 0.0, accN = 0.0;
   const float eps = (float)kNorEps;
@@ -540,6 +578,7 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
     for (int v = 0; v < V; ++v) ym1[v] = (d + v < D ? (float)Y[b * ldY + d + v] : 1.f) - 1.f;
     // Btilde, Ctilde (noisyor.py:121-132) and new_pi (:117): this slot's units of every state, columns d .. d + V - 1
     for (int w = 0; w < W64; ++w) {
+      const uint64_t slotmask = masks[slot * W64 + w];
 #pragma unroll
       for (int r = 0; r < kNorQR; ++r) {  // 32 states tested at once, one per lane (the slot is warp-uniform)
         const int s0 = 32 * r, sl = s0 + lane;
@@ -648,7 +687,8 @@ int nor_mstep_slot<float>(const uint8_t *Y, int64_t ldY, const int64_t *idx, con
   done = false;
   const int Dpad = nor_dpad(D), W64 = n_words(H);
   if (!(Dpad <= 256 && 512 % Dpad == 0 && S <= 32 * kNorQR)) return TVO_OK;
-  const size_t smem = ((size_t)2 * H * Dpad + H) * 4;
+  const int nslots_h = 512 / (Dpad >= 128 ? Dpad / 4 : Dpad);
+  const size_t smem = ((size_t)2 * H * Dpad + ((H + 3) & ~3)) * 4 + (size_t)nslots_h * W64 * 8 + ((H + 15) & ~15);
   if (smem > 110 * 1024) return TVO_OK;  // two CTAs per SM
   auto kern = Dpad >= 128 ? nor_mstep_slot_kernel<4> : nor_mstep_slot_kernel<1>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -657,7 +697,7 @@ int nor_mstep_slot<float>(const uint8_t *Y, int64_t ldY, const int64_t *idx, con
   const int gx = (int)max((int64_t)1, min(B, (int64_t)sm_count() * max(occ, 1)));
   const NorTheta<float> th = nor_theta_view<float>(ws, H, D);
   kern<<<gx, 512, smem, (cudaStream_t)stream>>>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, th.W1mT, &th.hdr->prior_sum,
-                                                stats, B, S, H, D, W64, Dpad);
+                                                th.prior, stats, B, S, H, D, W64, Dpad);
   TVO_AFTER_LAUNCH("noisyor_mstep_slot");
   done = true;
   return TVO_OK;
