@@ -483,7 +483,7 @@ nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *
 // datapoints the fp32 partial sums are added to the fp64 statistics in global memory (REDs) and cleared, which bounds
 // the fp32 accumulation error (a few hundred terms per flush).
 // V = 4 (Dpad >= 128): a slot is ONE warp — 4 consecutive columns per lane, vector loads; V = 1 for narrower D.
-constexpr int kNorFlush = 256;
+constexpr int kNorFlush = 256;  // datapoints per CTA between flushes (1024 measured the same: the wait at the flush barrier is the slowest slot, not the flush)
 constexpr int kNorQR = 4;  // softmax weights per lane: S <= 128
 template <int V>
 __global__ void __launch_bounds__(512, 2)
@@ -508,6 +508,8 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
   // Longest-processing-time-first on the prior activity pi_h (the model's own estimate of how often unit h is on):
   // units by descending pi_h, each to the least loaded slot.  Any assignment gives the same sums (one owner per
   // accumulator, datapoints in the same order), so this only moves work around.
+  for (int h = tid; h < H; h += 512) pi_sm[h] = __ldg(prior + h);  // staged: the greedy pass below is one thread
+  __syncthreads();
   if (tid == 0) {
     float load[16];
     for (int k = 0; k < nslots; ++k) load[k] = 0.f;
@@ -517,7 +519,7 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
         int best = -1;
         float bp = -INFINITY;
         for (int h = 0; h < H; ++h) {
-          const float ph = __ldg(prior + h);  // log-odds: monotone in pi_h
+          const float ph = pi_sm[h];  // log-odds: monotone in pi_h
           if (slot_of[h] == 255 && ph > bp) {
             bp = ph;
             best = h;
@@ -533,8 +535,8 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
       for (int h = 0; h < H; ++h) slot_of[h] = (unsigned char)(h % nslots);
     }
   }
-  for (int t = tid; t < 2 * H * Dpad + H; t += 512) accB[t] = 0.f;
   __syncthreads();
+  for (int t = tid; t < 2 * H * Dpad + H; t += 512) accB[t] = 0.f;
   for (int t = tid; t < nslots * W64; t += 512) {
     const int k = t / W64, w = t - k * W64;
     uint64_t mk = 0;
