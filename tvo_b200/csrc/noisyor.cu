@@ -485,13 +485,40 @@ nor_mstep_reg_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *
 // V = 4 (Dpad >= 128): a slot is ONE warp — 4 consecutive columns per lane, vector loads; V = 1 for narrower D.
 constexpr int kNorFlush = 256;  // datapoints per CTA between flushes (1024 measured the same: the wait at the flush barrier is the slowest slot, not the flush)
 constexpr int kNorQR = 4;  // softmax weights per lane: S <= 128
+constexpr int kNorCountSample = 8192;  // datapoints whose states are counted to balance the slots
+
+// counts[h] += number of states (of the first B datapoints of this call) that contain unit h: the work a slot gets per
+// unit is exactly this number, so the slot kernel deals the units out by it.
+__global__ void __launch_bounds__(256)
+nor_unit_counts_kernel(const uint64_t *__restrict__ K, int64_t k_stride_n, const int64_t *__restrict__ idx, int64_t B,
+                       int S, int W64, int H, unsigned *__restrict__ counts) {
+  extern __shared__ unsigned hist[];
+  for (int h = threadIdx.x; h < H; h += blockDim.x) hist[h] = 0;
+  __syncthreads();
+  const int64_t nwords = B * S * W64;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nwords; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / ((int64_t)S * W64);
+    const int r = (int)(t - b * (int64_t)S * W64);
+    const int64_t row = idx ? idx[b] : b;
+    uint64_t m = K[row * k_stride_n + r];
+    const int w = r % W64;
+    while (m) {
+      const int h = (w << 6) + __ffsll((long long)m) - 1;
+      m &= m - 1;
+      atomicAdd(&hist[h], 1u);
+    }
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x)
+    if (hist[h]) atomicAdd(counts + h, hist[h]);
+}
 template <int V>
 __global__ void __launch_bounds__(512, 2)
 nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx,
                       const uint64_t *__restrict__ K, int64_t k_stride_n, const float *__restrict__ lpj,
                       int64_t lpj_stride_n, const float *__restrict__ W1mT, const double *__restrict__ prior_sum,
-                      const float *__restrict__ prior, double *__restrict__ stats, int64_t B, int S, int H, int D, int W64,
-                      int Dpad) {
+                      const unsigned *__restrict__ counts, double *__restrict__ stats, int64_t B, int S, int H, int D,
+                      int W64, int Dpad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int tps = Dpad / V;        // threads per slot (a multiple of 32)
@@ -505,10 +532,11 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
   unsigned char *slot_of = (unsigned char *)(masks + (size_t)nslots * W64);  // H
   // Which slot owns which unit.  No barrier means a slot's warp is as slow as its units are popular, and learned
   // units are anything but equally popular: h mod nslots left the warps of the rare units idle at the flush barrier.
-  // Longest-processing-time-first on the prior activity pi_h (the model's own estimate of how often unit h is on):
-  // units by descending pi_h, each to the least loaded slot.  Any assignment gives the same sums (one owner per
+  // Longest-processing-time-first on the number of states that contain each unit (counted over a sample of the
+  // datapoints by nor_unit_counts_kernel — the per-unit work is exactly that number; the prior pi_h predicted it
+  // poorly): units by descending count, each to the least loaded slot.  Any assignment gives the same sums (one owner per
   // accumulator, datapoints in the same order), so this only moves work around.
-  for (int h = tid; h < H; h += 512) pi_sm[h] = __ldg(prior + h);  // staged: the greedy pass below is one thread
+  for (int h = tid; h < H; h += 512) pi_sm[h] = (float)__ldg(counts + h);  // staged: the greedy pass is one thread
   __syncthreads();
   if (tid == 0) {
     float load[16];
@@ -519,7 +547,7 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
         int best = -1;
         float bp = -INFINITY;
         for (int h = 0; h < H; ++h) {
-          const float ph = pi_sm[h];  // log-odds: monotone in pi_h
+          const float ph = pi_sm[h];
           if (slot_of[h] == 255 && ph > bp) {
             bp = ph;
             best = h;
@@ -529,7 +557,7 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
         for (int k = 1; k < nslots; ++k)
           if (load[k] < load[ks]) ks = k;
         slot_of[best] = (unsigned char)ks;
-        load[ks] += 1.f / (1.f + expf(-bp)) + 1e-3f;
+        load[ks] += bp + 1.f;
       }
     } else {
       for (int h = 0; h < H; ++h) slot_of[h] = (unsigned char)(h % nslots);
@@ -676,6 +704,24 @@ nor_mstep_slot_kernel(const uint8_t *__restrict__ Y, int64_t ldY, const int64_t 
   }
 }
 
+// per-device buffer of unit counts (part of the per-device context, grown on demand and kept)
+static unsigned *g_nor_counts[64];
+static int g_nor_counts_len[64];
+static int nor_counts_buffer(int H, unsigned **out) {
+  int dev = 0;
+  TVO_CUDA(cudaGetDevice(&dev));
+  TVO_REQUIRE(dev >= 0 && dev < 64, "noisyor counts buffer: device index %d out of range", dev);
+  if (g_nor_counts_len[dev] < H) {
+    if (g_nor_counts[dev]) TVO_CUDA(cudaFree(g_nor_counts[dev]));
+    g_nor_counts[dev] = nullptr;
+    g_nor_counts_len[dev] = 0;
+    TVO_CUDA(cudaMalloc((void **)&g_nor_counts[dev], (size_t)H * sizeof(unsigned)));
+    g_nor_counts_len[dev] = H;
+  }
+  *out = g_nor_counts[dev];
+  return TVO_OK;
+}
+
 template <typename T>
 static int nor_mstep_slot(const uint8_t *, int64_t, const int64_t *, const uint64_t *, int64_t, const T *, int64_t,
                           const void *, double *, int64_t, int, int, int, void *, bool &done) {
@@ -698,8 +744,18 @@ int nor_mstep_slot<float>(const uint8_t *Y, int64_t ldY, const int64_t *idx, con
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 512, smem));
   const int gx = (int)max((int64_t)1, min(B, (int64_t)sm_count() * max(occ, 1)));
   const NorTheta<float> th = nor_theta_view<float>(ws, H, D);
+  unsigned *counts = nullptr;
+  {
+    int rc = nor_counts_buffer(H, &counts);
+    if (rc) return rc;
+  }
+  TVO_CUDA(cudaMemsetAsync(counts, 0, (size_t)H * sizeof(unsigned), (cudaStream_t)stream));
+  const int64_t Bs = min(B, (int64_t)kNorCountSample);
+  nor_unit_counts_kernel<<<(int)min((Bs * S * W64 + 255) / 256, (int64_t)sm_count() * 4), 256, (size_t)H * 4,
+                           (cudaStream_t)stream>>>(K, k_stride_n, idx, Bs, S, W64, H, counts);
+  TVO_AFTER_LAUNCH("noisyor_unit_counts");
   kern<<<gx, 512, smem, (cudaStream_t)stream>>>(Y, ldY, idx, K, k_stride_n, lpj, lpj_stride_n, th.W1mT, &th.hdr->prior_sum,
-                                                th.prior, stats, B, S, H, D, W64, Dpad);
+                                                counts, stats, B, S, H, D, W64, Dpad);
   TVO_AFTER_LAUNCH("noisyor_mstep_slot");
   done = true;
   return TVO_OK;
