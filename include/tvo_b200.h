@@ -169,6 +169,10 @@ int tvo_select_topS_f32(const uint64_t *new_states, const float *new_lpj, uint64
  *      TVO_SEL_FITPARENTS (batch-global normaliser) is not available fused: use the stand-alone
  *      kernels. ---- */
 int64_t tvo_bsc_estep_scratch_bytes(int64_t B, int32_t H, int32_t is_f64);
+/* Sparse states at 64 <= H <= 256 with randparents + sparseflip run the list-based kernel (states held as
+ * sorted position lists, children scored incrementally); datapoints it cannot hold and all other shapes run
+ * the generic kernel.  Both produce the same K.  generic_only != 0 disables the list-based kernel (tests). */
+int tvo_bsc_estep_variant(int32_t generic_only);
 int tvo_estep_evo_bsc_f64(const double *Y, int64_t ldY, const int64_t *idx, uint64_t *K, double *lpj,
                           const void *theta_ws, const tvo_evo_config *cfg, const double *sparsity, void *scratch,
                           int64_t scratch_bytes, int64_t B, int32_t S, int32_t H, int32_t D, int64_t *nsubs,

@@ -1,0 +1,133 @@
+"""GPU parity tests of the list-based fused BSC E-step (csrc/bsc_estep_v2.cuh): against the CPU oracle, against the
+generic kernel (tvo_bsc_estep_variant(1)) and through its overflow hand-back (dense states, NaN rows, many flips).
+
+Bars as everywhere: K / nsubs bit-exact, lpj 1e-10 relative (fp64)."""
+import numpy as np
+import pytest
+import torch as to
+
+pytestmark = pytest.mark.gpu
+
+cuda = to.cuda.is_available()
+if cuda:
+    import tvo_b200
+    from tvo_b200 import _lib
+    from tvo_b200.models import BSC
+    from tvo_b200.variational import EVOVariationalStates
+
+from oracle import evo as oevo
+from oracle import models as om
+from oracle import states as ost
+
+DEV = "cuda:0"
+
+
+def dev(a, dtype=None):
+    t = to.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def rand_K(rng, N, S, H, p):
+    K = np.zeros((N, S, H), np.uint8)
+    for n in range(N):
+        seen = {}
+        while len(seen) < S:
+            s = (rng.random(H) < p).astype(np.uint8)
+            seen.setdefault(s.tobytes(), s)
+        K[n] = list(seen.values())
+    return K
+
+
+def oracle_estep(o, Y, K, P, Cn, G, p_bf, n_glob, seed, step, sparsity):
+    lpj = o.log_pseudo_joint(Y, K)
+    new_s, new_l = oevo.evolve_states(lpj, K, lambda s: o.log_pseudo_joint(Y, s), P, Cn, G, "randparents", "sparseflip",
+                                      sparsity, p_bf, n_glob, seed, step)
+    Kc, lc = K.copy(), lpj.copy()
+    nsubs = ost.update_states_for_batch(new_s, new_l, np.arange(len(K)), Kc, lc)
+    return Kc, lc, nsubs
+
+
+def make(rng, N, H, D, S, p_state, pies_val, dense_rows=(), nan_rows=()):
+    W = rng.standard_normal((D, H))
+    pies = np.full(H, pies_val)
+    Y = (rng.random((N, H)) < pies) @ W.T + rng.standard_normal((N, D))
+    K = rand_K(rng, N, S, H, p_state)
+    for n in dense_rows:  # one state with more than 15 active units: the list cannot hold it
+        K[n, n % S] = 0
+        K[n, n % S, rng.choice(H, 17 + (n % 5), replace=False)] = 1
+    for n in nan_rows:
+        Y[n, n % D] = np.nan
+    return W, pies, Y, K
+
+
+@pytest.mark.parametrize("H,D,S,P,Cn,G,pbf_mult", [
+    (256, 144, 64, 16, 2, 2, 1.0),   # BASELINE configs[1]
+    (64, 20, 10, 4, 3, 2, 2.0),      # one word, smallest H of the fast path
+    (100, 33, 33, 7, 2, 3, 1.5),     # two words, S not a multiple of 32, three generations
+    (130, 30, 100, 20, 3, 2, 1.5),   # three words, S' = 120
+    (200, 16, 128, 32, 4, 1, 1.0),   # S = S' = 128 (EPL 4)
+    (256, 40, 17, 5, 7, 2, 6.0),     # many flips per child: more than 8 added units happen -> overflow hand-back
+])
+def test_v2_matches_oracle_and_generic(H, D, S, P, Cn, G, pbf_mult):
+    rng = np.random.default_rng(H * 7 + S)
+    N = 40
+    dense_rows, nan_rows = (3, 17), (5, 17, 39)
+    W, pies, Y, K = make(rng, N, H, D, S, min(0.3, 3.0 / H), min(0.3, 3.0 / H), dense_rows, nan_rows)
+    p_bf = pbf_mult / H
+    tvo_b200._set_device(to.device(DEV))
+    outs = {}
+    for variant in (0, 1):
+        _lib.call("tvo_bsc_estep_variant", variant)
+        try:
+            m = BSC(H, D, dev(W), to.tensor([1.2], dtype=to.float64), dev(pies), precision=to.float64)
+            st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", P, G, Cn, bitflip_frequency=p_bf,
+                                      seed=31, K_init=dev(K))
+            st.n_offset = 1000
+            res = []
+            for step in range(3):
+                nsubs = st.update(to.arange(N, device=DEV), dev(Y), m)
+                res.append((st.K.unpack().cpu().numpy(), st.lpj.cpu().numpy().copy(), nsubs))
+            outs[variant] = (res, float(m._tvo_sparsity().item()))
+        finally:
+            _lib.call("tvo_bsc_estep_variant", 0)
+    # list-based == generic, step by step (K, order, nsubs exactly; lpj to rounding)
+    for (Ka, la, na), (Kb, lb, nb) in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(Ka, Kb)
+        assert na == nb
+        ok = ~np.isnan(la)
+        assert np.array_equal(np.isnan(la), np.isnan(lb))
+        assert np.allclose(la[ok], lb[ok], rtol=1e-12, atol=1e-10)
+    # == oracle on the rows without NaN (the oracle's nansum rows are covered by test_gpu_bsc_path)
+    good = np.array([n for n in range(N) if n not in nan_rows])
+    o = om.BSC(H, D, W, [1.2], pies)
+    Kw = K[good]
+    for step in range(3):
+        Kw, Lw, _ = oracle_estep(o, Y[good], Kw, P, Cn, G, p_bf, 1000 + good, 31, step, outs[0][1])
+        Kg, lg, _ = outs[0][0][step]
+        assert np.array_equal(Kg[good], Kw), f"K differs from the oracle at step {step}"
+        assert np.allclose(lg[good], Lw, rtol=1e-10, atol=1e-10)
+
+
+def test_v2_incremental_lpj_equals_full_rescore():
+    """Children are scored as parent + flipped terms; the stored lpj must equal a full re-score of the stored
+    state (to 1e-12)."""
+    rng = np.random.default_rng(4)
+    N, H, D, S = 4000, 256, 144, 64
+    W, pies, Y, K = make(rng, 64, H, D, S, 5.0 / H, 5.0 / H)
+    Y = np.tile(Y, (N // 64 + 1, 1))[:N] + 0.01 * rng.standard_normal((N, D))
+    K = np.tile(K, (N // 64 + 1, 1, 1))[:N]
+    tvo_b200._set_device(to.device(DEV))
+    m = BSC(H, D, dev(W), to.tensor([1.0], dtype=to.float64), dev(pies), precision=to.float64)
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", 16, 2, 2, bitflip_frequency=1.0 / H,
+                              seed=5, K_init=dev(K))
+    idx = to.arange(N, device=DEV)
+    Yd = dev(Y)
+    for it in range(4):
+        nsubs = st.update(idx, Yd, m)
+        assert nsubs > 0
+        full = m._tvo_lpj_packed(Yd, st._Kp, H)
+        rel = ((full - st.lpj).abs() / full.abs().clamp_min(1.0)).max().item()
+        assert rel < 1e-12, rel
+        assert bool((st.lpj[:, 1:] >= st.lpj[:, :-1]).all())
+        rows = to.cat([idx[:, None, None].expand(-1, S, 1), st._Kp], dim=2).reshape(N * S, -1)
+        assert to.unique(rows, dim=0).shape[0] == N * S  # no duplicate state inside any K_n

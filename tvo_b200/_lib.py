@@ -52,6 +52,7 @@ _PROTOS = {
     "tvo_bsc_stats_len": [_I32, _I32],
     "tvo_bsc_estep_scratch_bytes": [_I64, _I32, _I32],
     "tvo_bsc_mstep_scratch_bytes": [_I64, _I32, _I32, _I32],
+    "tvo_bsc_estep_variant": [_I32],
     "tvo_random_states": [_P, _P, _I64, _I32, _I32, _F64, _U64, _U32, _U32, _P],
     "tvo_noisyor_theta_ws_bytes": [_I32, _I32, _I32],
     "tvo_noisyor_stats_len": [_I32, _I32],

@@ -26,9 +26,19 @@ template <typename T>
 __host__ __device__ inline size_t bsc_gram_off(int H, int D) {
   return align16(bsc_wt_off<T>(H) + (size_t)H * bsc_dpad(D) * sizeof(T));
 }
+// G2 = 2 coef G (H x H fp64) and gp_h = coef G_hh + prior_h (H fp64): the list-based fused E-step (bsc_estep_v2.cuh)
+// evaluates  lpj = coef ||y||^2 + sum_{h in s} (gp_h - 2 coef a_h) + sum_{h<h' in s} G2_hh'
+template <typename T>
+__host__ __device__ inline size_t bsc_gram2_off(int H, int D) {
+  return bsc_gram_off<T>(H, D) + (size_t)H * H * sizeof(double);
+}
+template <typename T>
+__host__ __device__ inline size_t bsc_gp_off(int H, int D) {
+  return bsc_gram2_off<T>(H, D) + (size_t)H * H * sizeof(double);
+}
 template <typename T>
 __host__ __device__ inline size_t bsc_ws_bytes(int H, int D) {
-  return bsc_gram_off<T>(H, D) + (size_t)H * H * sizeof(double);
+  return bsc_gp_off<T>(H, D) + align16((size_t)H * sizeof(double));
 }
 
 template <typename T>
@@ -37,6 +47,8 @@ struct BscTheta {
   const T *prior;  // H
   const T *Wt;     // H x Dpad, zero padded
   const double *G; // H x H Gram matrix W^T W (fp64)
+  const double *G2;  // 2 coef G
+  const double *gp;  // coef G_hh + prior_h
   int Dpad;
 };
 template <typename T>
@@ -47,6 +59,8 @@ __host__ __device__ inline BscTheta<T> bsc_theta_view(const void *ws, int H, int
   t.prior = (const T *)(p + bsc_prior_off<T>());
   t.Wt = (const T *)(p + bsc_wt_off<T>(H));
   t.G = (const double *)(p + bsc_gram_off<T>(H, D));
+  t.G2 = (const double *)(p + bsc_gram2_off<T>(H, D));
+  t.gp = (const double *)(p + bsc_gp_off<T>(H, D));
   t.Dpad = bsc_dpad(D);
   return t;
 }
@@ -71,11 +85,19 @@ __global__ void bsc_prepare_kernel(const T *__restrict__ W, const T *__restrict_
   }
   // G = W^T W in fp64 (read straight from W so that it does not depend on Wt being complete)
   double *G = (double *)(p + bsc_gram_off<T>(H, D));
+  double *G2 = (double *)(p + bsc_gram2_off<T>(H, D));
+  double *gp = (double *)(p + bsc_gp_off<T>(H, D));
+  const double coef_d = (double)(T(-0.5) / sigma2[0]);  // == hdr->coef
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)H * H; i += (size_t)gridDim.x * blockDim.x) {
     const int h1 = (int)(i / H), h2 = (int)(i % H);
     double acc = 0.0;
     for (int d = 0; d < D; ++d) acc += (double)W[(size_t)d * H + h1] * (double)W[(size_t)d * H + h2];
     G[i] = acc;
+    G2[i] = 2.0 * coef_d * acc;
+    if (h1 == h2) {
+      const T pi = pies[n_pies == 1 ? 0 : h1];
+      gp[h1] = coef_d * acc + (double)log(pi / (T(1) - pi));  // the same expression as prior[h1] above
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < 32) {
     double s = 0.0;

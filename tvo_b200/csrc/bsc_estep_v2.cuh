@@ -1,0 +1,518 @@
+// tvo_b200 — list-based fused EVO E-step for BSC (EVOVariationalStates.update, evo.py:80-115): the fast path for
+// sparse states, 64 <= H <= 256, randparents + sparseflip.
+//
+// TVO states are sparse bit vectors (|s| ~ 1-6 of H).  Inside this kernel a state is not a bit row but a SORTED
+// POSITION LIST: 15 ascending one-byte positions + the count in byte 15 = one uint4 (`PosList`).  With that
+// representation
+//   * the old states are turned into lists once (one lane per state, one find-first-set walk) and scored in the same
+//     walk:  lpj = coef ||y||^2 + sum_{h in s} (gp_h - 2 coef a_h) + sum_{h<h' in s} G2_hh'   (bsc.py:100-119 in Gram
+//     form; a = W^T y from the chunk GEMM, gp / G2 from the theta workspace);
+//   * a sparseflip child is (parent list, removed entries, added positions): the mutation draws positions, so no bit
+//     row is ever searched, and the child's lpj is the parent's plus the flipped terms
+//         lpj(s') = lpj(s) - sum_{h in R} d_h - sum_{h in R, j in K} G2_hj - sum_{{h,h'} in R} G2_hh'
+//                          + sum_{z in A} d_z + sum_{z in A, j in K} G2_zj + sum_{{z,z'} in A} G2_zz'
+//     (R removed, A added, K kept units, d_h = gp_h - 2 coef a_h) — |R u A| (|K| + 1) gathers instead of |s'|^2 / 2;
+//   * duplicates are list-equal (canonical: ascending, zero padded), the dedup hash is three multiplies;
+//   * bit rows are rebuilt only for the S states that are written back.
+// Same random stream, same draws and the same results as the generic kernel (estep_device.cuh) and the oracle:
+// candidate selection, flip counts, rejection order and the n-th-remaining rule are restated on lists.
+//
+// Datapoints the lists cannot hold — a state with more than 15 active units, more than 8 added units in one child,
+// a NaN in y (nansum form), the (practically unreachable) rejection cap — are appended to an overflow list and
+// processed by the generic kernel in a second launch; nothing has been written for them.
+#pragma once
+#include "bsc_device.cuh"
+
+namespace tvo {
+
+constexpr int kV2MaxList = 15;  // positions per list
+constexpr int kV2MaxAdd = 8;    // added units per child (sorted bytes in one 64-bit register)
+
+struct V2Dims {
+  int S, Snew, Sgen, P, C, G, W64, H;
+};
+
+__host__ __device__ inline size_t v2_warp_bytes(const V2Dims &d) {
+  const int nI = d.P > d.S ? d.P : d.S;
+  return (size_t)(d.S + d.Snew) * 16 + align16((size_t)(d.S + d.Snew) * 8) + align16((size_t)hash_len(d.S, d.Snew) * 4) +
+         align16((size_t)nI * 4);
+}
+
+__host__ inline bool v2_supported(const EvoParams &ep, const V2Dims &d) {
+  return ep.sel == TVO_SEL_RANDPARENTS && ep.mut == TVO_MUT_SPARSEFLIP && ep.flip_tab != nullptr && d.H >= 64 &&
+         d.H <= 256 && d.S <= 128 && d.Sgen <= 128 && d.Snew <= 128;
+}
+
+// ---- position lists ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pl_get(const uint4 &l, uint32_t i) {  // i < 15
+  const bool hi = (i & 8u) != 0;
+  return __byte_perm(hi ? l.z : l.x, hi ? l.w : l.y, i & 7u) & 0xFFu;
+}
+__device__ __forceinline__ bool pl_equal(const uint4 &a, const uint4 &b) {
+  return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) == 0u;
+}
+__device__ __forceinline__ uint32_t pl_hash(const uint4 &l) {
+  uint32_t h = (l.x * 0x9E3779B1u) ^ (l.y * 0x85EBCA77u) ^ (l.z * 0xC2B2AE3Du) ^ (l.w * 0x27D4EB2Fu);
+  h ^= h >> 15;
+  return h | 1u;  // odd: the zero padding of the hash runs never matches
+}
+
+// ---- dedup (same scan as mark_redundant_cpl, states compared as lists) ------------------------------------------
+template <typename T, int CPL>
+__device__ __forceinline__ void v2_mark_redundant_cpl(const uint4 *lists, double *lpjs, const uint32_t *hash, int S,
+                                                      int Snew, int lane) {
+  const int Sp = hash_old_pad(S), Snp = (Snew + 3) & ~3;
+  const uint32_t *ho = hash, *hn = hash + Sp;
+#pragma unroll 1
+  for (int c0 = 0; c0 < Snew; c0 += 32 * CPL) {
+    uint32_t hc[CPL];
+    int hit[CPL];
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+      const int c = c0 + 32 * t + lane;
+      hc[t] = c < Snew ? hn[c] : 0u;
+      hit[t] = -1;
+    }
+#pragma unroll 2
+    for (int j = 0; j < Sp; j += 4) {
+      const uint4 h4 = *reinterpret_cast<const uint4 *>(ho + j);
+#pragma unroll
+      for (int t = 0; t < CPL; ++t) {
+        if (h4.x == hc[t]) hit[t] = j;
+        if (h4.y == hc[t]) hit[t] = j + 1;
+        if (h4.z == hc[t]) hit[t] = j + 2;
+        if (h4.w == hc[t]) hit[t] = j + 3;
+      }
+    }
+#pragma unroll
+    for (int g = 1; g < CPL; ++g) {  // children of later 32-groups of this sweep
+      const int jb = c0 + 32 * g, je = min(jb + 32, Snp);
+      for (int j = jb; j < je; j += 4) {
+        const uint4 h4 = *reinterpret_cast<const uint4 *>(hn + j);
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) {
+          if (t < g) {
+            if (h4.x == hc[t]) hit[t] = S + j;
+            if (h4.y == hc[t]) hit[t] = S + j + 1;
+            if (h4.z == hc[t]) hit[t] = S + j + 2;
+            if (h4.w == hc[t]) hit[t] = S + j + 3;
+          }
+        }
+      }
+    }
+    for (int j = c0 + 32 * CPL; j < Snp; j += 4) {  // children of later sweeps
+      const uint4 h4 = *reinterpret_cast<const uint4 *>(hn + j);
+#pragma unroll
+      for (int t = 0; t < CPL; ++t) {
+        if (h4.x == hc[t]) hit[t] = S + j;
+        if (h4.y == hc[t]) hit[t] = S + j + 1;
+        if (h4.z == hc[t]) hit[t] = S + j + 2;
+        if (h4.w == hc[t]) hit[t] = S + j + 3;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {  // later children of the same 32-group
+      const unsigned later = __match_any_sync(FULL, hc[t]) & ~((2u << lane) - 1u);
+      if (later && hc[t]) hit[t] = S + c0 + 32 * t + __ffs(later) - 1;
+    }
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+      const int c = c0 + 32 * t + lane;
+      if (c < Snew && hit[t] >= 0) {
+        const uint4 mine = lists[S + c];
+        bool dup = pl_equal(lists[hit[t]], mine);
+        if (!dup) {  // hash collision: exhaustive rescan (practically never)
+          for (int j2 = 0; j2 < S && !dup; ++j2)
+            if (ho[j2] == hc[t]) dup = pl_equal(lists[j2], mine);
+          for (int j2 = c + 1; j2 < Snew && !dup; ++j2)
+            if (hn[j2] == hc[t]) dup = pl_equal(lists[S + j2], mine);
+        }
+        if (dup) lpjs[S + c] = (double)LowLpj<T>::v();
+      }
+    }
+  }
+}
+
+// ---- top-S merge (select_merge of estep_device.cuh with the keys taken from the fp64 lpj row) -------------------
+template <typename T>
+__device__ __forceinline__ uint64_t v2_key(const double *lpjs, int i) {
+  return sort_key((double)(T)lpjs[i]);  // ordered by the value that is stored (T), like the generic kernel
+}
+
+template <typename T, int EPL>
+__device__ __forceinline__ void v2_sort_survivors(const double *lpjs, int32_t *slist, int ns, int lane) {
+  uint64_t key[EPL];
+  int src[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    src[r] = e < ns ? slist[e] : kPadSrc;
+    key[r] = e < ns ? v2_key<T>(lpjs, src[r]) : 0ull;
+  }
+  __syncwarp();
+  bitonic_network<EPL>(key, src, lane, 2);
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    if (e < ns) slist[e] = src[r];
+  }
+  __syncwarp();
+}
+
+// order[pos] = concatenated index of the state stored at position pos (ascending lpj, best last); lpj_row written
+template <typename T, int EPL>
+__device__ __forceinline__ void v2_select_merge(const double *lpjs, int32_t *slist, int32_t *order, int S, int Snew,
+                                                T *lpj_row, int lane, int &nsub) {
+  constexpr int MP = 32 * EPL;
+  uint64_t key[EPL];
+  int src[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    key[r] = e < S ? v2_key<T>(lpjs, e) : 0ull;
+    src[r] = e < S ? e : kPadSrc;
+  }
+  bitonic_network<EPL>(key, src, lane, 2);
+  uint64_t wkey = 0;
+#pragma unroll
+  for (int r = 0; r < EPL; ++r)
+    if (((S - 1) % EPL) == r) wkey = key[r];
+  wkey = __shfl_sync(FULL, wkey, (S - 1) / EPL);
+  int ns = 0;
+  for (int c0 = 0; c0 < Snew; c0 += 32) {
+    const int c = c0 + lane;
+    const bool keep = c < Snew && v2_key<T>(lpjs, S + c) > wkey;  // ties go to the old state (lower index)
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) slist[ns + __popc(m & ((1u << lane) - 1u))] = S + c;
+    ns += __popc(m);
+  }
+  __syncwarp();
+  if (ns > 0) {  // ns <= Snew <= 128
+    if (ns <= 32)
+      v2_sort_survivors<T, 1>(lpjs, slist, ns, lane);
+    else if (ns <= 64)
+      v2_sort_survivors<T, 2>(lpjs, slist, ns, lane);
+    else
+      v2_sort_survivors<T, 4>(lpjs, slist, ns, lane);
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) {
+      const int bi = MP - 1 - (lane * EPL + r);
+      if (bi < ns) {
+        const int bs = slist[bi];
+        const uint64_t bk = v2_key<T>(lpjs, bs);
+        if (ranks_before(bk, bs, key[r], src[r])) {
+          key[r] = bk;
+          src[r] = bs;
+        }
+      }
+    }
+    bitonic_network<EPL>(key, src, lane, MP);
+  }
+  nsub = 0;
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    if (e < S) {
+      const int pos = S - 1 - e;
+      lpj_row[pos] = (T)lpjs[src[r]];
+      order[pos] = src[r];
+      nsub += (src[r] >= S) ? 1 : 0;
+    }
+  }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
+                        int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
+                        V2Dims dims, int64_t B, int D, unsigned long long *nsubs, int32_t *ovf_count,
+                        int32_t *__restrict__ ovf_list) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64, H = dims.H, C = dims.C;
+  const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
+  unsigned char *p = smem_raw + (size_t)wib * v2_warp_bytes(dims);
+  uint4 *lists = (uint4 *)p;  // S old + Snew children
+  p += (size_t)(S + Snew) * 16;
+  double *lpjs = (double *)p;
+  p += align16((size_t)(S + Snew) * 8);
+  uint32_t *hash = (uint32_t *)p;  // dedup hashes; survivor list of the merge afterwards
+  p += align16((size_t)hash_len(S, Snew) * 4);
+  int32_t *iscr = (int32_t *)p;  // chosen parents (P); order of the merged set (S)
+  const double coef = th.hdr->coef, m2c = -2.0 * coef;
+  const double *__restrict__ G2 = th.G2;
+  const double *__restrict__ gp = th.gp;
+  unsigned long long my_subs = 0;
+
+  // the warps of a CTA walk the phases in lockstep (instruction-cache locality, see bsc_fast.cu)
+#define V2_PHASE_SYNC() __syncthreads()
+  for (int64_t b0 = (int64_t)blockIdx.x * wpb; b0 < B; b0 += (int64_t)gridDim.x * wpb) {
+    const bool active = b0 + wib < B;
+    const int64_t b = active ? b0 + wib : 0;
+    const int64_t row = idx ? idx[b] : row0 + b;
+    const uint32_t n_glob = ep.n_offset + (uint32_t)row;
+    uint64_t *Krow = K + row * (int64_t)S * W64;
+    const T *__restrict__ y = Y + b * ldY;
+    const T *__restrict__ a_row = A + b * (int64_t)H;
+    double yy = 0.0;
+    bool bail = !active;  // idle warps only keep the barriers company
+    for (int d = lane; d < D; d += 32) {
+      const double v = (double)y[d];
+      bail |= (v != v);
+      yy += v * v;
+    }
+    yy = warp_sum(yy);
+    const double yyc = yy * coef;
+    __syncwarp();  // the previous datapoint's readers of this warp's shared memory are done
+    V2_PHASE_SYNC();
+
+    // ---- old states: bit rows -> lists, scored in the same walk (evo.py:95) ----
+    for (int s0 = 0; s0 < S && active; s0 += 32) {
+      const int s = s0 + lane;
+      if (s < S) {
+        lists[s] = make_uint4(0u, 0u, 0u, 0u);
+        unsigned char *lb = (unsigned char *)(lists + s);
+        const uint64_t *st = Krow + (size_t)s * W64;
+        int n = 0;
+        double acc = yyc;
+        for (int w = 0; w < W64; ++w) {
+          uint64_t m = st[w];
+          while (m) {
+            const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+            const int h = (w << 6) + (lo ? __ffs((int)lo) - 1 : 31 + __ffs((int)hi));
+            m &= m - 1;
+            if (n < kV2MaxList) {
+              acc += fma(m2c, (double)a_row[h], gp[h]);
+              const double *g2 = G2 + (size_t)h * H;
+              for (int i = 0; i < n; ++i) acc += g2[lb[i]];
+              lb[n] = (unsigned char)h;
+            }
+            ++n;
+          }
+        }
+        if (n > kV2MaxList)
+          bail = true;
+        else
+          lb[15] = (unsigned char)n;
+        lpjs[s] = acc;
+      }
+    }
+    bail = __any_sync(FULL, bail);
+
+    // ---- G generations: select, mutate, score incrementally ----
+    for (int g = 0; g < ep.G; ++g) {
+      V2_PHASE_SYNC();
+      if (bail) {
+        V2_PHASE_SYNC();
+        continue;
+      }
+      const int cand_base = g == 0 ? 0 : S + (g - 1) * Sgen;
+      const int S_c = g == 0 ? S : Sgen;
+      Stream st;
+      st.key = ep.key;
+      st.n = n_glob;
+      st.tag = make_tag(ep.step, g, PUR_SELECT);
+      const int bits = index_bits(S_c);
+      __syncwarp();
+      if (S_c <= 32)
+        randparents_sort<1>(S_c, ep.P, bits, st, iscr, lane);
+      else if (S_c <= 64)
+        randparents_sort<2>(S_c, ep.P, bits, st, iscr, lane);
+      else
+        randparents_sort<4>(S_c, ep.P, bits, st, iscr, lane);
+      __syncwarp();
+      V2_PHASE_SYNC();
+      st.tag = make_tag(ep.step, g, PUR_FLIP0);
+      for (int j0 = 0; j0 < Sgen; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < Sgen) {
+          const int src = cand_base + iscr[j / C];
+          const uint4 L = lists[src];
+          const int a = (int)(L.w >> 24);
+          // flip counts (batch_sparseflip evo.py:310-329 as Binomial counts, mutate_sparseflip of estep_device.cuh)
+          const FlipEntry *te = ep.flip_tab + a;
+          FlipClass f0, f1;
+          f0.pmf0 = __ldg(&te->c[0].pmf0);
+          f0.r = __ldg(&te->c[0].r);
+          f0.kconst = __ldg(&te->c[0].kconst);
+          f0.flip = __ldg(&te->c[0].flip);
+          f1.pmf0 = __ldg(&te->c[1].pmf0);
+          f1.r = __ldg(&te->c[1].r);
+          f1.kconst = __ldg(&te->c[1].kconst);
+          f1.flip = __ldg(&te->c[1].flip);
+          int k0 = f0.kconst, k1 = f1.kconst;
+          if (k0 < 0 || k1 < 0) {
+            const uint4 b0 = st.block((uint32_t)j, 0);
+            if (k0 < 0) k0 = flip_class_sample(f0, unit_double((uint64_t)b0.y << 32 | b0.x), H - a);
+            if (k1 < 0) k1 = flip_class_sample(f1, unit_double((uint64_t)b0.w << 32 | b0.z), a);
+          }
+          uint32_t t = 0;
+          uint4 r = make_uint4(0u, 0u, 0u, 0u);
+          // zero bits: k0 of the H - a candidates by rejection over all H positions (H - a >= 49: the dense class,
+          // never its complement form)
+          uint64_t add = 0;  // added positions, ascending bytes
+          int ka = 0;
+          if (k0 > kV2MaxAdd) {
+            bail = true;
+            k0 = 0;
+            k1 = 0;
+          }
+          if (k0 > 0) {
+            const uint32_t cap = 64u + 64u * (uint32_t)k0;
+            while (ka < k0 && t < cap) {
+              if ((t & 3u) == 0u) r = st.block((uint32_t)j, 1u + (t >> 2));
+              const uint32_t ri = (t & 3u) == 0u ? r.x : (t & 3u) == 1u ? r.y : (t & 3u) == 2u ? r.z : r.w;
+              ++t;
+              const uint32_t pos = randint_u32(ri, (uint32_t)H);
+              bool taken = false;
+              for (int i = 0; i < a; ++i) taken |= (pl_get(L, (uint32_t)i) == pos);
+              int below = 0;
+              for (int q = 0; q < ka; ++q) {
+                const uint32_t z = (uint32_t)(add >> (8 * q)) & 0xFFu;
+                taken |= (z == pos);
+                below += (z < pos) ? 1 : 0;
+              }
+              if (!taken) {  // sorted insert at byte `below`
+                const uint64_t lowmask = below >= 8 ? ~0ull : ((1ull << (8 * below)) - 1ull);
+                add = (add & lowmask) | ((uint64_t)pos << (8 * below)) | ((add & ~lowmask) << 8);
+                ++ka;
+              }
+            }
+            if (ka < k0) bail = true;  // rejection cap (the generic kernel continues with the n-th-remaining rule)
+          }
+          // one bits: k1 of the a candidates, each draw the idx-th REMAINING entry (2a < H: the sparse class)
+          uint32_t fl = 0;  // entries of L that are flipped (removed)
+          if (k1 > 0) {
+            const bool comp = 2 * k1 > a;
+            const int draws = k1 >= a ? 0 : (comp ? a - k1 : k1);
+            uint32_t dr = 0;
+            for (int got = 0; got < draws; ++got) {
+              if ((t & 3u) == 0u) r = st.block((uint32_t)j, 1u + (t >> 2));
+              const uint32_t ri = (t & 3u) == 0u ? r.x : (t & 3u) == 1u ? r.y : (t & 3u) == 2u ? r.z : r.w;
+              ++t;
+              int ix = (int)randint_u32(ri, (uint32_t)(a - got));
+              int e = 0;
+              while (true) {
+                if (!((dr >> e) & 1u)) {
+                  if (ix == 0) break;
+                  --ix;
+                }
+                ++e;
+              }
+              dr |= 1u << e;
+            }
+            const uint32_t valid = (1u << a) - 1u;
+            fl = (k1 >= a || comp) ? (valid & ~dr) : dr;
+          }
+          const int nc = a - __popc(fl) + ka;
+          if (nc > kV2MaxList) bail = true;
+          // lpj(child) - lpj(parent)
+          double dl = 0.0;
+          for (int i = 0; i < a; ++i) {
+            if ((fl >> i) & 1u) {
+              const uint32_t h = pl_get(L, (uint32_t)i);
+              double t1 = fma(m2c, (double)a_row[h], gp[h]);
+              const double *g2 = G2 + (size_t)h * H;
+              for (int i2 = 0; i2 < a; ++i2)
+                if (i2 != i && (!((fl >> i2) & 1u) || i2 > i)) t1 += g2[pl_get(L, (uint32_t)i2)];
+              dl -= t1;
+            }
+          }
+          for (int q = 0; q < ka; ++q) {
+            const uint32_t z = (uint32_t)(add >> (8 * q)) & 0xFFu;
+            double t1 = fma(m2c, (double)a_row[z], gp[z]);
+            const double *g2 = G2 + (size_t)z * H;
+            for (int i = 0; i < a; ++i)
+              if (!((fl >> i) & 1u)) t1 += g2[pl_get(L, (uint32_t)i)];
+            for (int q2 = 0; q2 < q; ++q2) t1 += g2[(uint32_t)(add >> (8 * q2)) & 0xFFu];
+            dl += t1;
+          }
+          // the child's list: kept entries merged with the added positions, ascending
+          const int child = S + g * Sgen + j;
+          lists[child] = make_uint4(0u, 0u, 0u, 0u);
+          if (nc <= kV2MaxList) {
+            unsigned char *cb = (unsigned char *)(lists + child);
+            int m = 0, q = 0;
+            uint32_t nextz = ka ? (uint32_t)add & 0xFFu : 256u;
+            for (int i = 0; i < a; ++i) {
+              if ((fl >> i) & 1u) continue;
+              const uint32_t e = pl_get(L, (uint32_t)i);
+              while (nextz < e) {
+                cb[m++] = (unsigned char)nextz;
+                ++q;
+                nextz = q < ka ? (uint32_t)(add >> (8 * q)) & 0xFFu : 256u;
+              }
+              cb[m++] = (unsigned char)e;
+            }
+            while (q < ka) {
+              cb[m++] = (unsigned char)((add >> (8 * q)) & 0xFFu);
+              ++q;
+            }
+            cb[15] = (unsigned char)m;
+          }
+          lpjs[child] = lpjs[src] + dl;
+        }
+      }
+      bail = __any_sync(FULL, bail);
+    }
+    if (bail && active && lane == 0) ovf_list[atomicAdd(ovf_count, 1)] = (int32_t)b;  // -> the generic kernel
+    __syncwarp();
+    V2_PHASE_SYNC();
+    if (!bail)
+
+    // ---- dedup: a child equal to a later child or to an old state is redundant (_set_redundant_lpj_to_low) ----
+    {
+      const int Sp = hash_old_pad(S), Snp = (Snew + 3) & ~3;
+      for (int i = lane; i < Sp; i += 32) hash[i] = i < S ? pl_hash(lists[i]) : 0u;
+      for (int i = lane; i < Snp; i += 32) hash[Sp + i] = i < Snew ? pl_hash(lists[S + i]) : 0u;
+      __syncwarp();
+      if (Snew <= 32)
+        v2_mark_redundant_cpl<T, 1>(lists, lpjs, hash, S, Snew, lane);
+      else if (Snew <= 64)
+        v2_mark_redundant_cpl<T, 2>(lists, lpjs, hash, S, Snew, lane);
+      else
+        v2_mark_redundant_cpl<T, 4>(lists, lpjs, hash, S, Snew, lane);
+      __syncwarp();
+    }
+
+    V2_PHASE_SYNC();
+    if (bail) continue;
+    // ---- top-S merge (update_states_for_batch) and write-back ----
+    int nsub = 0;
+    T *lrow = lpj + row * (int64_t)S;
+    int32_t *slist = (int32_t *)hash;
+    if (S <= 32)
+      v2_select_merge<T, 1>(lpjs, slist, iscr, S, Snew, lrow, lane, nsub);
+    else if (S <= 64)
+      v2_select_merge<T, 2>(lpjs, slist, iscr, S, Snew, lrow, lane, nsub);
+    else
+      v2_select_merge<T, 4>(lpjs, slist, iscr, S, Snew, lrow, lane, nsub);
+    my_subs += (unsigned long long)warp_sum(nsub);
+    __syncwarp();
+    for (int p0 = 0; p0 < S; p0 += 32) {
+      const int pos = p0 + lane;
+      if (pos < S) {
+        const uint4 L = lists[iscr[pos]];
+        const int n = (int)(L.w >> 24);
+        uint64_t wd[4] = {0ull, 0ull, 0ull, 0ull};
+        for (int i = 0; i < n; ++i) {
+          const uint32_t h = pl_get(L, (uint32_t)i);
+          const uint64_t bit = 1ull << (h & 63u);
+          const uint32_t w = h >> 6;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (w == (uint32_t)k) wd[k] |= bit;
+        }
+        uint64_t *dst = Krow + (size_t)pos * W64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < W64) dst[k] = wd[k];
+      }
+    }
+  }
+#undef V2_PHASE_SYNC
+  if (lane == 0 && my_subs) atomicAdd(nsubs, my_subs);
+}
+
+}  // namespace tvo

@@ -13,11 +13,13 @@
 #include <cublas_v2.h>
 
 #include "bsc_device.cuh"
+#include "bsc_estep_v2.cuh"
 
 namespace tvo {
 
 constexpr int kMaxSmemFast = 227 * 1024;
 constexpr int kMaxWarpsLarge = 12;  // warps per CTA of the one-CTA-per-SM E-step variant (large H*S)
+static int g_disable_v2 = 0;         // tvo_bsc_estep_variant(1): generic kernel only (tests compare the two)
 
 int evo_params_from_cfg(const tvo_evo_config *cfg, int S, int H, EvoParams &ep, EstepDims &dims, const char *who);
 template <typename T>
@@ -308,10 +310,13 @@ __global__ void __launch_bounds__(MINB == 1 ? 32 * kMaxWarpsLarge : 256, MINB)
 estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                           int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
                           const double *__restrict__ sparsity_p, EstepDims dims, int64_t B, int H, int D,
-                          unsigned long long *nsubs, uint64_t *stage_rows) {
+                          unsigned long long *nsubs, uint64_t *stage_rows, const int32_t *__restrict__ bsel,
+                          const int32_t *__restrict__ bsel_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
+  // bsel: process only the listed datapoints of this launch (the overflow list of the list-based kernel)
+  if (bsel) B = *bsel_count;
   const size_t wbytes = warp_buf_bytes<T>(dims);
   unsigned char *base = smem_raw + (size_t)wib * wbytes;
   WarpBuf<T> wb = carve_warp_buf<T>(base, dims);
@@ -332,13 +337,13 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
   // share the cache lines of the phase they are all in.
 #define PHASE_SYNC() __syncthreads()
   for (int64_t b0 = (int64_t)blockIdx.x * wpb; b0 < B; b0 += (int64_t)gridDim.x * wpb) {
-    const int64_t b = b0 + wib;
-    const bool active = b < B;
+    const bool active = b0 + wib < B;
+    const int64_t b = active ? (bsel ? (int64_t)bsel[b0 + wib] : b0 + wib) : 0;
     const int64_t row = active ? (idx ? idx[b] : row0 + b) : 0;
     const uint32_t n_glob = ep.n_offset + (uint32_t)row;
     uint64_t *Krow = K + row * (int64_t)S * W64;
     T *lrow = lpj + row * (int64_t)S;
-    const T *y = Y + (active ? b : 0) * ldY;
+    const T *y = Y + b * ldY;
     double yy = 0.0;
     bool has_nan = false;
     if (active) {
@@ -357,7 +362,7 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
       __syncwarp();
     }
     PHASE_SYNC();
-    const T *a_sm = A + (active ? b : 0) * (int64_t)H;  // a = W^T y row, read through L1/L2 (written by the DGEMM)
+    const T *a_sm = A + b * (int64_t)H;  // a = W^T y row, read through L1/L2 (written by the DGEMM)
     if (active) score_states<T, kOldInGlobal>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, plist, pcap, lane, W64);  // evo.py:95
     for (int g = 0; g < ep.G; ++g) {
       const uint64_t *cand = g == 0 ? wb.oldK : wb.newK + (size_t)(g - 1) * Sgen * wb.rs;
@@ -543,12 +548,17 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
                   int S, int H, int D, int64_t *nsubs, void *stream) {
   TVO_REQUIRE(Y && K && lpj && ws && cfg && nsubs, "estep_evo_bsc: null pointer");
   const int64_t per = estep_scratch_per_dp<T>(H);
-  // scratch layout: [sparseflip table (flip_table_bytes(H), only when it fits)] [a = W^T y rows]
+  // scratch layout: [sparseflip table (flip_table_bytes(H), only when it fits)] [overflow counter (16 B) + overflow
+  // list of the list-based kernel (4 B per datapoint of a chunk)] [a = W^T y rows]
   const bool sparse = cfg->mutation == TVO_MUT_SPARSEFLIP || cfg->mutation == TVO_MUT_CROSS_SPARSEFLIP;
   const int64_t tab_bytes = sparse && scratch && sparsity ? (int64_t)flip_table_bytes(H) : 0;
-  const bool use_tab = tab_bytes > 0 && scratch_bytes >= tab_bytes + per * min((int64_t)1024, B);
-  unsigned char *scratch_a = (unsigned char *)scratch + (use_tab ? tab_bytes : 0);
-  int64_t cap = scratch ? (scratch_bytes - (use_tab ? tab_bytes : 0)) / per : 0;
+  const bool use_tab = tab_bytes > 0 && scratch_bytes >= tab_bytes + 32 + (per + 4) * min((int64_t)1024, B);
+  int64_t cap = !scratch ? 0 : use_tab ? (scratch_bytes - tab_bytes - 32) / (per + 4) : scratch_bytes / per;
+  if (cap > B) cap = B;
+  const int64_t ovf_bytes = use_tab ? (int64_t)align16((size_t)(16 + 4 * cap)) : 0;
+  int32_t *ovf_count = use_tab ? (int32_t *)((unsigned char *)scratch + tab_bytes) : nullptr;
+  int32_t *ovf_list = use_tab ? ovf_count + 4 : nullptr;
+  unsigned char *scratch_a = (unsigned char *)scratch + (use_tab ? tab_bytes + ovf_bytes : 0);
   if (cap < 1024 && cap < B)  // no (useful) scratch: direct column-walk form
     return estep_evo_bsc_direct<T>(Y, ldY, idx, K, lpj, ws, cfg, sparsity, B, S, H, D, nsubs, stream);
   EvoParams ep;
@@ -601,15 +611,42 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
     TVO_AFTER_LAUNCH("flip_table");
     ep.flip_tab = tab;
   }
+  // list-based kernel (bsc_estep_v2.cuh) for sparse states at 64 <= H <= 256, randparents + sparseflip; the generic
+  // kernel then takes the datapoints it handed back (overflow list) — or everything when the shape is not covered
+  V2Dims v2{S, dims.Snew, dims.Sgen, ep.P, ep.C, ep.G, dims.W64, H};
+  const size_t v2_smem = v2_warp_bytes(v2) * 8;
+  const bool use_v2 = use_tab && v2_supported(ep, v2) && v2_smem <= (size_t)kMaxSmemFast && !g_disable_v2;
+  auto kern2 = estep_evo_bsc_v2_kernel<T>;
+  int occ2 = 1;
+  if (use_v2) {
+    TVO_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2_smem));
+    TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, 256, v2_smem));
+    occ2 = max(occ2, 1);
+  }
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
     const int Bc = (int)min(cap, B - c0);
     rc = gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, A, Bc, H, D);
     if (rc) return rc;
     const int grid = (int)max((int64_t)1, min((int64_t)(Bc + wpb - 1) / wpb, (int64_t)sm_count() * occ));
     void *tok;
+    if (use_v2) {
+      TVO_CUDA(cudaMemsetAsync(ovf_count, 0, 16, st));
+      const int grid2 = (int)max((int64_t)1, min((int64_t)(Bc + 7) / 8, (int64_t)sm_count() * occ2));
+      kernel_timing_begin(TVO_TIMED_ESTEP_EVO_BSC, st, &tok);
+      kern2<<<grid2, 256, v2_smem, st>>>(Y + c0 * ldY, ldY, A, idx ? idx + c0 : nullptr, c0, K, lpj, ws, ep, v2, Bc, D,
+                                         (unsigned long long *)nsubs, ovf_count, ovf_list);
+      kernel_timing_end(tok, st);
+      TVO_AFTER_LAUNCH("estep_evo_bsc_v2");
+      // overflow datapoints: the generic kernel reads their count on the device (an empty list costs one idle launch)
+      kern<<<min(grid, sm_count()), wpb * 32, smem, st>>>(Y + c0 * ldY, ldY, A, idx ? idx + c0 : nullptr, c0, K, lpj, ws, ep,
+                                                          sparsity, dims, Bc, H, D, (unsigned long long *)nsubs, stage_rows,
+                                                          ovf_list, ovf_count);
+      TVO_AFTER_LAUNCH("estep_evo_bsc_gram(overflow)");
+      continue;
+    }
     kernel_timing_begin(TVO_TIMED_ESTEP_EVO_BSC, st, &tok);
     kern<<<grid, wpb * 32, smem, st>>>(Y + c0 * ldY, ldY, A, idx ? idx + c0 : nullptr, c0, K, lpj, ws, ep, sparsity, dims,
-                                       Bc, H, D, (unsigned long long *)nsubs, stage_rows);
+                                       Bc, H, D, (unsigned long long *)nsubs, stage_rows, nullptr, nullptr);
     kernel_timing_end(tok, st);
     TVO_AFTER_LAUNCH("estep_evo_bsc_gram");
   }
@@ -668,7 +705,11 @@ using namespace tvo;
 extern "C" {
 int64_t tvo_bsc_stats_len(int32_t H, int32_t D) { return (int64_t)H * D + (int64_t)H * H + H + 3; }
 int64_t tvo_bsc_estep_scratch_bytes(int64_t B, int32_t H, int32_t is_f64) {
-  return B * (int64_t)H * (is_f64 ? 8 : 4) + (int64_t)flip_table_bytes(H);
+  return B * ((int64_t)H * (is_f64 ? 8 : 4) + 4) + 32 + (int64_t)flip_table_bytes(H);
+}
+int tvo_bsc_estep_variant(int32_t generic_only) {
+  g_disable_v2 = generic_only ? 1 : 0;
+  return TVO_OK;
 }
 int64_t tvo_bsc_mstep_scratch_bytes(int64_t B, int32_t H, int32_t D, int32_t is_f64) {
   return B * ((int64_t)H * 8 + (is_f64 ? 0 : (int64_t)D * 8));

@@ -97,8 +97,9 @@ class BSC(Optimized, Sampler, Reconstructor):
     def _get_scratch(self, B: int) -> Tensor:
         D, H = self._shape
         n = min(max(int(B), 1), int(self.scratch_datapoints))
-        # chunk rows (a = W^T y / E and the fp64 copy of Y for fp32 models) + the sparseflip table of the E-step
-        nbytes = n * (H * 8 + (0 if self._precision == to.float64 else D * 8)) + 48 * (H + 1) + 256
+        # chunk rows (a = W^T y / E and the fp64 copy of Y for fp32 models) + the E-step's sparseflip table / overflow list
+        f64 = int(self._precision == to.float64)
+        nbytes = max(_lib.lib().tvo_bsc_estep_scratch_bytes(n, H, f64), _lib.lib().tvo_bsc_mstep_scratch_bytes(n, H, D, f64))
         if self._scratch is None or self._scratch.numel() < nbytes or self._scratch.device != self._stats.device:
             self._scratch = to.empty(nbytes, dtype=to.uint8, device=self._stats.device)
         return self._scratch
