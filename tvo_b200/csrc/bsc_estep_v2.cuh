@@ -32,10 +32,15 @@ struct V2Dims {
   int S, Snew, Sgen, P, C, G, W64, H;
 };
 
+// hash region: the dedup hashes, afterwards the survivors of the merge (8-byte composite keys or 4-byte indices)
+__host__ __device__ inline size_t v2_hash_bytes(const V2Dims &d) {
+  const size_t h = (size_t)hash_len(d.S, d.Snew) * 4, k = (size_t)d.Snew * 8;
+  return align16(h > k ? h : k);
+}
 __host__ __device__ inline size_t v2_warp_bytes(const V2Dims &d) {
   const int nI = d.P > d.S ? d.P : d.S;
-  return (size_t)(d.S + d.Snew) * 16 + align16((size_t)(d.S + d.Snew) * 8) + align16((size_t)hash_len(d.S, d.Snew) * 4) +
-         align16((size_t)nI * 4);
+  return (size_t)(d.S + d.Snew) * 16 + align16((size_t)(d.S + d.Snew) * 8) + v2_hash_bytes(d) + align16((size_t)nI * 4) +
+         align16((size_t)d.H * 8);
 }
 
 __host__ inline bool v2_supported(const EvoParams &ep, const V2Dims &d) {
@@ -44,10 +49,6 @@ __host__ inline bool v2_supported(const EvoParams &ep, const V2Dims &d) {
 }
 
 // ---- position lists ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pl_get(const uint4 &l, uint32_t i) {  // i < 15
-  const bool hi = (i & 8u) != 0;
-  return __byte_perm(hi ? l.z : l.x, hi ? l.w : l.y, i & 7u) & 0xFFu;
-}
 __device__ __forceinline__ bool pl_equal(const uint4 &a, const uint4 &b) {
   return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) == 0u;
 }
@@ -221,8 +222,168 @@ __device__ __forceinline__ void v2_select_merge(const double *lpjs, int32_t *sli
   }
 }
 
-// ---- the kernel -----------------------------------------------------------------------------------------------
+// ---- top-S merge on COMPOSITE keys ---------------------------------------------------------------------------
+// ckey = the 64-bit sort key with its low 8 bits replaced by 255 - (concatenated index): all keys of a datapoint are
+// distinct, "ranks before" is one unsigned 64-bit compare and the index rides in the key (no payload register, no
+// 96-bit compare).  Dropping the 8 low mantissa bits can only matter when two candidates agree in the upper 56 bits;
+// the merge checks exactly that for every adjacent pair of the result and for the best excluded candidate, and
+// reports `false` (nothing written) so that the caller runs the exact merge instead.  True ties order by index
+// either way, so equal lpj values pass the check as well when they are exactly equal — they are sent to the exact
+// path too, which costs time, not correctness.
 template <typename T>
+__device__ __forceinline__ uint64_t v2_ckey(const double *lpjs, int i) {
+  return (sort_key((double)(T)lpjs[i]) & ~0xFFull) | (uint64_t)(255 - i);
+}
+
+template <int EPL>
+__device__ __forceinline__ void bitonic_desc_u64(uint64_t (&key)[EPL], int lane, int k_first) {
+  constexpr int MP = 32 * EPL;
+#pragma unroll 1
+  for (int k = k_first; k <= MP; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j >= EPL; j >>= 1) {  // partner in another lane
+      const int lm = j / EPL;
+      const bool want_max = ((lane & lm) == 0) == ((lane & (k / EPL)) == 0);
+#pragma unroll
+      for (int r = 0; r < EPL; ++r) {
+        const uint64_t o = __shfl_xor_sync(FULL, key[r], lm);
+        key[r] = ((o > key[r]) == want_max) ? o : key[r];
+      }
+    }
+#pragma unroll
+    for (int jj = EPL >> 1; jj > 0; jj >>= 1) {  // partner in the same lane
+      if (jj < k) {
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+          if ((r & jj) == 0) {
+            const int e = lane * EPL + r;
+            const bool up = (e & k) == 0;  // best-first block
+            const uint64_t hi = key[r] > key[r ^ jj] ? key[r] : key[r ^ jj];
+            const uint64_t lo = key[r] > key[r ^ jj] ? key[r ^ jj] : key[r];
+            key[r] = up ? hi : lo;
+            key[r ^ jj] = up ? lo : hi;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int EPL>
+__device__ __forceinline__ void v2_sort_survivors_ck(uint64_t *sk, int ns, int lane) {
+  uint64_t key[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    key[r] = e < ns ? sk[e] : 0ull;
+  }
+  __syncwarp();
+  bitonic_desc_u64<EPL>(key, lane, 2);
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    if (e < ns) sk[e] = key[r];
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+  const uint32_t hi = __reduce_max_sync(FULL, (uint32_t)(v >> 32));
+  const uint32_t lo = __reduce_max_sync(FULL, (uint32_t)(v >> 32) == hi ? (uint32_t)v : 0u);
+  return (uint64_t)hi << 32 | lo;
+}
+
+// EPL: 32*EPL >= S;  EPLN: 32*EPLN >= Snew.  sk: Snew composite keys of scratch.
+template <typename T, int EPL, int EPLN>
+__device__ __forceinline__ bool v2_select_merge_ck(const double *lpjs, uint64_t *sk, int32_t *order, int S, int Snew,
+                                                   T *lpj_row, int lane, int &nsub) {
+  constexpr int MP = 32 * EPL;
+  uint64_t key[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    key[r] = e < S ? v2_ckey<T>(lpjs, e) : 0ull;
+  }
+  bitonic_desc_u64<EPL>(key, lane, 2);
+  uint64_t wkey = 0;
+#pragma unroll
+  for (int r = 0; r < EPL; ++r)
+    if (((S - 1) % EPL) == r) wkey = key[r];
+  wkey = __shfl_sync(FULL, wkey, (S - 1) / EPL) & ~0xFFull;
+  // children whose upper 56 bits reach the worst old state's (conservative: an exact tie loses to the old state,
+  // a 56-bit tie is resolved by the check below)
+  int ns = 0;
+  for (int c0 = 0; c0 < Snew; c0 += 32) {
+    const int c = c0 + lane;
+    const uint64_t ck = c < Snew ? v2_ckey<T>(lpjs, S + c) : 0ull;
+    const bool keep = c < Snew && ck >= wkey;
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) sk[ns + __popc(m & ((1u << lane) - 1u))] = ck;
+    ns += __popc(m);
+  }
+  __syncwarp();
+  uint64_t dropped = 0;  // best candidate that does not make the top MP
+  if (ns > 0) {
+    if (EPLN == 1 || ns <= 32)
+      v2_sort_survivors_ck<1>(sk, ns, lane);
+    else if (EPLN == 2 || ns <= 64)
+      v2_sort_survivors_ck<(EPLN >= 2 ? 2 : 1)>(sk, ns, lane);
+    else
+      v2_sort_survivors_ck<(EPLN >= 4 ? 4 : 1)>(sk, ns, lane);
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) {
+      const int bi = MP - 1 - (lane * EPL + r);
+      if (bi < ns) {
+        const uint64_t bk = sk[bi];
+        const uint64_t lo = bk > key[r] ? key[r] : bk;
+        key[r] = bk > key[r] ? bk : key[r];
+        dropped = lo > dropped ? lo : dropped;
+      }
+    }
+    for (int bi = MP + lane; bi < ns; bi += 32) dropped = sk[bi] > dropped ? sk[bi] : dropped;  // survivors beyond MP
+    bitonic_desc_u64<EPL>(key, lane, MP);
+  }
+  // 56-bit ties: adjacent elements of the result (ranks 0..S, the first excluded one included when it is held here) ...
+  bool amb = false;
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    uint64_t nxt;
+    if (r + 1 < EPL) {
+      nxt = key[r + 1];
+    } else {
+      nxt = __shfl_down_sync(FULL, key[0], 1);
+      if (lane == 31) nxt = 0ull;
+    }
+    amb |= e < S && nxt != 0ull && (key[r] >> 8) == (nxt >> 8);
+  }
+  // ... and the last selected element against the best candidate dropped by the merge
+  uint64_t last = 0;
+#pragma unroll
+  for (int r = 0; r < EPL; ++r)
+    if (((S - 1) % EPL) == r) last = key[r];
+  last = __shfl_sync(FULL, last, (S - 1) / EPL);
+  dropped = warp_max_u64(dropped);
+  amb |= dropped != 0ull && (dropped >> 8) == (last >> 8);
+  if (__any_sync(FULL, amb)) return false;
+  nsub = 0;
+#pragma unroll
+  for (int r = 0; r < EPL; ++r) {
+    const int e = lane * EPL + r;
+    if (e < S) {
+      const int pos = S - 1 - e, src = 255 - (int)(key[r] & 0xFFull);
+      lpj_row[pos] = (T)lpjs[src];
+      order[pos] = src;
+      nsub += (src >= S) ? 1 : 0;
+    }
+  }
+  return true;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------
+// ES / EG / EN: elements per lane that hold S, S_gen and S_new (1, 2 or 4): only the networks of one shape class are
+// compiled into a kernel (the instruction cache is the scarce resource here)
+template <typename T, int ES, int EG, int EN>
 __global__ void __launch_bounds__(256, 4)
 estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                         int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
@@ -238,8 +399,10 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
   double *lpjs = (double *)p;
   p += align16((size_t)(S + Snew) * 8);
   uint32_t *hash = (uint32_t *)p;  // dedup hashes; survivor list of the merge afterwards
-  p += align16((size_t)hash_len(S, Snew) * 4);
+  p += v2_hash_bytes(dims);
   int32_t *iscr = (int32_t *)p;  // chosen parents (P); order of the merged set (S)
+  p += align16((size_t)(dims.P > S ? dims.P : S) * 4);
+  double *dsm = (double *)p;  // d_h = gp_h - 2 coef a_h of this datapoint, all H units
   const double coef = th.hdr->coef, m2c = -2.0 * coef;
   const double *__restrict__ G2 = th.G2;
   const double *__restrict__ gp = th.gp;
@@ -265,6 +428,8 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
     yy = warp_sum(yy);
     const double yyc = yy * coef;
     __syncwarp();  // the previous datapoint's readers of this warp's shared memory are done
+    for (int h = lane; h < H; h += 32) dsm[h] = fma(m2c, (double)a_row[h], gp[h]);  // coalesced read of the a row
+    __syncwarp();
     V2_PHASE_SYNC();
 
     // ---- old states: bit rows -> lists, scored in the same walk (evo.py:95) ----
@@ -283,7 +448,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
             const int h = (w << 6) + (lo ? __ffs((int)lo) - 1 : 31 + __ffs((int)hi));
             m &= m - 1;
             if (n < kV2MaxList) {
-              acc += fma(m2c, (double)a_row[h], gp[h]);
+              acc += dsm[h];
               const double *g2 = G2 + (size_t)h * H;
               for (int i = 0; i < n; ++i) acc += g2[lb[i]];
               lb[n] = (unsigned char)h;
@@ -315,12 +480,10 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
       st.tag = make_tag(ep.step, g, PUR_SELECT);
       const int bits = index_bits(S_c);
       __syncwarp();
-      if (S_c <= 32)
-        randparents_sort<1>(S_c, ep.P, bits, st, iscr, lane);
-      else if (S_c <= 64)
-        randparents_sort<2>(S_c, ep.P, bits, st, iscr, lane);
+      if (g == 0)
+        randparents_sort<ES>(S_c, ep.P, bits, st, iscr, lane);
       else
-        randparents_sort<4>(S_c, ep.P, bits, st, iscr, lane);
+        randparents_sort<EG>(S_c, ep.P, bits, st, iscr, lane);
       __syncwarp();
       V2_PHASE_SYNC();
       st.tag = make_tag(ep.step, g, PUR_FLIP0);
@@ -328,8 +491,8 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
         const int j = j0 + lane;
         if (j < Sgen) {
           const int src = cand_base + iscr[j / C];
-          const uint4 L = lists[src];
-          const int a = (int)(L.w >> 24);
+          const unsigned char *pb = (const unsigned char *)(lists + src);  // the parent's list
+          const int a = (int)pb[15];
           // flip counts (batch_sparseflip evo.py:310-329 as Binomial counts, mutate_sparseflip of estep_device.cuh)
           const FlipEntry *te = ep.flip_tab + a;
           FlipClass f0, f1;
@@ -366,7 +529,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
               ++t;
               const uint32_t pos = randint_u32(ri, (uint32_t)H);
               bool taken = false;
-              for (int i = 0; i < a; ++i) taken |= (pl_get(L, (uint32_t)i) == pos);
+              for (int i = 0; i < a; ++i) taken |= ((uint32_t)pb[i] == pos);
               int below = 0;
               for (int q = 0; q < ka; ++q) {
                 const uint32_t z = (uint32_t)(add >> (8 * q)) & 0xFFu;
@@ -407,24 +570,31 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
           }
           const int nc = a - __popc(fl) + ka;
           if (nc > kV2MaxList) bail = true;
-          // lpj(child) - lpj(parent)
+          // lpj(child) - lpj(parent): the removed units, then the added ones, each against the units present
+          const uint32_t kept = ((1u << a) - 1u) & ~fl;
           double dl = 0.0;
-          for (int i = 0; i < a; ++i) {
-            if ((fl >> i) & 1u) {
-              const uint32_t h = pl_get(L, (uint32_t)i);
-              double t1 = fma(m2c, (double)a_row[h], gp[h]);
-              const double *g2 = G2 + (size_t)h * H;
-              for (int i2 = 0; i2 < a; ++i2)
-                if (i2 != i && (!((fl >> i2) & 1u) || i2 > i)) t1 += g2[pl_get(L, (uint32_t)i2)];
-              dl -= t1;
+          for (uint32_t f = fl; f;) {
+            const int i = __ffs((int)f) - 1;
+            f &= f - 1;
+            const uint32_t h = pb[i];
+            double t1 = dsm[h];
+            const double *g2 = G2 + (size_t)h * H;
+            for (uint32_t mm = kept | f; mm;) {  // kept units and the removed ones after i
+              const int i2 = __ffs((int)mm) - 1;
+              mm &= mm - 1;
+              t1 += g2[pb[i2]];
             }
+            dl -= t1;
           }
           for (int q = 0; q < ka; ++q) {
             const uint32_t z = (uint32_t)(add >> (8 * q)) & 0xFFu;
-            double t1 = fma(m2c, (double)a_row[z], gp[z]);
+            double t1 = dsm[z];
             const double *g2 = G2 + (size_t)z * H;
-            for (int i = 0; i < a; ++i)
-              if (!((fl >> i) & 1u)) t1 += g2[pl_get(L, (uint32_t)i)];
+            for (uint32_t mm = kept; mm;) {
+              const int i2 = __ffs((int)mm) - 1;
+              mm &= mm - 1;
+              t1 += g2[pb[i2]];
+            }
             for (int q2 = 0; q2 < q; ++q2) t1 += g2[(uint32_t)(add >> (8 * q2)) & 0xFFu];
             dl += t1;
           }
@@ -435,9 +605,10 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
             unsigned char *cb = (unsigned char *)(lists + child);
             int m = 0, q = 0;
             uint32_t nextz = ka ? (uint32_t)add & 0xFFu : 256u;
-            for (int i = 0; i < a; ++i) {
-              if ((fl >> i) & 1u) continue;
-              const uint32_t e = pl_get(L, (uint32_t)i);
+            for (uint32_t mm = kept; mm;) {
+              const int i = __ffs((int)mm) - 1;
+              mm &= mm - 1;
+              const uint32_t e = pb[i];
               while (nextz < e) {
                 cb[m++] = (unsigned char)nextz;
                 ++q;
@@ -467,12 +638,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
       for (int i = lane; i < Sp; i += 32) hash[i] = i < S ? pl_hash(lists[i]) : 0u;
       for (int i = lane; i < Snp; i += 32) hash[Sp + i] = i < Snew ? pl_hash(lists[S + i]) : 0u;
       __syncwarp();
-      if (Snew <= 32)
-        v2_mark_redundant_cpl<T, 1>(lists, lpjs, hash, S, Snew, lane);
-      else if (Snew <= 64)
-        v2_mark_redundant_cpl<T, 2>(lists, lpjs, hash, S, Snew, lane);
-      else
-        v2_mark_redundant_cpl<T, 4>(lists, lpjs, hash, S, Snew, lane);
+      v2_mark_redundant_cpl<T, EN>(lists, lpjs, hash, S, Snew, lane);
       __syncwarp();
     }
 
@@ -481,23 +647,20 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
     // ---- top-S merge (update_states_for_batch) and write-back ----
     int nsub = 0;
     T *lrow = lpj + row * (int64_t)S;
-    int32_t *slist = (int32_t *)hash;
-    if (S <= 32)
-      v2_select_merge<T, 1>(lpjs, slist, iscr, S, Snew, lrow, lane, nsub);
-    else if (S <= 64)
-      v2_select_merge<T, 2>(lpjs, slist, iscr, S, Snew, lrow, lane, nsub);
-    else
-      v2_select_merge<T, 4>(lpjs, slist, iscr, S, Snew, lrow, lane, nsub);
+    if (!v2_select_merge_ck<T, ES, EN>(lpjs, (uint64_t *)hash, iscr, S, Snew, lrow, lane, nsub)) {
+      __syncwarp();
+      v2_select_merge<T, ES>(lpjs, (int32_t *)hash, iscr, S, Snew, lrow, lane, nsub);  // exact keys (56-bit tie)
+    }
     my_subs += (unsigned long long)warp_sum(nsub);
     __syncwarp();
     for (int p0 = 0; p0 < S; p0 += 32) {
       const int pos = p0 + lane;
       if (pos < S) {
-        const uint4 L = lists[iscr[pos]];
-        const int n = (int)(L.w >> 24);
+        const unsigned char *ob = (const unsigned char *)(lists + iscr[pos]);
+        const int n = (int)ob[15];
         uint64_t wd[4] = {0ull, 0ull, 0ull, 0ull};
         for (int i = 0; i < n; ++i) {
-          const uint32_t h = pl_get(L, (uint32_t)i);
+          const uint32_t h = ob[i];
           const uint64_t bit = 1ull << (h & 63u);
           const uint32_t w = h >> 6;
 #pragma unroll

@@ -616,7 +616,11 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   V2Dims v2{S, dims.Snew, dims.Sgen, ep.P, ep.C, ep.G, dims.W64, H};
   const size_t v2_smem = v2_warp_bytes(v2) * 8;
   const bool use_v2 = use_tab && v2_supported(ep, v2) && v2_smem <= (size_t)kMaxSmemFast && !g_disable_v2;
-  auto kern2 = estep_evo_bsc_v2_kernel<T>;
+  const int eS = S <= 32 ? 1 : S <= 64 ? 2 : 4, eG = dims.Sgen <= 32 ? 1 : dims.Sgen <= 64 ? 2 : 4,
+            eN = dims.Snew <= 32 ? 1 : dims.Snew <= 64 ? 2 : 4;
+  auto kern2 = eS == 1 && eG == 1 && eN == 1   ? estep_evo_bsc_v2_kernel<T, 1, 1, 1>
+               : eS <= 2 && eG == 1 && eN <= 2 ? estep_evo_bsc_v2_kernel<T, 2, 1, 2>
+                                               : estep_evo_bsc_v2_kernel<T, 4, 4, 4>;
   int occ2 = 1;
   if (use_v2) {
     TVO_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2_smem));
