@@ -30,6 +30,8 @@ constexpr int kV2MaxAdd = 8;    // added units per child (sorted bytes in one 64
 
 struct V2Dims {
   int S, Snew, Sgen, P, C, G, W64, H;
+  // filled by v2_finish(): per-warp shared-memory layout (bytes) and the 16-bit magic of j / C (exact for j < 256)
+  int off_lpj, off_hash, off_iscr, off_d, warp_bytes, cinv;
 };
 
 // hash region: the dedup hashes, afterwards the survivors of the merge (8-byte composite keys or 4-byte indices)
@@ -41,6 +43,15 @@ __host__ __device__ inline size_t v2_warp_bytes(const V2Dims &d) {
   const int nI = d.P > d.S ? d.P : d.S;
   return (size_t)(d.S + d.Snew) * 16 + align16((size_t)(d.S + d.Snew) * 8) + v2_hash_bytes(d) + align16((size_t)nI * 4) +
          align16((size_t)d.H * 8);
+}
+
+__host__ inline void v2_finish(V2Dims &d) {
+  d.off_lpj = (d.S + d.Snew) * 16;
+  d.off_hash = d.off_lpj + (int)align16((size_t)(d.S + d.Snew) * 8);
+  d.off_iscr = d.off_hash + (int)v2_hash_bytes(d);
+  d.off_d = d.off_iscr + (int)align16((size_t)(d.P > d.S ? d.P : d.S) * 4);
+  d.warp_bytes = (int)v2_warp_bytes(d);
+  d.cinv = (65536 + d.C - 1) / d.C;
 }
 
 __host__ inline bool v2_supported(const EvoParams &ep, const V2Dims &d) {
@@ -391,18 +402,14 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
                         int32_t *__restrict__ ovf_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64, H = dims.H, C = dims.C;
+  const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64, H = dims.H;
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
-  unsigned char *p = smem_raw + (size_t)wib * v2_warp_bytes(dims);
-  uint4 *lists = (uint4 *)p;  // S old + Snew children
-  p += (size_t)(S + Snew) * 16;
-  double *lpjs = (double *)p;
-  p += align16((size_t)(S + Snew) * 8);
-  uint32_t *hash = (uint32_t *)p;  // dedup hashes; survivor list of the merge afterwards
-  p += v2_hash_bytes(dims);
-  int32_t *iscr = (int32_t *)p;  // chosen parents (P); order of the merged set (S)
-  p += align16((size_t)(dims.P > S ? dims.P : S) * 4);
-  double *dsm = (double *)p;  // d_h = gp_h - 2 coef a_h of this datapoint, all H units
+  unsigned char *p = smem_raw + wib * dims.warp_bytes;
+  uint4 *lists = (uint4 *)p;                        // S old + Snew children
+  double *lpjs = (double *)(p + dims.off_lpj);      // their lpj, fp64
+  uint32_t *hash = (uint32_t *)(p + dims.off_hash);  // dedup hashes; survivor list of the merge afterwards
+  int32_t *iscr = (int32_t *)(p + dims.off_iscr);   // chosen parents (P); order of the merged set (S)
+  double *dsm = (double *)(p + dims.off_d);         // d_h = gp_h - 2 coef a_h of this datapoint, all H units
   const double coef = th.hdr->coef, m2c = -2.0 * coef;
   const double *__restrict__ G2 = th.G2;
   const double *__restrict__ gp = th.gp;
@@ -428,7 +435,14 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
     yy = warp_sum(yy);
     const double yyc = yy * coef;
     __syncwarp();  // the previous datapoint's readers of this warp's shared memory are done
-    for (int h = lane; h < H; h += 32) dsm[h] = fma(m2c, (double)a_row[h], gp[h]);  // coalesced read of the a row
+    if ((H & 1) == 0 && sizeof(T) == 8) {  // coalesced read of the a row, two units per lane
+      for (int h = 2 * lane; h < H; h += 64) {
+        const double2 av = *reinterpret_cast<const double2 *>(a_row + h), gv = *reinterpret_cast<const double2 *>(gp + h);
+        *reinterpret_cast<double2 *>(dsm + h) = make_double2(fma(m2c, av.x, gv.x), fma(m2c, av.y, gv.y));
+      }
+    } else {
+      for (int h = lane; h < H; h += 32) dsm[h] = fma(m2c, (double)a_row[h], gp[h]);
+    }
     __syncwarp();
     V2_PHASE_SYNC();
 
@@ -438,18 +452,18 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
       if (s < S) {
         lists[s] = make_uint4(0u, 0u, 0u, 0u);
         unsigned char *lb = (unsigned char *)(lists + s);
-        const uint64_t *st = Krow + (size_t)s * W64;
+        const uint32_t *st = (const uint32_t *)(Krow + (size_t)s * W64);  // 2 W64 half words
         int n = 0;
         double acc = yyc;
-        for (int w = 0; w < W64; ++w) {
-          uint64_t m = st[w];
+        for (int hw = 0; hw < 2 * W64; ++hw) {
+          uint32_t m = st[hw];
           while (m) {
-            const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-            const int h = (w << 6) + (lo ? __ffs((int)lo) - 1 : 31 + __ffs((int)hi));
+            const int h = (hw << 5) + __ffs((int)m) - 1;
             m &= m - 1;
             if (n < kV2MaxList) {
               acc += dsm[h];
               const double *g2 = G2 + (size_t)h * H;
+#pragma unroll 1
               for (int i = 0; i < n; ++i) acc += g2[lb[i]];
               lb[n] = (unsigned char)h;
             }
@@ -490,7 +504,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
       for (int j0 = 0; j0 < Sgen; j0 += 32) {
         const int j = j0 + lane;
         if (j < Sgen) {
-          const int src = cand_base + iscr[j / C];
+          const int src = cand_base + iscr[(j * dims.cinv) >> 16];  // j / C
           const unsigned char *pb = (const unsigned char *)(lists + src);  // the parent's list
           const int a = (int)pb[15];
           // flip counts (batch_sparseflip evo.py:310-329 as Binomial counts, mutate_sparseflip of estep_device.cuh)
@@ -529,10 +543,13 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
               ++t;
               const uint32_t pos = randint_u32(ri, (uint32_t)H);
               bool taken = false;
+#pragma unroll 1
               for (int i = 0; i < a; ++i) taken |= ((uint32_t)pb[i] == pos);
               int below = 0;
-              for (int q = 0; q < ka; ++q) {
-                const uint32_t z = (uint32_t)(add >> (8 * q)) & 0xFFu;
+              uint64_t aa = add;
+#pragma unroll 1
+              for (int q = 0; q < ka; ++q, aa >>= 8) {
+                const uint32_t z = (uint32_t)aa & 0xFFu;
                 taken |= (z == pos);
                 below += (z < pos) ? 1 : 0;
               }
@@ -586,17 +603,23 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
             }
             dl -= t1;
           }
-          for (int q = 0; q < ka; ++q) {
-            const uint32_t z = (uint32_t)(add >> (8 * q)) & 0xFFu;
-            double t1 = dsm[z];
-            const double *g2 = G2 + (size_t)z * H;
-            for (uint32_t mm = kept; mm;) {
-              const int i2 = __ffs((int)mm) - 1;
-              mm &= mm - 1;
-              t1 += g2[pb[i2]];
+          {
+            uint64_t aq = add;
+#pragma unroll 1
+            for (int q = 0; q < ka; ++q, aq >>= 8) {
+              const uint32_t z = (uint32_t)aq & 0xFFu;
+              double t1 = dsm[z];
+              const double *g2 = G2 + (size_t)z * H;
+              for (uint32_t mm = kept; mm;) {
+                const int i2 = __ffs((int)mm) - 1;
+                mm &= mm - 1;
+                t1 += g2[pb[i2]];
+              }
+              uint64_t a2 = add;
+#pragma unroll 1
+              for (int q2 = 0; q2 < q; ++q2, a2 >>= 8) t1 += g2[(uint32_t)a2 & 0xFFu];
+              dl += t1;
             }
-            for (int q2 = 0; q2 < q; ++q2) t1 += g2[(uint32_t)(add >> (8 * q2)) & 0xFFu];
-            dl += t1;
           }
           // the child's list: kept entries merged with the added positions, ascending
           const int child = S + g * Sgen + j;
@@ -604,7 +627,8 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
           if (nc <= kV2MaxList) {
             unsigned char *cb = (unsigned char *)(lists + child);
             int m = 0, q = 0;
-            uint32_t nextz = ka ? (uint32_t)add & 0xFFu : 256u;
+            uint64_t ar = add;  // the added positions not yet written, ascending from the low byte
+            uint32_t nextz = ka ? (uint32_t)ar & 0xFFu : 256u;
             for (uint32_t mm = kept; mm;) {
               const int i = __ffs((int)mm) - 1;
               mm &= mm - 1;
@@ -612,14 +636,13 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
               while (nextz < e) {
                 cb[m++] = (unsigned char)nextz;
                 ++q;
-                nextz = q < ka ? (uint32_t)(add >> (8 * q)) & 0xFFu : 256u;
+                ar >>= 8;
+                nextz = q < ka ? (uint32_t)ar & 0xFFu : 256u;
               }
               cb[m++] = (unsigned char)e;
             }
-            while (q < ka) {
-              cb[m++] = (unsigned char)((add >> (8 * q)) & 0xFFu);
-              ++q;
-            }
+#pragma unroll 1
+            for (; q < ka; ++q, ar >>= 8) cb[m++] = (unsigned char)((uint32_t)ar & 0xFFu);
             cb[15] = (unsigned char)m;
           }
           lpjs[child] = lpjs[src] + dl;

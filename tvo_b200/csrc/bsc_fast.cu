@@ -613,8 +613,9 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   }
   // list-based kernel (bsc_estep_v2.cuh) for sparse states at 64 <= H <= 256, randparents + sparseflip; the generic
   // kernel then takes the datapoints it handed back (overflow list) — or everything when the shape is not covered
-  V2Dims v2{S, dims.Snew, dims.Sgen, ep.P, ep.C, ep.G, dims.W64, H};
-  const size_t v2_smem = v2_warp_bytes(v2) * 8;
+  V2Dims v2{S, dims.Snew, dims.Sgen, ep.P, ep.C, ep.G, dims.W64, H, 0, 0, 0, 0, 0, 0};
+  v2_finish(v2);
+  const size_t v2_smem = (size_t)v2.warp_bytes * 8;
   const bool use_v2 = use_tab && v2_supported(ep, v2) && v2_smem <= (size_t)kMaxSmemFast && !g_disable_v2;
   const int eS = S <= 32 ? 1 : S <= 64 ? 2 : 4, eG = dims.Sgen <= 32 ? 1 : dims.Sgen <= 64 ? 2 : 4,
             eN = dims.Snew <= 32 ? 1 : dims.Snew <= 64 ? 2 : 4;
