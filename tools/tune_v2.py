@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Time the fused BSC E-step at the headline shape for several settings of tvo_bsc_estep_variant (tuning aid).
+usage (GPU box): python tools/tune_v2.py [N] [variant ...]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch as to
+import tvo_b200
+from tvo_b200 import _lib
+from tvo_b200.models import BSC
+from tvo_b200.variational import EVOVariationalStates
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 500000
+variants = [int(v, 0) for v in sys.argv[2:]] or [0]
+H, D, S = 256, 144, 64
+dev = to.device("cuda:0")
+tvo_b200._set_device(dev)
+g0 = to.Generator(device=dev).manual_seed(1234)
+Wgen = to.randn(D, H, dtype=to.float64, device=dev, generator=g0)
+W0 = Wgen + 0.5 * to.randn(D, H, dtype=to.float64, device=dev, generator=g0)
+s = (to.rand(N, H, device=dev, generator=g0) < 5.0 / H).double()
+Y = s @ Wgen.t() + to.randn(N, D, dtype=to.float64, device=dev, generator=g0)
+del s
+idx = to.arange(N, device=dev)
+for v in variants:
+    np.random.seed(0)
+    _lib.call("tvo_bsc_estep_variant", v)
+    model = BSC(H, D, W0, to.tensor([1.0], dtype=to.float64), to.full((H,), 1.0 / H, dtype=to.float64), precision=to.float64)
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", n_parents=16, n_generations=2, n_children=2,
+                              bitflip_frequency=1.0 / H, seed=2024)
+    for _ in range(6):  # same warm-up trajectory as bench.py (EM iterations from the 1/H init)
+        st.update_device(idx, Y, model); model.update_param_batch(idx, Y, st); model.update_param_epoch()
+    to.cuda.synchronize()
+    _lib.kernel_timing_enable(True)
+    ev = [to.cuda.Event(enable_timing=True) for _ in range(2)]
+    tot = 0.0
+    for _ in range(6):
+        ev[0].record(); st.update_device(idx, Y, model); ev[1].record()
+        model.update_param_batch(idx, Y, st); model.update_param_epoch()
+        to.cuda.synchronize(); tot += ev[0].elapsed_time(ev[1])
+    k_ms, k_n = _lib.kernel_timing_read(_lib.TIMED_ESTEP_EVO_BSC)
+    _lib.kernel_timing_enable(False)
+    print(f"variant {v:#x}: E-step {tot / 6:.3f} ms ({N / (tot / 6) / 1e3:.1f} M dp/s), kernel {k_ms / 6:.3f} ms/step, "
+          f"nsubs/dp {st._take_nsubs() / N / 6:.2f}", flush=True)
+_lib.call("tvo_bsc_estep_variant", 0)

@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(256, 4)
 estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                         int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
                         V2Dims dims, int64_t B, int D, unsigned long long *nsubs, int32_t *ovf_count,
-                        int32_t *__restrict__ ovf_list) {
+                        int32_t *__restrict__ ovf_list, uint32_t sync_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64, H = dims.H;
@@ -416,8 +416,14 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
   unsigned long long my_subs = 0;
 
   // the warps of a CTA walk the phases in lockstep (instruction-cache locality, see bsc_fast.cu)
-#define V2_PHASE_SYNC() __syncthreads()
+  int sync_id = 0;
+#define V2_PHASE_SYNC()                          \
+  do {                                           \
+    if ((sync_mask >> sync_id) & 1u) __syncthreads(); \
+    ++sync_id;                                   \
+  } while (0)
   for (int64_t b0 = (int64_t)blockIdx.x * wpb; b0 < B; b0 += (int64_t)gridDim.x * wpb) {
+    sync_id = 0;
     const bool active = b0 + wib < B;
     const int64_t b = active ? b0 + wib : 0;
     const int64_t row = idx ? idx[b] : row0 + b;
@@ -453,27 +459,47 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
         lists[s] = make_uint4(0u, 0u, 0u, 0u);
         unsigned char *lb = (unsigned char *)(lists + s);
         const uint32_t *st = (const uint32_t *)(Krow + (size_t)s * W64);  // 2 W64 half words
-        int n = 0;
-        double acc = yyc;
-        for (int hw = 0; hw < 2 * W64; ++hw) {
-          uint32_t m = st[hw];
-          while (m) {
-            const int h = (hw << 5) + __ffs((int)m) - 1;
-            m &= m - 1;
-            if (n < kV2MaxList) {
-              acc += dsm[h];
-              const double *g2 = G2 + (size_t)h * H;
-#pragma unroll 1
-              for (int i = 0; i < n; ++i) acc += g2[lb[i]];
-              lb[n] = (unsigned char)h;
-            }
-            ++n;
+        // which half words are non-empty and how many units are active; then ONE loop over the active units that
+        // re-reads a half word (an L1 hit) only when the current one is used up: the warp iterates max-over-lanes |s|
+        // times instead of once per non-empty half word of any lane
+        uint32_t nz = 0;
+        int ntot = 0;
+        if ((W64 & 1) == 0) {
+          for (int q = 0; q < W64 / 2; ++q) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(st + 4 * q);
+            nz |= ((v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u)) << (4 * q);
+            ntot += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+          }
+        } else {
+          for (int hw = 0; hw < 2 * W64; ++hw) {
+            const uint32_t v = st[hw];
+            nz |= (v ? 1u : 0u) << hw;
+            ntot += __popc(v);
           }
         }
-        if (n > kV2MaxList)
+        double acc = yyc;
+        if (ntot > kV2MaxList) {
           bail = true;
-        else
-          lb[15] = (unsigned char)n;
+          ntot = 0;
+        }
+        uint32_t m = 0;
+        int hw = 0;
+#pragma unroll 1
+        for (int n = 0; n < ntot; ++n) {
+          if (m == 0) {
+            hw = __ffs((int)nz) - 1;
+            nz &= nz - 1;
+            m = st[hw];
+          }
+          const int h = (hw << 5) + __ffs((int)m) - 1;
+          m &= m - 1;
+          acc += dsm[h];
+          const double *g2 = G2 + (size_t)h * H;
+#pragma unroll 1
+          for (int i = 0; i < n; ++i) acc += g2[lb[i]];
+          lb[n] = (unsigned char)h;
+        }
+        lb[15] = (unsigned char)ntot;
         lpjs[s] = acc;
       }
     }

@@ -19,6 +19,7 @@ namespace tvo {
 
 constexpr int kMaxSmemFast = 227 * 1024;
 constexpr int kMaxWarpsLarge = 12;  // warps per CTA of the one-CTA-per-SM E-step variant (large H*S)
+static unsigned g_v2_sync_mask = 0x41u;  // which phase barriers of the list-based kernel are on (tuning)
 static int g_disable_v2 = 0;         // tvo_bsc_estep_variant(1): generic kernel only (tests compare the two)
 
 int evo_params_from_cfg(const tvo_evo_config *cfg, int S, int H, EvoParams &ep, EstepDims &dims, const char *who);
@@ -639,7 +640,7 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
       const int grid2 = (int)max((int64_t)1, min((int64_t)(Bc + 7) / 8, (int64_t)sm_count() * occ2));
       kernel_timing_begin(TVO_TIMED_ESTEP_EVO_BSC, st, &tok);
       kern2<<<grid2, 256, v2_smem, st>>>(Y + c0 * ldY, ldY, A, idx ? idx + c0 : nullptr, c0, K, lpj, ws, ep, v2, Bc, D,
-                                         (unsigned long long *)nsubs, ovf_count, ovf_list);
+                                         (unsigned long long *)nsubs, ovf_count, ovf_list, g_v2_sync_mask);
       kernel_timing_end(tok, st);
       TVO_AFTER_LAUNCH("estep_evo_bsc_v2");
       // overflow datapoints: the generic kernel reads their count on the device (an empty list costs one idle launch)
@@ -713,7 +714,8 @@ int64_t tvo_bsc_estep_scratch_bytes(int64_t B, int32_t H, int32_t is_f64) {
   return B * ((int64_t)H * (is_f64 ? 8 : 4) + 4) + 32 + (int64_t)flip_table_bytes(H);
 }
 int tvo_bsc_estep_variant(int32_t generic_only) {
-  g_disable_v2 = generic_only ? 1 : 0;
+  g_disable_v2 = (generic_only & 1) ? 1 : 0;
+  if (generic_only & ~1) g_v2_sync_mask = (unsigned)generic_only >> 1;  // tuning: bits 1.. = phase-barrier mask
   return TVO_OK;
 }
 int64_t tvo_bsc_mstep_scratch_bytes(int64_t B, int32_t H, int32_t D, int32_t is_f64) {
