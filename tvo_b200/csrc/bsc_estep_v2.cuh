@@ -246,15 +246,18 @@ __device__ __forceinline__ uint64_t v2_ckey(const double *lpjs, int i) {
   return (sort_key((double)(T)lpjs[i]) & ~0xFFull) | (uint64_t)(255 - i);
 }
 
-template <int EPL>
-__device__ __forceinline__ void bitonic_desc_u64(uint64_t (&key)[EPL], int lane, int k_first) {
+// Fully unrolled (the rolled network spends half of its instructions on loop control and direction flags; the three
+// instances a shape class needs are ~600 instructions).  KFIRST = 2 sorts, KFIRST = 32*EPL merges a bitonic sequence.
+template <int EPL, int KFIRST>
+__device__ __forceinline__ void bitonic_desc_u64(uint64_t (&key)[EPL], int lane) {
   constexpr int MP = 32 * EPL;
-#pragma unroll 1
-  for (int k = k_first; k <= MP; k <<= 1) {
-#pragma unroll 1
+#pragma unroll
+  for (int k = KFIRST; k <= MP; k <<= 1) {
+#pragma unroll
     for (int j = k >> 1; j >= EPL; j >>= 1) {  // partner in another lane
       const int lm = j / EPL;
-      const bool want_max = ((lane & lm) == 0) == ((lane & (k / EPL)) == 0);
+      // j and k are multiples of EPL here, so the direction is a property of the lane, not of the element
+      const bool want_max = (((lane / lm) ^ (lane / (k / EPL))) & 1) == 0;
 #pragma unroll
       for (int r = 0; r < EPL; ++r) {
         const uint64_t o = __shfl_xor_sync(FULL, key[r], lm);
@@ -267,8 +270,7 @@ __device__ __forceinline__ void bitonic_desc_u64(uint64_t (&key)[EPL], int lane,
 #pragma unroll
         for (int r = 0; r < EPL; ++r) {
           if ((r & jj) == 0) {
-            const int e = lane * EPL + r;
-            const bool up = (e & k) == 0;  // best-first block
+            const bool up = k >= MP ? true : ((lane * EPL + r) & k) == 0;  // best-first block
             const uint64_t hi = key[r] > key[r ^ jj] ? key[r] : key[r ^ jj];
             const uint64_t lo = key[r] > key[r ^ jj] ? key[r ^ jj] : key[r];
             key[r] = up ? hi : lo;
@@ -289,7 +291,7 @@ __device__ __forceinline__ void v2_sort_survivors_ck(uint64_t *sk, int ns, int l
     key[r] = e < ns ? sk[e] : 0ull;
   }
   __syncwarp();
-  bitonic_desc_u64<EPL>(key, lane, 2);
+  bitonic_desc_u64<EPL, 2>(key, lane);
 #pragma unroll
   for (int r = 0; r < EPL; ++r) {
     const int e = lane * EPL + r;
@@ -315,7 +317,7 @@ __device__ __forceinline__ bool v2_select_merge_ck(const double *lpjs, uint64_t 
     const int e = lane * EPL + r;
     key[r] = e < S ? v2_ckey<T>(lpjs, e) : 0ull;
   }
-  bitonic_desc_u64<EPL>(key, lane, 2);
+  bitonic_desc_u64<EPL, 2>(key, lane);
   uint64_t wkey = 0;
 #pragma unroll
   for (int r = 0; r < EPL; ++r)
@@ -352,7 +354,7 @@ __device__ __forceinline__ bool v2_select_merge_ck(const double *lpjs, uint64_t 
       }
     }
     for (int bi = MP + lane; bi < ns; bi += 32) dropped = sk[bi] > dropped ? sk[bi] : dropped;  // survivors beyond MP
-    bitonic_desc_u64<EPL>(key, lane, MP);
+    bitonic_desc_u64<EPL, MP>(key, lane);
   }
   // 56-bit ties: adjacent elements of the result (ranks 0..S, the first excluded one included when it is held here) ...
   bool amb = false;
@@ -521,9 +523,9 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
       const int bits = index_bits(S_c);
       __syncwarp();
       if (g == 0)
-        randparents_sort<ES>(S_c, ep.P, bits, st, iscr, lane);
+        randparents_sort<ES, true>(S_c, ep.P, bits, st, iscr, lane);
       else
-        randparents_sort<EG>(S_c, ep.P, bits, st, iscr, lane);
+        randparents_sort<EG, true>(S_c, ep.P, bits, st, iscr, lane);
       __syncwarp();
       V2_PHASE_SYNC();
       st.tag = make_tag(ep.step, g, PUR_FLIP0);

@@ -104,7 +104,9 @@ __host__ __device__ inline int index_bits(int S_c) {
   return b;
 }
 
-template <int EPL>
+// UNROLL: the stage loops fully unrolled (list-based BSC kernel: half of the rolled network's instructions are loop
+// control); the generic kernels keep them rolled for code size.
+template <int EPL, bool UNROLL = false>
 __device__ __forceinline__ void randparents_sort(int S_c, int P, int bits, const Stream &st, int32_t *chosen, int lane) {
   constexpr int MP = 32 * EPL;
   uint32_t key[EPL];
@@ -133,9 +135,9 @@ __device__ __forceinline__ void randparents_sort(int S_c, int P, int bits, const
     const int e = lane * EPL + r;
     key[r] = e < S_c ? ((key[r] & himask) | (uint32_t)e) : 0xFFFFFFFFu;
   }
-#pragma unroll 1
+#pragma unroll(UNROLL ? 16 : 1)
   for (int k = 2; k <= MP; k <<= 1) {
-#pragma unroll 1
+#pragma unroll(UNROLL ? 16 : 1)
     for (int j = k >> 1; j >= EPL; j >>= 1) {  // partner in another lane
       const int lm = j / EPL;
       // j and k are multiples of EPL here, so the direction is a property of the lane, not of the element
