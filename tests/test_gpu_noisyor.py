@@ -246,3 +246,75 @@ def test_noisyor_estep_c4_shape_properties():
     ref = m64.log_pseudo_joint(Y[:5000], st.K[:5000])
     ok = ref > -1e29
     assert to.allclose(st.lpj[:5000][ok].double(), ref[ok], rtol=1e-4, atol=1e-4 * float(ref[ok].abs().max()))
+
+
+def test_noisyor_c4_shape_estep_batch_fitparents_oracle_subset():
+    """BASELINE configs[3] shape (NoisyOR D=100 H=64 S=64, fp32, crossover + randflip, P=8, G=1) with the REFERENCE's
+    parent selection `batch_fitparents` (batch-global normaliser, evo.py:404-406) inside a 20k-datapoint launch,
+    against the oracle on 12 of the datapoints.  The normaliser (m, T) is a function of the whole batch's lpj, so the
+    oracle takes it from the batch lpj (fit_norm of the same fp32 values); parents and children are then bit-identical
+    by construction of the stream, and the merged K sets must be equal (fp32 rounding may reorder a near-tie: one
+    datapoint of slack), lpj within 1e-4."""
+    tvo_b200._set_device(to.device(DEV))
+    rng = np.random.default_rng(17)
+    N, H, D, S, P = 20_000, 64, 100, 64, 8
+    W = (rng.random((D, H)) * 0.9 + 0.05).astype(np.float32)
+    pies = np.full(H, 2.0 / H, np.float32)
+    Y = (rng.random((N, D)) < 0.2).astype(np.uint8)
+    m = NoisyOR(H, D, dev(W), dev(pies), precision=to.float32)
+    o = om.NoisyOR(H, D, W, pies, precision=np.float32)
+    np.random.seed(2)
+    st = EVOVariationalStates(N, H, S, to.float32, "batch_fitparents", "randflip", P, 1, crossover=True, seed=9)
+    st.n_offset = 300
+    idx = to.arange(N, device=DEV)
+    Yd = dev(Y)
+    sub = np.array([0, 1, 2, 3, 500, 4097, 9999, 10000, 12345, 19997, 19998, 19999])
+    for step in range(2):
+        K_before = st.K.unpack()[dev(sub)].cpu().numpy()
+        lpj_batch = m.log_pseudo_joint(Yd, st.K).cpu().numpy()           # what the E-step re-scores (evo.py:95)
+        norm = oevo.fit_norm(lpj_batch)
+        lpj_old = lpj_batch[sub]
+        assert np.allclose(lpj_old, o.log_pseudo_joint(Y[sub], K_before), rtol=1e-4, atol=1e-4)
+        pidx = oevo.fitparents_idx(lpj_old, 300 + sub, P, 9, step, 0, norm=norm)
+        parents = oevo.take_parents(K_before, pidx)
+        children = oevo.mutate(parents, "cross_randflip", P - 1, None, None, 300 + sub, 9, step, 0)
+        new_l = o.log_pseudo_joint(Y[sub], children)
+        ost.set_redundant_lpj_to_low(children, new_l, K_before)
+        Kw, Lw = K_before.copy(), lpj_old.copy()
+        ost.update_states_for_batch(children, new_l, np.arange(len(sub)), Kw, Lw)
+        nsubs = st.update(idx, Yd, m)
+        assert 0 < nsubs <= N * S
+        got_K = st.K.unpack()[dev(sub)].cpu().numpy()
+        got_l = st.lpj[dev(sub)].cpu().numpy()
+        same = [set(map(bytes, got_K[i])) == set(map(bytes, Kw[i])) for i in range(len(sub))]
+        assert sum(same) >= len(sub) - 1, f"K sets differ from the oracle at step {step}: {same}"
+        assert np.allclose(np.sort(got_l, 1)[:, 4:], np.sort(Lw, 1)[:, 4:], rtol=1e-4, atol=1e-4)
+        assert bool((st.lpj[:, 1:] >= st.lpj[:, :-1]).all())
+
+
+def test_noisyor_c4_shape_slot_mstep_vs_oracle_tiled():
+    """The fp32 slot-form M-step kernel at the C4 shape with MORE THAN TWO FLUSHES per CTA (296 CTAs x 256 datapoints
+    per flush => 160k datapoints) against `om.NoisyOR`: the batch is 320 tiles of 500 distinct datapoints, the
+    statistics are additive, so the oracle evaluates the 500 and scales by 320 (fp32 tolerance 2e-4 of the largest
+    entry)."""
+    tvo_b200._set_device(to.device(DEV))
+    rng = np.random.default_rng(23)
+    n0, reps, H, D, S = 500, 320, 64, 100, 64
+    W = rng.random((D, H)) * 0.96 + 0.02
+    pies = np.full(H, 1.0 / H)
+    Y0 = (rng.random((n0, D)) < 0.25).astype(np.uint8)
+    K0 = (rng.random((n0, S, H)) < 1.5 / H).astype(np.uint8)
+    K0[:, 0] = 0
+    o = om.NoisyOR(H, D, W, pies, precision=np.float64)
+    lpj0 = o.log_pseudo_joint(Y0, K0)
+    o.update_param_batch(Y0, K0, lpj0)
+    m = NoisyOR(H, D, dev(W, to.float32), dev(pies, to.float32), precision=to.float32)
+    N = n0 * reps
+    K = dev(K0).repeat(reps, 1, 1)
+    Y = dev(Y0).repeat(reps, 1)
+    st = EVOVariationalStates(N, H, S, to.float32, "randparents", "randflip", 2, 1, 1, K_init=K)
+    st.lpj[:] = dev(lpj0, to.float32).repeat(reps, 1)
+    m.update_param_batch(to.arange(N, device=DEV), Y, st)
+    for got, want in ((m.Btilde, o.Btilde), (m.Ctilde, o.Ctilde), (m.new_pi, o.new_pi)):
+        want = want * reps
+        assert np.allclose(got.double().cpu().numpy(), want, rtol=2e-4, atol=2e-4 * np.abs(want).max())

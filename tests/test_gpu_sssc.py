@@ -241,3 +241,61 @@ def test_sssc_c3_shape_properties():
     m2.update_param_batch(idx[N // 2:], Y[N // 2:], st)
     assert to.allclose(full, m2._stats, rtol=1e-9, atol=1e-9 * float(full.abs().max()))
     m._check_overflow()
+
+
+def test_sssc_c3_shape_oracle_subset():
+    """BASELINE configs[2] shape (SSSC D=64 H=256 S=32, EVO randparents + sparseflip P=8 C=4 G=1, fp64) inside a
+    20k-datapoint launch, so that the wide-CTA tier (16 warps, 4 lanes per state) is the one running: E-step K
+    bit-exact and lpj to 1e-10 against the oracle on 10 of the datapoints, two consecutive E-steps; M-step statistics
+    of those datapoints against `om.SSSC` (same kernel tier: it is picked by the shape, not the batch size) and
+    additivity of the 20k launch over (subset, complement)."""
+    tvo_b200._set_device(to.device(DEV))
+    rng = np.random.default_rng(31)
+    N, H, D, S, P, Cn, G = 20_000, 256, 64, 32, 8, 4, 1
+    Wg = rng.standard_normal((D, H))
+    s = rng.random((N, H)) < 4.0 / H
+    Y = (s * rng.standard_normal((N, H))) @ Wg.T + (0.1 ** 0.5) * rng.standard_normal((N, D))
+    W0 = Wg + 0.1 * rng.standard_normal((D, H))
+    A = 0.05 * rng.standard_normal((H, H))
+    Psi = np.eye(H) + A @ A.T          # a full covariance: the state-dependent blocks are not diagonal
+    mus = 0.2 * rng.standard_normal(H)
+    pies = np.full(H, 4.0 / H)
+    m = SSSC(H, D, dev(W0), dev(np.array([0.1])), dev(mus), dev(Psi), dev(pies), precision=to.float64)
+    o = om.SSSC(H, D, W0, np.array([0.1]), mus, Psi, pies)
+    np.random.seed(0)
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", P, G, Cn, bitflip_frequency=1.0 / H, seed=77)
+    K0 = st.K.unpack().cpu().numpy()
+    sub = np.array([0, 1, 2, 777, 5000, 9999, 10000, 15001, 19998, 19999])
+    idx = to.arange(N, device=DEV)
+    Yd = dev(Y)
+    Kw = K0[sub]
+    sparsity = float(m._tvo_sparsity().item())
+    for step in range(2):
+        lpj = o.log_pseudo_joint(Y[sub], Kw)
+        new_s, new_l = oevo.evolve_states(lpj, Kw, lambda x: o.log_pseudo_joint(Y[sub], x), P, Cn, G, "randparents",
+                                          "sparseflip", sparsity, 1.0 / H, sub, 77, step)
+        Kw = Kw.copy()
+        ost.update_states_for_batch(new_s, new_l, np.arange(len(sub)), Kw, lpj)
+        nsubs = st.update(idx, Yd, m)
+        assert 0 < nsubs <= N * S
+        got = st.K.unpack()[dev(sub)].cpu().numpy()
+        assert np.array_equal(got, Kw), f"K differs from the oracle at step {step}"
+        assert np.allclose(st.lpj[dev(sub)].cpu().numpy(), lpj, rtol=1e-10, atol=1e-10 * np.abs(lpj).max())
+    # M-step: the subset against the oracle, then additivity of the full launch
+    names = ("_my_sum_xpt_s", "_my_sum_xpt_sz", "_my_sum_xpt_ssT", "_my_sum_xpt_szszT", "_my_sum_xpt_sz_xpt_szT",
+             "_my_sum_y_szT", "_my_sum_diag_yyT")
+    lp = st.lpj.cpu().numpy()
+    m.update_param_batch(dev(sub), Yd[dev(sub)], st)
+    o.update_param_batch(Y[sub], Kw, lp[sub])
+    for attr in names:
+        a, b = getattr(m, attr).cpu().numpy(), getattr(o, attr[len("_my_"):])
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-10 * max(1.0, np.abs(b).max())), attr
+    part = m._stats.clone()
+    comp = np.setdiff1d(np.arange(N), sub)
+    m.update_param_batch(dev(comp), Yd[dev(comp)], st)   # accumulates on top of the subset
+    both = m._stats.clone()
+    m._stats.zero_()
+    m.update_param_batch(idx, Yd, st)
+    assert to.allclose(m._stats, both, rtol=1e-10, atol=1e-10 * float(both.abs().max()))
+    assert float((both - part).abs().max()) > 0
+    m._check_overflow()
