@@ -317,7 +317,9 @@ int tvo_logsumexp_sum_f32(const float *lpj, int64_t stride_n, const int64_t *idx
  *      the M-step, <kappa>_q and <s>_q) for one chunk of datapoints; GEMMs on it are cuBLAS.
  *      M-step (sssc.py:366-452) stats layout (fp64, INCREMENTED):
  *      [y_szT^T (H*D) | sz_szT (H*H) | szszT (H*H) | ssT (H*H, upper triangle) | ssz (H*H) | s (H) | sz (H)
- *       | diag_yyT (D) | N | F]. ---- */
+ *       | diag_yyT (D) | N | F].  `with_ssz` is a bit set: 1 = also accumulate ssz (reformulated_psi_update),
+ *      2 = rows of Y with NaN take the restricted moments (data_estimator on incomplete data, sssc.py:563-597;
+ *      the statistics are then not meaningful and the caller discards them). ---- */
 int64_t tvo_sssc_theta_ws_bytes(int32_t H, int32_t D, int32_t is_f64);
 int64_t tvo_sssc_stats_len(int32_t H, int32_t D);
 int64_t tvo_sssc_scratch_bytes(int64_t B, int32_t H, int32_t D, int32_t is_f64);

@@ -746,3 +746,28 @@ def test_lpj2pjc_mean_posterior_golden():
     assert np.allclose(vu.lpj2pjc(dev(g["all_lpj"])).cpu().numpy(), g["pjc"], rtol=1e-12)
     assert np.allclose(vu.mean_posterior(dev(g["g"]), dev(g["all_lpj"])).cpu().numpy(), g["mean_post"], rtol=1e-11)
     assert np.allclose(vu.lpj2pjc(dev(g["all_lpj"], to.float32)).cpu().numpy(), g["pjc"], rtol=1e-4)
+
+
+def test_trainer_accepts_the_references_own_dataloader():
+    """The Trainer only iterates a loader and reads .dataset / .batch_size, so the REFERENCE's TVODataLoader class
+    (tvo/utils/data.py:14-58, from baseline/_ref — the unmodified reference staged for the benchmark's CPU arm) drives
+    tvo_b200 unchanged: same F trajectory as with this package's device-resident loader on CPU-resident data."""
+    import bench
+    if not bench.reference_installed():
+        pytest.skip("baseline/_ref not installed (python -c 'import __graft_entry__ as g; g.build()' stages it)")
+    bench._import_reference()
+    from tvo.utils.data import TVODataLoader as RefLoader
+    rng = np.random.default_rng(2)
+    N, H, D, S = 96, 10, 7, 6
+    W = rng.standard_normal((D, H))
+    Y = ((rng.random((N, H)) < 0.2) @ W.T + 0.3 * rng.standard_normal((N, D)))
+    K = rand_K(rng, N, S, H, p=0.25)
+    tvo_b200._set_device(to.device(DEV))
+    Fs = []
+    for loader in (RefLoader(to.tensor(Y), batch_size=32), TVODataLoader(dev(Y), batch_size=32)):
+        m = BSC(H, D, dev(W + 0.2), to.tensor([0.5], dtype=to.float64), to.full((H,), 0.2, dtype=to.float64),
+                precision=to.float64)
+        st = EVOVariationalStates(N, H, S, to.float64, "randparents", "randflip", 3, 1, 2, seed=4, K_init=dev(K))
+        tr = Trainer(m, loader, st)
+        Fs.append([tr.em_step()["train_F"] for _ in range(3)])
+    assert np.allclose(Fs[0], Fs[1], rtol=1e-12)

@@ -27,11 +27,11 @@ def test_k_init_file_npz_and_checkpoint_roundtrip(tmp_path):
     m = BSC(H, D, to.tensor(W, device=DEV), to.tensor([0.7], device=DEV), to.full((H,), 0.1, device=DEV), precision=to.float64)
     Y = to.tensor(rng.standard_normal((N, D)), device=DEV)
     st.update(to.arange(N, device=DEV), Y, m)
-    ck = str(tmp_path / "ckpt.npz")
+    ck = str(tmp_path / "ckpt")  # no suffix: save and load must agree on the file
     tio.save_checkpoint(ck, m, st, extra={"epoch": np.array(3)})
-    z = np.load(ck)
+    z = np.load(ck + ".npz")
     assert z["train_states"].dtype == np.uint8 and z["train_states"].shape == (N, S, H)   # reference layout on disk
-    assert set(["W", "pies", "sigma2", "train_lpj", "epoch"]) <= set(z.files)
+    assert set(["theta/W", "theta/pies", "theta/sigma2", "train_lpj", "epoch"]) <= set(z.files)  # H5Logger's names
     K1, l1 = st.K.unpack().clone(), st.lpj.clone()
     m2 = BSC(H, D, to.zeros(D, H, device=DEV), to.tensor([1.0], device=DEV), to.full((H,), 0.5, device=DEV), precision=to.float64)
     st2 = EVOVariationalStates(N, H, S, to.float64, "randparents", "randflip", 2, 1, 1)

@@ -299,3 +299,24 @@ def test_sssc_c3_shape_oracle_subset():
     assert to.allclose(m._stats, both, rtol=1e-10, atol=1e-10 * float(both.abs().max()))
     assert float((both - part).abs().max()) > 0
     m._check_overflow()
+
+
+def test_sssc_data_estimator_golden_with_missing_values():
+    """SSSC.data_estimator against the unmodified reference (tests/golden/sssc_estimator.npz, tools/make_golden.py):
+    complete data and data with NaNs — the reference computes kappa from the observed dimensions only
+    (sssc.py:563-597); a zero fill would give different reconstructions."""
+    g = load_golden("sssc_estimator.npz")
+    D, H = g["W"].shape
+    tvo_b200._set_device(to.device(DEV))
+    m = SSSC(H, D, dev(g["W"]), dev(g["sigma2"]), dev(g["mus"]), dev(g["Psi"]), dev(g["pies"]), precision=to.float64)
+    N, S = g["K"].shape[:2]
+    for tag, Y in (("full", g["Y"]), ("nan", g["Ynan"])):
+        st = EVOVariationalStates(N, H, S, to.float64, "randparents", "randflip", 2, 1, 1, K_init=dev(g["K"]))
+        lpj = m.log_pseudo_joint(dev(Y), st.K)
+        assert np.allclose(lpj.cpu().numpy(), g[f"lpj_{tag}"], rtol=1e-9, atol=1e-9)
+        st.lpj[:] = lpj
+        before = m._stats.clone()
+        est = m.data_estimator(to.arange(N, device=DEV), dev(Y), st)
+        assert np.allclose(est.cpu().numpy(), g[f"est_{tag}"], rtol=1e-9, atol=1e-9), tag
+        assert to.equal(m._stats, before)  # the scratch pass leaves the statistics alone
+    assert not np.allclose(g["est_full"], g["est_nan"])

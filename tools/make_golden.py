@@ -151,6 +151,34 @@ def golden_sssc():
             Psi_new=m.theta["Psi"], sigma2_new=m.theta["sigma2"], **acc)))
 
 
+def golden_sssc_estimator():
+    """SSSC.data_estimator (sssc.py:542-599) on complete data and on data with missing values (NaN): the reference
+    restricts W_s and the datapoint to the observed dimensions (sssc.py:563-597)."""
+    rng = np.random.default_rng(33)
+    N, D, H, S = 6, 8, 6, 7
+    W = rng.standard_normal((D, H))
+    A = rng.standard_normal((H, H)) * 0.3
+    Psi = A @ A.T + np.eye(H)
+    mus = rng.standard_normal(H)
+    pies = rng.uniform(0.1, 0.6, H)
+    sigma2 = np.array([0.4])
+    Y = rng.standard_normal((N, D)) * 1.5
+    Ynan = Y.copy()
+    Ynan[0, 2] = np.nan
+    Ynan[3, [0, 5, 7]] = np.nan
+    Ynan[5, 1] = np.nan
+    K = rand_states(rng, N, S, H, p=0.4, zero_row=True)
+    out = {}
+    for tag, data in (("full", Y), ("nan", Ynan)):
+        m = SSSC(H, D, to.tensor(W), to.tensor(sigma2), to.tensor(mus), to.tensor(Psi), to.tensor(pies), precision=to.float64)
+        Yt, Kt = to.tensor(data), to.tensor(K)
+        lpj = m.log_pseudo_joint(Yt, Kt)
+        est = m.data_estimator(to.arange(N), Yt, _States(Kt, lpj.clone()))
+        out[f"lpj_{tag}"], out[f"est_{tag}"] = lpj, est
+    np.savez(os.path.join(OUT, "sssc_estimator.npz"), **_np(dict(
+        W=W, Psi=Psi, mus=mus, pies=pies, sigma2=sigma2, Y=Y, Ynan=Ynan, K=K, **out)))
+
+
 def golden_mixtures():
     """GMM / PMM with FullEMSingleCauseModels (gmm.py:91-180, pmm.py:76-143, fullem.py:61-82): lpj, log_joint,
     free energy, accumulators after one batch, theta after the epoch update, F after a second E-step."""
@@ -340,7 +368,7 @@ def golden_tvae():
 
 if __name__ == "__main__":
     to.set_default_dtype(to.float32)
-    todo = {"bsc": golden_bsc, "noisyor": golden_noisyor, "sssc": golden_sssc, "dedup_merge": golden_dedup_merge,
+    todo = {"bsc": golden_bsc, "noisyor": golden_noisyor, "sssc": golden_sssc, "sssc_estimator": golden_sssc_estimator, "dedup_merge": golden_dedup_merge,
             "evo_stats": golden_evo_stats, "trainer": golden_trainer, "mixtures": golden_mixtures, "tvae": golden_tvae}
     for name in (sys.argv[1:] or list(todo)):  # python tools/make_golden.py [name ...]
         todo[name]()

@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(512)  // up to 16 warps: one CTA per SM at H =
 sssc_mstep_kernel(typename SsscModel<T>::Params p, const int64_t *__restrict__ idx, int64_t row0,
                   const uint64_t *__restrict__ K, int64_t k_stride_n, const T *__restrict__ lpj, int64_t lpj_stride_n,
                   double *__restrict__ stats, double *__restrict__ X_out, double *__restrict__ E_out,
-                  double *__restrict__ Yd_out, int64_t B, int S, size_t wbytes) {
+                  double *__restrict__ Yd_out, int64_t B, int S, size_t wbytes, int nan_aware) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int H = p.H, D = p.D, W64 = n_words(H);
@@ -519,9 +519,10 @@ sssc_mstep_kernel(typename SsscModel<T>::Params p, const int64_t *__restrict__ i
     accF += mx + log(se) + th.hdr->prior_sum - 0.5 * (double)dn * th.hdr->log_2pi_sigma2;
     accN += 1.0;
     __syncwarp();
-    // M-step moments with the batch's own y (NaNs were filled by the Trainer): the plain path
+    // M-step moments with the batch's own y (NaNs were filled by the Trainer): the plain path.  nan_aware
+    // (data_estimator on incomplete data, sssc.py:563-597): kappa from the observed dimensions only.
     const bool saved_nan = ctx.has_nan;
-    ctx.has_nan = false;
+    if (!nan_aware) ctx.has_nan = false;
     ctx.template for_each_state<true>(
         p, Ksm, S, W64, lane, [&](int s, double, int na, const SsscScratch &sc, int amax, int gl, int gs, unsigned gmask) {
           const double qs = q[s] / se;
@@ -742,7 +743,7 @@ int sssc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, i
     p.Y = Y + c0 * ldY;
     const int grid = (int)max((int64_t)1, min((int64_t)(Bc + wpb - 1) / wpb, (int64_t)sm_count() * max(occ, 1)));
     kern<<<grid, wpb * 32, wbytes * wpb, st>>>(p, idx ? idx + c0 : nullptr, c0, K, k_stride_n, lpj, lpj_stride_n, stats, X, E,
-                                              Yd, Bc, S, wbytes);
+                                              Yd, Bc, S, wbytes, (with_ssz & 2) ? 1 : 0);
     TVO_AFTER_LAUNCH("sssc_mstep");
     const double *Yp = f64 ? (const double *)(Y + c0 * ldY) : Yd;
     const int ldy = f64 ? (int)ldY : D;
@@ -751,7 +752,7 @@ int sssc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, i
     // sz_szT (H x H) += X^T X                                 (sssc.py:443)
     TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, H, H, Bc, &one, X, H, X, H, &one, stats + HD, H));
     // ssz (H x H row-major, [h_s][h_kappa]) += E^T X         (sssc.py:448-450); col-major view: ssz^T = X^T E
-    if (with_ssz)
+    if (with_ssz & 1)
       TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, H, H, Bc, &one, X, H, E, H, &one, stats + HD + 3 * HH, H));
   }
   TVO_CUDA(cudaFreeAsync(p.big, st));

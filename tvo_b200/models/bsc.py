@@ -248,8 +248,10 @@ class BSC(Optimized, Sampler, Reconstructor):
         return None
 
     def update_param_epoch(self) -> None:
-        """bsc.py:160-204.  One all-reduce of the packed statistics; the update itself is the
-        reference's torch code, run identically on every rank (no broadcast needed)."""
+        """bsc.py:160-204.  One all-reduce of the packed statistics, then the reference's closed forms on every rank and
+        ONE packed broadcast of the new theta from rank 0 (cuSOLVER / LAPACK solves are not bit-reproducible across
+        processes; the reference broadcasts W, pies, sigma2 separately, sanity.py:40).  The always-drawn noisy copy
+        of W (bsc.py:174) is broadcast as well, as in the reference: it is the fallback when the solve fails."""
         theta, policy = self.theta, self.policy
         D, H = self.shape
         all_reduce(self._stats)

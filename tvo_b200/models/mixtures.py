@@ -97,6 +97,10 @@ class _SingleCauseMixture(Optimized, Sampler, Reconstructor):
         _lib.call(f"tvo_mixture_lpj_{_lib.sfx(self._precision)}", self.KIND, _lib.ptr(Y), Y.stride(0), _lib.ptr(idx),
                   _lib.ptr(self._prepare()), _lib.ptr(out), out.stride(0), Y.shape[0], H, D, _lib.stream())
 
+    def _supports_fast(self, states) -> bool:
+        """The dense kernels evaluate all H single-cause states at once: only FullEMSingleCauseModels qualifies."""
+        return _is_single_cause(states)
+
     def _tvo_lpj_rows(self, states, idx: Tensor, batch: Tensor) -> None:
         """states.lpj[idx] = lpj(batch, identity) in place (FullEMSingleCauseModels.update)."""
         assert _is_single_cause(states)

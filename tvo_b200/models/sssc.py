@@ -242,7 +242,8 @@ class SSSC(Sampler, Optimized, Reconstructor):
         _lib.call(f"tvo_sssc_mstep_{_lib.sfx(self._precision)}", _lib.ptr(Y), Y.stride(0), _lib.ptr(idx), _lib.ptr(Kp),
                   0 if Kp.shape[0] == 1 and lpj.shape[0] != 1 else S * W, _lib.ptr(lpj), lpj.shape[1],
                   _lib.ptr(self._prepare()), _lib.ptr(self._stats), _lib.ptr(sc), sc.numel(), _lib.ptr(self._overflow),
-                  idx.numel(), S, H, D, int(self._reformulated_psi_update), _lib.stream())
+                  idx.numel(), S, H, D, int(self._reformulated_psi_update) | (2 if kwargs.get("_nan_aware") else 0),
+                  _lib.stream())
         return None
 
     def _invert_my_sum_xpt_ssT(self, ssT) -> to.Tensor:
@@ -323,12 +324,14 @@ class SSSC(Sampler, Optimized, Reconstructor):
         return (Y, hidden_state) if must_return_hidden_state else Y
 
     def data_estimator(self, idx: to.Tensor, batch: to.Tensor, states) -> to.Tensor:
-        """sssc.py:542-599: W <kappa>_q.  <kappa>_q is taken from a scratch M-step pass (statistics discarded)."""
+        """sssc.py:542-599: W <kappa>_q.  <kappa>_q is taken from a scratch M-step pass (statistics discarded).
+        Datapoints with missing values (NaN) are handled like the reference (sssc.py:563-597): kappa of a state is
+        computed from the observed dimensions only (the kernel's restricted path), not from zero-filled data."""
         D, H = self._shape
         saved = self._stats.clone()
-        Y = self._batch(to.nan_to_num(batch, nan=0.0)) if to.isnan(batch).any() else self._batch(batch)
+        Y = self._batch(batch)
         idx = idx.to(device=Y.device, dtype=to.int64).contiguous()
-        self.update_param_batch(idx, Y, states)
+        self.update_param_batch(idx, Y, states, _nan_aware=bool(to.isnan(Y).any()))
         self._stats.copy_(saved)
         sc = self._scratch
         B = idx.numel()

@@ -164,18 +164,10 @@ class _TVAE:
         """(D, Hn, ..., H0) (tvae.py:136-139)."""
         return tuple(reversed(self._net_shape))
 
-    def init_storage(self, S, Snew, batch_size):
-        pass
-
-    def init_epoch(self):
-        pass
-
-    def init_batch(self):
-        pass
-
-    @property
-    def sorted_by_lpj(self):
-        return {}
+    # NOTE: no log_pseudo_joint / init_storage / init_epoch / init_batch / sorted_by_lpj here.  The reference's TVAE is
+    # `Trainable`, not `Optimized` (tvae.py:86); `Optimized` is a runtime-checkable Protocol, so defining those names
+    # would make isinstance(model, Optimized) true and the Trainer / generic states paths would store pseudo-joints
+    # in states.lpj where free_energy expects log-joints.
 
     # ------------------------------------------------------------------------------------ decoder
     def _finish(self, x: Tensor) -> Tensor:  # output non-linearity
@@ -285,8 +277,6 @@ class _TVAE:
     def _log_pseudo_joint(self, data: Tensor, states) -> Tensor:
         packed, H, bc = as_packed(states)
         return self._lpj_packed(data, packed, H, k_broadcast=bc)
-
-    log_pseudo_joint = _log_pseudo_joint
 
     def _free_energy_from_logjoints(self, logjoints: Tensor) -> Tensor:
         Fn = to.logsumexp(logjoints, dim=1)

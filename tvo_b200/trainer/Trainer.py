@@ -23,7 +23,13 @@ from tvo_b200.variational import TVOVariationalStates
 
 
 def _fast(model, states) -> bool:
-    return hasattr(model, "_free_energy_device") and hasattr(states, "_nsubs_dev")
+    """tvo_b200 CUDA model + tvo_b200 states, and the model's device paths cover this kind of states (the mixtures'
+    dense kernels only do for FullEMSingleCauseModels; GMM / PMM with EVO / TVS / FullEM states take the generic
+    path like any third-party model, as the reference allows: gmm.py:91-102)."""
+    if not (hasattr(model, "_free_energy_device") and hasattr(states, "_nsubs_dev")):
+        return False
+    supports = getattr(model, "_supports_fast", None)
+    return True if supports is None else bool(supports(states))
 
 
 class Trainer:

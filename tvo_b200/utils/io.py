@@ -28,7 +28,11 @@ def read_arrays(path: str, *names: str) -> Dict[str, np.ndarray]:
         except ImportError as e:  # pragma: no cover
             raise RuntimeError(f"{path}: reading HDF5 needs h5py, which is not installed; use .npz") from e
         with h5py.File(path, "r") as f:
-            return {n: f[n][...] for n in (names or f.keys()) if n in f}
+            if names:
+                return {n: f[n][...] for n in names if n in f}
+            out: Dict[str, np.ndarray] = {}
+            f.visititems(lambda n, o: out.__setitem__(n, o[...]) if isinstance(o, h5py.Dataset) else None)
+            return out
     if path.endswith(".npy"):
         assert len(names) <= 1, ".npy holds one array"
         return {(names[0] if names else "data"): np.load(path, allow_pickle=False)}
@@ -61,13 +65,21 @@ def load_initial_states(path: str, N: int, S: int, H: int) -> to.Tensor:
     return K
 
 
+def _checkpoint_path(path: str) -> str:
+    """The file save_checkpoint writes for `path` (and load_checkpoint reads): .h5 / .hdf5 as given, anything else is
+    an .npz archive (the suffix is appended when missing)."""
+    return path if _is_h5(path) or path.endswith(".npz") else path + ".npz"
+
+
 def save_checkpoint(path: str, model=None, states=None, extra: Optional[Dict[str, np.ndarray]] = None) -> None:
-    """theta, K (uint8, gathered over ranks) and lpj under the names the reference logs
-    (_experiments.py:200-207: 'theta/<name>' flattened to '<name>', 'train_states', 'train_lpj').  Rank 0 writes."""
+    """theta, K (uint8, gathered over ranks) and lpj under the names the reference's H5Logger writes
+    (_experiments.py:200-207, H5Logger.py:94-123): 'theta/<name>' (an HDF5 group; the same slash-separated key in an
+    .npz), 'train_states', 'train_lpj'.  Rank 0 writes.  The tvo.exp layer itself (ExpConfig, Training / Testing,
+    H5Logger) is out of scope; this is the file format only."""
     out: Dict[str, np.ndarray] = dict(extra or {})
     if model is not None:
         for k, v in model.theta.items():
-            out[k] = v.detach().cpu().numpy()
+            out["theta/" + k] = v.detach().cpu().numpy()
     if states is not None:
         K = gather_from_processes(states.K.unpack())
         lpj = gather_from_processes(states.lpj)
@@ -88,17 +100,18 @@ def save_checkpoint(path: str, model=None, states=None, extra: Optional[Dict[str
         return
     tmp = path + ".tmp.npz"
     np.savez(tmp, **out)
-    os.replace(tmp, path if path.endswith(".npz") else path + ".npz")
+    os.replace(tmp, _checkpoint_path(path))
 
 
 def load_checkpoint(path: str, model=None, states=None) -> Dict[str, np.ndarray]:
     """Inverse of save_checkpoint: theta written in place (model.theta tensors keep their identity), K packed
     onto the device, lpj restored.  Returns every array of the file."""
-    arrs = read_arrays(path)
+    arrs = read_arrays(_checkpoint_path(path))
     if model is not None:
         for k, v in model.theta.items():
-            if k in arrs:
-                v.copy_(to.from_numpy(arrs[k]).to(device=v.device, dtype=v.dtype))
+            src = arrs.get("theta/" + k, arrs.get(k))  # the reference's layout, or the flat names of older files
+            if src is not None:
+                v.copy_(to.from_numpy(np.asarray(src)).to(device=v.device, dtype=v.dtype))
     if states is not None and "train_states" in arrs:
         lo, hi = my_shard(arrs["train_states"].shape[0])
         states.K = to.from_numpy(np.ascontiguousarray(arrs["train_states"][lo:hi]))

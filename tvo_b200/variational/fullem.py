@@ -49,7 +49,8 @@ class FullEM(TVOVariationalStates):
 
     def update_device(self, idx: Tensor, batch: Tensor, model) -> None:
         idx = idx.to(device=self.lpj.device, dtype=to.int64).contiguous()
-        if hasattr(model, "_tvo_lpj_rows"):
+        supports = getattr(model, "_supports_fast", None)
+        if hasattr(model, "_tvo_lpj_rows") and (supports is None or supports(self)):
             model._tvo_lpj_rows(self, idx, batch)
         else:
             lpj_fn = model.log_pseudo_joint if isinstance(model, Optimized) else model.log_joint
