@@ -82,6 +82,8 @@ void tvo_reset_launch_count(void);
  * recorded events and returns the summed duration and the number of launches of kernel `which`. */
 #define TVO_TIMED_ESTEP_EVO_BSC 1 /* estep_evo_bsc_gram_kernel / estep_evo_bsc_kernel */
 #define TVO_TIMED_BSC_MSTEP 2     /* bsc_mstep_kernel */
+#define TVO_TIMED_BSC_GEMM_YW 3   /* bsc_gemm_yw_kernel: a = Y W of the Gram-form E-step */
+#define TVO_TIMED_BSC_GEMM_ETY 4  /* bsc_gemm_ety_kernel: WpT += E^T Y of the M-step */
 void tvo_kernel_timing_enable(int32_t on);
 int tvo_kernel_timing_read(int32_t which, double *total_ms, int64_t *launches);
 int tvo_device_sm_count(int *out);

@@ -131,3 +131,38 @@ def test_v2_incremental_lpj_equals_full_rescore():
         assert bool((st.lpj[:, 1:] >= st.lpj[:, :-1]).all())
         rows = to.cat([idx[:, None, None].expand(-1, S, 1), st._Kp], dim=2).reshape(N * S, -1)
         assert to.unique(rows, dim=0).shape[0] == N * S  # no duplicate state inside any K_n
+
+
+@pytest.mark.parametrize("N", [1, 15, 17, 64, 200, 4099])
+def test_own_gemms_match_library(N):
+    """The hand-written TMA + FP64 tensor-core GEMMs (csrc/bsc_gemm.cuh: a = Y W with ||y||^2 for the E-step,
+    WpT += E^T Y for the M-step) against the library GEMM path (tvo_bsc_estep_variant bit 16) on the same inputs,
+    including partial 64-row tiles and partial 16-datapoint chunks: identical K, lpj / statistics to 1e-12."""
+    rng = np.random.default_rng(N)
+    H, D, S = 256, 144, 16
+    W, pies, Y, K = make(rng, N, H, D, S, 4.0 / H, 4.0 / H)
+    tvo_b200._set_device(to.device(DEV))
+    out = {}
+    for variant in (0, 0x10000):
+        _lib.call("tvo_bsc_estep_variant", variant)
+        try:
+            m = BSC(H, D, dev(W), to.tensor([0.9], dtype=to.float64), dev(pies), precision=to.float64)
+            st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", 4, 2, 2, bitflip_frequency=1.0 / H,
+                                      seed=8, K_init=dev(K))
+            idx = to.arange(N, device=DEV)
+            _lib.reset_launch_count()
+            nsubs = st.update(idx, dev(Y), m)
+            m.update_param_batch(idx, dev(Y), st)
+            out[variant] = (st.K.unpack().cpu().numpy(), st.lpj.cpu().numpy().copy(), nsubs, m._stats.cpu().numpy().copy())
+        finally:
+            _lib.call("tvo_bsc_estep_variant", 0)
+    a, b = out[0], out[0x10000]
+    assert np.array_equal(a[0], b[0]) and a[2] == b[2]
+    assert np.allclose(a[1], b[1], rtol=1e-12, atol=1e-10)
+    assert np.allclose(a[3], b[3], rtol=1e-12, atol=1e-12 * np.abs(b[3]).max())
+    # and against a plain fp64 product of the same operands
+    lp = to.as_tensor(a[1], device=DEV)
+    q = to.softmax(lp, dim=1)
+    E = (q[:, :, None] * to.as_tensor(a[0], device=DEV).double()).sum(dim=1)
+    WpT = (E.t() @ dev(Y)).cpu().numpy()
+    assert np.allclose(a[3][: H * D].reshape(H, D), WpT, rtol=1e-10, atol=1e-10 * np.abs(WpT).max())

@@ -32,14 +32,19 @@ for v in variants:
         st.update_device(idx, Y, model); model.update_param_batch(idx, Y, st); model.update_param_epoch()
     to.cuda.synchronize()
     _lib.kernel_timing_enable(True)
-    ev = [to.cuda.Event(enable_timing=True) for _ in range(2)]
-    tot = 0.0
+    ev = [to.cuda.Event(enable_timing=True) for _ in range(4)]
+    tot = totm = tote = 0.0
     for _ in range(6):
         ev[0].record(); st.update_device(idx, Y, model); ev[1].record()
-        model.update_param_batch(idx, Y, st); model.update_param_epoch()
-        to.cuda.synchronize(); tot += ev[0].elapsed_time(ev[1])
+        model.update_param_batch(idx, Y, st); ev[2].record(); model.update_param_epoch(); ev[3].record()
+        to.cuda.synchronize(); tot += ev[0].elapsed_time(ev[1]); totm += ev[1].elapsed_time(ev[2]); tote += ev[2].elapsed_time(ev[3])
     k_ms, k_n = _lib.kernel_timing_read(_lib.TIMED_ESTEP_EVO_BSC)
+    g_ms, g_n = _lib.kernel_timing_read(_lib.TIMED_BSC_GEMM_YW)
+    m_ms, _ = _lib.kernel_timing_read(_lib.TIMED_BSC_MSTEP)
+    ge_ms, _ = _lib.kernel_timing_read(_lib.TIMED_BSC_GEMM_ETY)
+    print(f"   M-step {totm / 6:.3f} ms (kernel {m_ms / 6:.3f}, own E^T Y GEMM {ge_ms / 6:.3f}), epoch update {tote / 6:.3f} ms", flush=True)
     _lib.kernel_timing_enable(False)
     print(f"variant {v:#x}: E-step {tot / 6:.3f} ms ({N / (tot / 6) / 1e3:.1f} M dp/s), kernel {k_ms / 6:.3f} ms/step, "
-          f"nsubs/dp {st._take_nsubs() / N / 6:.2f}", flush=True)
+          f"own GEMM {g_ms / 6:.3f} ms/step ({g_n} launches), nsubs/dp {st._take_nsubs() / N / 6:.2f}, "
+          f"F/N {float(model._last_F) / N:.9f}", flush=True)
 _lib.call("tvo_bsc_estep_variant", 0)

@@ -188,7 +188,7 @@ def reset_launch_count():
     lib().tvo_reset_launch_count()
 
 
-TIMED_ESTEP_EVO_BSC, TIMED_BSC_MSTEP = 1, 2
+TIMED_ESTEP_EVO_BSC, TIMED_BSC_MSTEP, TIMED_BSC_GEMM_YW, TIMED_BSC_GEMM_ETY = 1, 2, 3, 4
 
 
 def kernel_timing_enable(on=True):

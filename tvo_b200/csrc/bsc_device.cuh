@@ -36,9 +36,17 @@ template <typename T>
 __host__ __device__ inline size_t bsc_gp_off(int H, int D) {
   return bsc_gram2_off<T>(H, D) + (size_t)H * H * sizeof(double);
 }
+// Wg: W in the operand layout of the hand-written FP64 tensor-core GEMM a = Y W (bsc_gemm.cuh): [k/4][h][k%4] doubles,
+// k zero-padded to a multiple of 16, so that a K-chunk is one contiguous bulk copy and a warp's B fragments are
+// contiguous 256-byte shared-memory reads.
+__host__ __device__ inline int bsc_kpad16(int D) { return (D + 15) & ~15; }
+template <typename T>
+__host__ __device__ inline size_t bsc_wg_off(int H, int D) {
+  return bsc_gp_off<T>(H, D) + align16((size_t)H * sizeof(double));
+}
 template <typename T>
 __host__ __device__ inline size_t bsc_ws_bytes(int H, int D) {
-  return bsc_gp_off<T>(H, D) + align16((size_t)H * sizeof(double));
+  return bsc_wg_off<T>(H, D) + (size_t)bsc_kpad16(D) * H * sizeof(double);
 }
 
 template <typename T>
@@ -49,6 +57,7 @@ struct BscTheta {
   const double *G; // H x H Gram matrix W^T W (fp64)
   const double *G2;  // 2 coef G
   const double *gp;  // coef G_hh + prior_h
+  const double *Wg;  // [kpad16/4][H][4]: W for the tensor-core GEMM
   int Dpad;
 };
 template <typename T>
@@ -61,6 +70,7 @@ __host__ __device__ inline BscTheta<T> bsc_theta_view(const void *ws, int H, int
   t.G = (const double *)(p + bsc_gram_off<T>(H, D));
   t.G2 = (const double *)(p + bsc_gram2_off<T>(H, D));
   t.gp = (const double *)(p + bsc_gp_off<T>(H, D));
+  t.Wg = (const double *)(p + bsc_wg_off<T>(H, D));
   t.Dpad = bsc_dpad(D);
   return t;
 }
@@ -82,6 +92,15 @@ __global__ void bsc_prepare_kernel(const T *__restrict__ W, const T *__restrict_
   for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
     const T pi = pies[n_pies == 1 ? 0 : h];
     prior[h] = log(pi / (T(1) - pi));
+  }
+  {
+    double *Wg = (double *)(p + bsc_wg_off<T>(H, D));
+    const size_t nwg = (size_t)bsc_kpad16(D) * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwg; i += (size_t)gridDim.x * blockDim.x) {
+      const int kk = (int)(i & 3), h = (int)((i >> 2) % H), k4 = (int)((i >> 2) / H);
+      const int d = 4 * k4 + kk;
+      Wg[i] = d < D ? (double)W[(size_t)d * H + h] : 0.0;
+    }
   }
   // G = W^T W in fp64 (read straight from W so that it does not depend on Wt being complete)
   double *G = (double *)(p + bsc_gram_off<T>(H, D));

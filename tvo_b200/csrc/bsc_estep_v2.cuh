@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256, 4)
 estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                         int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
                         V2Dims dims, int64_t B, int D, unsigned long long *nsubs, int32_t *ovf_count,
-                        int32_t *__restrict__ ovf_list, uint32_t sync_mask) {
+                        int32_t *__restrict__ ovf_list, uint32_t sync_mask, const double *__restrict__ yy_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64, H = dims.H;
@@ -435,12 +435,17 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
     const T *__restrict__ a_row = A + b * (int64_t)H;
     double yy = 0.0;
     bool bail = !active;  // idle warps only keep the barriers company
-    for (int d = lane; d < D; d += 32) {
-      const double v = (double)y[d];
-      bail |= (v != v);
-      yy += v * v;
+    if (yy_in) {  // ||y||^2 from the GEMM's epilogue (NaN if y has a NaN): y itself is not read here
+      yy = yy_in[b];
+      bail |= (yy != yy);
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        const double v = (double)y[d];
+        bail |= (v != v);
+        yy += v * v;
+      }
+      yy = warp_sum(yy);
     }
-    yy = warp_sum(yy);
     const double yyc = yy * coef;
     __syncwarp();  // the previous datapoint's readers of this warp's shared memory are done
     if ((H & 1) == 0 && sizeof(T) == 8) {  // coalesced read of the a row, two units per lane

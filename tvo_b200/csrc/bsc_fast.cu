@@ -14,12 +14,14 @@
 
 #include "bsc_device.cuh"
 #include "bsc_estep_v2.cuh"
+#include "bsc_gemm.cuh"
 
 namespace tvo {
 
 constexpr int kMaxSmemFast = 227 * 1024;
 constexpr int kMaxWarpsLarge = 12;  // warps per CTA of the one-CTA-per-SM E-step variant (large H*S)
 static unsigned g_v2_sync_mask = 0x41u;  // which phase barriers of the list-based kernel are on (tuning)
+static int g_library_gemm = 0;  // tvo_bsc_estep_variant bit 16: cuBLAS instead of the hand-written GEMMs (tests)
 static int g_disable_v2 = 0;         // tvo_bsc_estep_variant(1): generic kernel only (tests compare the two)
 
 int evo_params_from_cfg(const tvo_evo_config *cfg, int S, int H, EvoParams &ep, EstepDims &dims, const char *who);
@@ -66,20 +68,21 @@ static int gemm_A(cublasHandle_t h, const float *Wt, int Dpad, const float *Y, i
 // per-device context, grown on demand and kept.  (A cudaMallocAsync / cudaFreeAsync pair per call hands the memory
 // back to the driver at every synchronisation with the default release threshold — measured as sporadic host-side
 // stalls of tens of ms per E-step.)  Calls on one device are serialised by the boundary's threading contract.
-static void *g_stage[64];
-static size_t g_stage_bytes[64];
-static int stage_buffer(size_t bytes, uint64_t **out) {
+// slot 0: the E-step's staging rows; slot 1: the slab partials of the M-step GEMM (22 MB at the headline shape)
+static void *g_stage[2][64];
+static size_t g_stage_bytes[2][64];
+static int stage_buffer(size_t bytes, uint64_t **out, int slot = 0) {
   int dev = 0;
   TVO_CUDA(cudaGetDevice(&dev));
   TVO_REQUIRE(dev >= 0 && dev < 64, "stage buffer: device index %d out of range", dev);
-  if (g_stage_bytes[dev] < bytes) {
-    if (g_stage[dev]) TVO_CUDA(cudaFree(g_stage[dev]));  // synchronises: no kernel still uses the old rows
-    g_stage[dev] = nullptr;
-    g_stage_bytes[dev] = 0;
-    TVO_CUDA(cudaMalloc(&g_stage[dev], bytes));
-    g_stage_bytes[dev] = bytes;
+  if (g_stage_bytes[slot][dev] < bytes) {
+    if (g_stage[slot][dev]) TVO_CUDA(cudaFree(g_stage[slot][dev]));  // synchronises: no kernel still uses the old rows
+    g_stage[slot][dev] = nullptr;
+    g_stage_bytes[slot][dev] = 0;
+    TVO_CUDA(cudaMalloc(&g_stage[slot][dev], bytes));
+    g_stage_bytes[slot][dev] = bytes;
   }
-  *out = (uint64_t *)g_stage[dev];
+  *out = (uint64_t *)g_stage[slot][dev];
   return TVO_OK;
 }
 
@@ -550,16 +553,18 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   TVO_REQUIRE(Y && K && lpj && ws && cfg && nsubs, "estep_evo_bsc: null pointer");
   const int64_t per = estep_scratch_per_dp<T>(H);
   // scratch layout: [sparseflip table (flip_table_bytes(H), only when it fits)] [overflow counter (16 B) + overflow
-  // list of the list-based kernel (4 B per datapoint of a chunk)] [a = W^T y rows]
+  // list of the list-based kernel (4 B per datapoint of a chunk)] [||y||^2 (8 B per datapoint)] [a = W^T y rows]
   const bool sparse = cfg->mutation == TVO_MUT_SPARSEFLIP || cfg->mutation == TVO_MUT_CROSS_SPARSEFLIP;
   const int64_t tab_bytes = sparse && scratch && sparsity ? (int64_t)flip_table_bytes(H) : 0;
-  const bool use_tab = tab_bytes > 0 && scratch_bytes >= tab_bytes + 32 + (per + 4) * min((int64_t)1024, B);
-  int64_t cap = !scratch ? 0 : use_tab ? (scratch_bytes - tab_bytes - 32) / (per + 4) : scratch_bytes / per;
+  const bool use_tab = tab_bytes > 0 && scratch_bytes >= tab_bytes + 48 + (per + 12) * min((int64_t)1024, B);
+  int64_t cap = !scratch ? 0 : use_tab ? (scratch_bytes - tab_bytes - 48) / (per + 12) : scratch_bytes / per;
   if (cap > B) cap = B;
   const int64_t ovf_bytes = use_tab ? (int64_t)align16((size_t)(16 + 4 * cap)) : 0;
+  const int64_t yy_bytes = use_tab ? (int64_t)align16((size_t)(8 * cap)) : 0;
   int32_t *ovf_count = use_tab ? (int32_t *)((unsigned char *)scratch + tab_bytes) : nullptr;
   int32_t *ovf_list = use_tab ? ovf_count + 4 : nullptr;
-  unsigned char *scratch_a = (unsigned char *)scratch + (use_tab ? tab_bytes + ovf_bytes : 0);
+  double *yy_buf = use_tab ? (double *)((unsigned char *)scratch + tab_bytes + ovf_bytes) : nullptr;
+  unsigned char *scratch_a = (unsigned char *)scratch + (use_tab ? tab_bytes + ovf_bytes + yy_bytes : 0);
   if (cap < 1024 && cap < B)  // no (useful) scratch: direct column-walk form
     return estep_evo_bsc_direct<T>(Y, ldY, idx, K, lpj, ws, cfg, sparsity, B, S, H, D, nsubs, stream);
   EvoParams ep;
@@ -629,10 +634,22 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
     TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, 256, v2_smem));
     occ2 = max(occ2, 1);
   }
+  // a = Y W: the hand-written TMA + FP64 tensor-core kernel (bsc_gemm.cuh; also ||y||^2, so that the list-based
+  // kernel does not read Y), the library GEMM for shapes it does not cover and for the fp32 mode
+  const bool own_gemm = sizeof(T) == 8 && yy_buf && !g_library_gemm && gemm_yw_supported(H, D, ldY, Y);
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
     const int Bc = (int)min(cap, B - c0);
-    rc = gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, A, Bc, H, D);
-    if (rc) return rc;
+    if (own_gemm) {
+      void *tokg;
+      kernel_timing_begin(TVO_TIMED_BSC_GEMM_YW, st, &tokg);
+      cudaError_t ge = launch_gemm_yw((const double *)(Y + c0 * ldY), ldY, th.Wg, (double *)A, yy_buf, Bc, H, D, sm_count(), st);
+      kernel_timing_end(tokg, st);
+      if (ge != cudaSuccess) return set_error(TVO_ECUDA, "launch bsc_gemm_yw: %s", cudaGetErrorString(ge));
+      count_launch();
+    } else {
+      rc = gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, A, Bc, H, D);
+      if (rc) return rc;
+    }
     const int grid = (int)max((int64_t)1, min((int64_t)(Bc + wpb - 1) / wpb, (int64_t)sm_count() * occ));
     void *tok;
     if (use_v2) {
@@ -640,7 +657,8 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
       const int grid2 = (int)max((int64_t)1, min((int64_t)(Bc + 7) / 8, (int64_t)sm_count() * occ2));
       kernel_timing_begin(TVO_TIMED_ESTEP_EVO_BSC, st, &tok);
       kern2<<<grid2, 256, v2_smem, st>>>(Y + c0 * ldY, ldY, A, idx ? idx + c0 : nullptr, c0, K, lpj, ws, ep, v2, Bc, D,
-                                         (unsigned long long *)nsubs, ovf_count, ovf_list, g_v2_sync_mask);
+                                         (unsigned long long *)nsubs, ovf_count, ovf_list, g_v2_sync_mask,
+                                         own_gemm ? yy_buf : nullptr);
       kernel_timing_end(tok, st);
       TVO_AFTER_LAUNCH("estep_evo_bsc_v2");
       // overflow datapoints: the generic kernel reads their count on the device (an empty list costs one idle launch)
@@ -696,10 +714,23 @@ int bsc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, in
                                        stats, E, Yd, Bc, S, H, D, exact, wbytes);
     kernel_timing_end(tok, st);
     TVO_AFTER_LAUNCH("bsc_mstep");
-    // WpT (H x D, row-major) += E^T (H x Bc) * Y (Bc x D)     (bsc.py:145,153)
+    // WpT (H x D, row-major) += E^T (H x Bc) * Y (Bc x D)     (bsc.py:145,153): the hand-written TMA + FP64
+    // tensor-core kernel (bsc_gemm.cuh, deterministic slab reduction), the library GEMM for shapes it does not cover
     const double *Yp = sizeof(T) == 8 ? (const double *)(Y + c0 * ldY) : Yd;
     const int ldy = sizeof(T) == 8 ? (int)ldY : D;
-    TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, D, H, Bc, &one, Yp, ldy, E, H, &one, stats, D));
+    if (!g_library_gemm && gemm_ety_supported(H, D, ldy, Yp, E)) {
+      uint64_t *part = nullptr;
+      rc = stage_buffer(gemm_ety_part_bytes(H, D, sm_count()), &part, 1);
+      if (rc) return rc;
+      void *tokg;
+      kernel_timing_begin(TVO_TIMED_BSC_GEMM_ETY, st, &tokg);
+      cudaError_t ge = launch_gemm_ety(E, Yp, ldy, (double *)part, stats, Bc, H, D, sm_count(), st);
+      kernel_timing_end(tokg, st);
+      if (ge != cudaSuccess) return set_error(TVO_ECUDA, "launch bsc_gemm_ety: %s", cudaGetErrorString(ge));
+      count_launch(2);
+    } else {
+      TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, D, H, Bc, &one, Yp, ldy, E, H, &one, stats, D));
+    }
   }
   return TVO_OK;
 }
@@ -711,11 +742,12 @@ using namespace tvo;
 extern "C" {
 int64_t tvo_bsc_stats_len(int32_t H, int32_t D) { return (int64_t)H * D + (int64_t)H * H + H + 3; }
 int64_t tvo_bsc_estep_scratch_bytes(int64_t B, int32_t H, int32_t is_f64) {
-  return B * ((int64_t)H * (is_f64 ? 8 : 4) + 4) + 32 + (int64_t)flip_table_bytes(H);
+  return B * ((int64_t)H * (is_f64 ? 8 : 4) + 12) + 48 + (int64_t)flip_table_bytes(H);
 }
 int tvo_bsc_estep_variant(int32_t generic_only) {
   g_disable_v2 = (generic_only & 1) ? 1 : 0;
-  if (generic_only & ~1) g_v2_sync_mask = (unsigned)generic_only >> 1;  // tuning: bits 1.. = phase-barrier mask
+  g_library_gemm = (generic_only & 0x10000) ? 1 : 0;
+  if (generic_only & 0xFFFE) g_v2_sync_mask = ((unsigned)generic_only & 0xFFFFu) >> 1;  // tuning: phase-barrier mask
   return TVO_OK;
 }
 int64_t tvo_bsc_mstep_scratch_bytes(int64_t B, int32_t H, int32_t D, int32_t is_f64) {
