@@ -161,6 +161,17 @@ int tvo_select_topS_f32(const uint64_t *new_states, const float *new_lpj, uint64
                         const int64_t *idx, int64_t B, int32_t S_new, int32_t S, int32_t H, int64_t *nsubs,
                         void *stream);
 
+/* ---- BSC.update_param_epoch (bsc.py:160-204) on the device.  tvo_bsc_symmetrize expands the accumulated upper
+ *      triangle of my_Wq to the full matrix the solve wants; tvo_bsc_epoch_finish turns the solution sol (H x D,
+ *      row-major, = W^T; NULL when the solve failed) and the reduced statistics into the new theta IN PLACE, with
+ *      fix_theta (sanity.py:76-88) applied: non-finite W entries <- W_noisy (bsc.py:174), pi clamped to
+ *      [1e-5, 1-1e-5], sigma2 >= 1e-5, non-finite pi / sigma2 keep their old values. ---- */
+int tvo_bsc_symmetrize(const double *upper, double *full, int32_t H, void *stream);
+int tvo_bsc_epoch_finish_f64(const double *stats, const double *sol, const double *W_noisy, double *W, double *pies,
+                             int32_t n_pies, double *sigma2, int32_t H, int32_t D, void *stream);
+int tvo_bsc_epoch_finish_f32(const double *stats, const double *sol, const float *W_noisy, float *W, float *pies,
+                             int32_t n_pies, float *sigma2, int32_t H, int32_t D, void *stream);
+
 /* ---- fused E-step for BSC: replaces EVOVariationalStates.update (evo.py:80-115) end to end:
  *      re-score K under theta, G generations of select+mutate+score with the children kept in
  *      shared memory, dedup against the original K, top-S merge, nsubs.

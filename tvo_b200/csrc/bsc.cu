@@ -265,6 +265,64 @@ int bsc_free_energy(const T *Y, int64_t ldY, const T *lpj, int64_t lpj_stride_n,
   return TVO_OK;
 }
 
+// ------------------------------------------------------------------------------------ epoch update
+// my_Wq is accumulated as its upper triangle (bsc_mstep_kernel); the solve wants the full symmetric matrix.
+static __global__ void bsc_symmetrize_kernel(const double *__restrict__ U, double *__restrict__ full, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * H) return;
+  const int r = i / H, c = i % H;
+  full[i] = r <= c ? U[i] : U[(size_t)c * H + r];
+}
+
+// BSC.update_param_epoch after the solve (bsc.py:178-198 + fix_theta, sanity.py:76-88) in ONE kernel, theta written in
+// place:  W = sol^T (non-finite entries <- the noisy old W, bsc.py:174,193);  pi = my_pies / N (or its mean over H for a
+// scalar prior), non-finite <- old, clamped to [1e-5, 1 - 1e-5];  sigma2 = my_sigma2 / N / D, non-finite <- old, >= 1e-5.
+// The arithmetic is the reference's torch expressions operation for operation (fp64 statistics, cast to T, then fixed).
+template <typename T>
+__global__ void bsc_epoch_finish_kernel(const double *__restrict__ stats, const double *__restrict__ sol,
+                                        const T *__restrict__ W_noisy, T *__restrict__ W, T *__restrict__ pies, int n_pies,
+                                        T *__restrict__ sigma2, int H, int D) {
+  const double *my_pies = stats + (size_t)H * D + (size_t)H * H;
+  const double N = my_pies[H + 1];
+  const T lo = (T)1.0e-5, hi = (T)(1.0 - 1.0e-5);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int i = tid; i < H * D; i += nth) {
+    const int d = i / H, h = i % H;
+    T v = sol ? (T)sol[(size_t)h * D + d] : W_noisy[i];
+    if (!isfinite((double)v)) v = W_noisy[i];
+    W[i] = v;
+  }
+  if (n_pies == H) {
+    for (int h = tid; h < H; h += nth) {
+      T v = (T)(my_pies[h] / N);
+      if (!isfinite((double)v)) v = pies[h];
+      pies[h] = v < lo ? lo : (v > hi ? hi : v);
+    }
+  } else if (tid == 0) {
+    double s = 0.0;
+    for (int h = 0; h < H; ++h) s += my_pies[h];
+    T v = (T)(s / N / (double)H);
+    if (!isfinite((double)v)) v = pies[0];
+    pies[0] = v < lo ? lo : (v > hi ? hi : v);
+  }
+  if (tid == 0) {
+    T v = (T)(my_pies[H] / N / (double)D);
+    if (!isfinite((double)v)) v = sigma2[0];
+    sigma2[0] = v < lo ? lo : v;
+  }
+}
+
+template <typename T>
+int bsc_epoch_finish(const double *stats, const double *sol, const T *W_noisy, T *W, T *pies, int n_pies, T *sigma2, int H,
+                     int D, void *stream) {
+  TVO_REQUIRE(stats && W_noisy && W && pies && sigma2, "bsc_epoch_finish: null pointer");
+  TVO_REQUIRE(H > 0 && D > 0 && (n_pies == 1 || n_pies == H), "bsc_epoch_finish: bad sizes");
+  bsc_epoch_finish_kernel<T><<<min((H * D + 255) / 256, 4 * sm_count()), 256, 0, (cudaStream_t)stream>>>(
+      stats, sol, W_noisy, W, pies, n_pies, sigma2, H, D);
+  TVO_AFTER_LAUNCH("bsc_epoch_finish");
+  return TVO_OK;
+}
+
 template int estep_evo_bsc_direct<double>(const double *, int64_t, const int64_t *, uint64_t *, double *, const void *,
                                           const tvo_evo_config *, const double *, int64_t, int, int, int, int64_t *, void *);
 template int estep_evo_bsc_direct<float>(const float *, int64_t, const int64_t *, uint64_t *, float *, const void *,
@@ -275,6 +333,20 @@ template int estep_evo_bsc_direct<float>(const float *, int64_t, const int64_t *
 using namespace tvo;
 
 extern "C" {
+int tvo_bsc_symmetrize(const double *upper, double *full, int32_t H, void *stream) {
+  TVO_REQUIRE(upper && full && H > 0, "bsc_symmetrize: bad arguments");
+  bsc_symmetrize_kernel<<<(H * H + 255) / 256, 256, 0, (cudaStream_t)stream>>>(upper, full, H);
+  TVO_AFTER_LAUNCH("bsc_symmetrize");
+  return TVO_OK;
+}
+int tvo_bsc_epoch_finish_f64(const double *stats, const double *sol, const double *W_noisy, double *W, double *pies,
+                             int32_t n_pies, double *sigma2, int32_t H, int32_t D, void *stream) {
+  return bsc_epoch_finish<double>(stats, sol, W_noisy, W, pies, n_pies, sigma2, H, D, stream);
+}
+int tvo_bsc_epoch_finish_f32(const double *stats, const double *sol, const float *W_noisy, float *W, float *pies,
+                             int32_t n_pies, float *sigma2, int32_t H, int32_t D, void *stream) {
+  return bsc_epoch_finish<float>(stats, sol, W_noisy, W, pies, n_pies, sigma2, H, D, stream);
+}
 int64_t tvo_bsc_theta_ws_bytes(int32_t H, int32_t D, int32_t is_f64) {
   return (int64_t)(is_f64 ? bsc_ws_bytes<double>(H, D) : bsc_ws_bytes<float>(H, D));
 }

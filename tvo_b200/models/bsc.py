@@ -78,8 +78,10 @@ class BSC(Optimized, Sampler, Reconstructor):
         self.use_gram = True  # Gram-form fused E-step (False: direct column-walk form, D <= 256)
         self.scratch_datapoints = 131072  # chunk size of the Gram E-step / M-step GEMMs (scratch = chunk*H*8 B)
         self._scratch = None
-        self.W_solver = "gpu"  # "gpu": torch.linalg.lstsq on the device (as the reference under TVO_GPU);
-        #                        "cpu": rank-revealing gelsy on the host (as the reference's CPU path)
+        self.W_solver = "gpu"  # "gpu": Cholesky on the device with lstsq as fallback; "gpu_lstsq": torch.linalg.lstsq
+        #                        on the device (as the reference under TVO_GPU); "cpu": rank-revealing gelsy on the host
+        #                        (as the reference's CPU path); see update_param_epoch
+        self._wq_full = None
 
     # --- accumulators under the reference's names (views into the packed buffer) ----------------
     @property
@@ -248,47 +250,73 @@ class BSC(Optimized, Sampler, Reconstructor):
         return None
 
     def update_param_epoch(self) -> None:
-        """bsc.py:160-204.  One all-reduce of the packed statistics, then the reference's closed forms on every rank and
-        ONE packed broadcast of the new theta from rank 0 (cuSOLVER / LAPACK solves are not bit-reproducible across
-        processes; the reference broadcasts W, pies, sigma2 separately, sanity.py:40).  The always-drawn noisy copy
-        of W (bsc.py:174) is broadcast as well, as in the reference: it is the fallback when the solve fails."""
-        theta, policy = self.theta, self.policy
+        """bsc.py:160-204.  One all-reduce of the packed statistics, then on every rank: the solve of
+        my_Wq W^T = my_Wp^T and ONE kernel (tvo_bsc_epoch_finish) that turns the solution and the statistics into the
+        new theta in place, fix_theta included.  With more than one rank a packed broadcast of theta from rank 0
+        follows (cuSOLVER / LAPACK are not guaranteed bit-reproducible across processes; the reference broadcasts
+        W, pies, sigma2 separately, sanity.py:40).
+
+        W_solver "gpu" (default): my_Wq is symmetric positive semi-definite, so the system is solved by a Cholesky
+        factorisation (potrf + potrs: 0.3 ms at H = 256 against 1.0 ms for the QR behind torch.linalg.lstsq, which
+        is what the reference calls under TVO_GPU); if the factorisation fails or its pivots signal a condition
+        number beyond ~1e12 (a unit that was never active), torch.linalg.lstsq takes over, and if that raises the
+        reference's fallback applies (W <- W + 0.1 randn, bsc.py:174,180-181).  "gpu_lstsq": always lstsq on the
+        device; "cpu": the host's rank-revealing gelsy (the reference's CPU path)."""
+        theta = self.theta
         D, H = self.shape
         all_reduce(self._stats)
-        N = self.my_N  # device scalar: no .item() sync
         self._last_F = self._stats[-1].clone()
-        self._last_N = N.clone()
+        self._last_N = self.my_N.clone()
+        self._fresh = None  # theta changes under the lpj stored in the states
         prec = self._precision
-        Wold_noisy = theta["W"] + 0.1 * to.randn_like(theta["W"])
-        broadcast(Wold_noisy)
-        theta_new = {}
+        Wold_noisy = theta["W"] + 0.1 * to.randn_like(theta["W"])  # always drawn, as in the reference (bsc.py:174)
         WpT = self._stats[: H * D].view(H, D)
-        try:
-            if self.W_solver == "cpu":
-                sol = to.linalg.lstsq(self.my_Wq.cpu(), WpT.cpu())[0].to(WpT.device)
-            else:
-                sol = to.linalg.lstsq(self.my_Wq, WpT)[0]
-            theta_new["W"] = sol.t().to(prec)
-        except RuntimeError:
-            pprint("Inversion error. Will not update W but add some noise instead.")
-            theta_new["W"] = Wold_noisy
-        theta_new["pies"] = ((self.my_pies / N) if self.config["individual_priors"]
-                             else self.my_pies.sum(dim=0, keepdim=True) / N / H).to(prec)
-        theta_new["sigma2"] = (self.my_sigma2 / N / D).to(prec)
-        policy["W"][0] = Wold_noisy
-        policy["pies"][0] = theta["pies"]
-        policy["sigma2"][0] = theta["sigma2"]
-        fix_theta(theta_new, policy)
-        # every rank solved the same reduced system, but LAPACK/cuSOLVER are not guaranteed to be
-        # bit-reproducible across processes: one small packed broadcast keeps theta identical
-        # everywhere (the reference broadcasts W, pies, sigma2 separately, sanity.py:40)
-        flat = to.cat([theta_new[k].reshape(-1) for k in theta])
-        broadcast(flat)
-        o = 0
-        for key in theta:
-            n = theta[key].numel()
-            theta[key][:] = flat[o:o + n].view_as(theta[key])
-            o += n
+        direct = self._stats.is_cuda and all(theta[k].is_contiguous() and theta[k].dtype == prec and
+                                             theta[k].device == self._stats.device for k in theta)
+        sol = None
+        if self.W_solver == "gpu" and direct:
+            if self._wq_full is None or self._wq_full.device != self._stats.device:
+                self._wq_full = to.empty((H, H), dtype=to.float64, device=self._stats.device)
+            _lib.call("tvo_bsc_symmetrize", _lib.ptr(self._stats[H * D: H * D + H * H]), _lib.ptr(self._wq_full), H,
+                      _lib.stream())
+            L, info = to.linalg.cholesky_ex(self._wq_full)
+            dg = to.diagonal(L)
+            flags = to.stack([info.to(to.float64), dg.min() / dg.max()]).tolist()  # one host read per EM iteration
+            if flags[0] == 0 and flags[1] > 1e-6:  # cond(my_Wq) ~ (max/min pivot)^2 < 1e12
+                sol = to.cholesky_solve(WpT, L)
+        if sol is None:
+            try:
+                Wq = self._wq_full if (self.W_solver == "gpu" and direct) else self.my_Wq
+                sol = (to.linalg.lstsq(Wq.cpu(), WpT.cpu())[0].to(WpT.device) if self.W_solver == "cpu"
+                       else to.linalg.lstsq(Wq, WpT)[0])
+            except RuntimeError:
+                pprint("Inversion error. Will not update W but add some noise instead.")
+                broadcast(Wold_noisy)
+                sol = None
+        if direct:
+            sol = None if sol is None else sol.contiguous()
+            _lib.call(f"tvo_bsc_epoch_finish_{_lib.sfx(prec)}", _lib.ptr(self._stats), _lib.ptr(sol),
+                      _lib.ptr(Wold_noisy.contiguous()), _lib.ptr(theta["W"]), _lib.ptr(theta["pies"]),
+                      theta["pies"].numel(), _lib.ptr(theta["sigma2"]), H, D, _lib.stream())
+        else:  # user-rebound theta tensors (other dtype / device / strides): the reference's torch expressions
+            N = self.my_N
+            policy = self.policy
+            theta_new = {"W": Wold_noisy if sol is None else sol.t().to(prec),
+                         "pies": ((self.my_pies / N) if self.config["individual_priors"]
+                                  else self.my_pies.sum(dim=0, keepdim=True) / N / H).to(prec),
+                         "sigma2": (self.my_sigma2 / N / D).to(prec)}
+            policy["W"][0], policy["pies"][0], policy["sigma2"][0] = Wold_noisy, theta["pies"], theta["sigma2"]
+            fix_theta(theta_new, policy)
+            for key in theta:
+                theta[key][:] = theta_new[key].to(device=theta[key].device, dtype=theta[key].dtype)
+        if tvo_b200.get_run_policy() == "mpi" and to.distributed.is_initialized() and to.distributed.get_world_size() > 1:
+            flat = to.cat([theta[k].reshape(-1) for k in theta])
+            broadcast(flat)
+            o = 0
+            for key in theta:
+                n = theta[key].numel()
+                theta[key][:] = flat[o:o + n].view_as(theta[key])
+                o += n
         self._stats.zero_()
 
     def generate_data(self, N: int = None, hidden_state: Tensor = None) -> Union[Tensor, Tuple[Tensor, Tensor]]:
