@@ -531,6 +531,202 @@ bsc_mstep_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict
   }
 }
 
+// ------------------------------------------------------------------------------------ M-step, list walk
+// BSC.update_param_batch (bsc.py:134-158) for H <= 256 when lpj was just produced by the E-step (residual from lpj).
+// One warp per datapoint, one LANE per state: the state's 32-byte bit row is read with 128-bit loads (the next
+// datapoint's rows and lpj are already in flight: the global K walk was what the previous kernel waited on), its
+// active units are walked once (non-empty half words first, as in the list-based E-step), and every unit adds the
+// state's posterior weight to
+//   * <s>_h in shared memory as a 64-bit FIXED-POINT integer (2^-56 units; q <= 1, S <= 128 states): shared fp64
+//     atomicAdd is a compare-and-swap spin loop on sm_100a, the integer add is one native ATOMS.ADD.64 and is
+//     order-independent (the sum is deterministic); the truncation is < S 2^-56 absolute per unit;
+//   * my_Wq's upper triangle in global memory, one fp64 RED per unit pair of the state.
+constexpr double kEFix = 72057594037927936.0;  // 2^56
+
+template <typename T, int EPL>  // EPL: states per lane = ceil(S / 32) (1, 2 or 4)
+__global__ void __launch_bounds__(256, EPL <= 2 ? 3 : 2)
+bsc_mstep_list_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx, int64_t row0,
+                      const uint64_t *__restrict__ K, int64_t k_stride_n, const T *__restrict__ lpj, int64_t lpj_stride_n,
+                      const void *ws, double *__restrict__ stats, double *__restrict__ E_out, double *__restrict__ Yd_out,
+                      int64_t B, int S, int H, int D, int /*exact_resid: never*/, size_t warp_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
+  const int W64 = n_words(H), HW = 2 * W64;
+  unsigned char *p = smem_raw + (size_t)wib * warp_bytes;
+  unsigned long long *Efx = (unsigned long long *)p;  // H fixed-point <s>_h of the current datapoint
+  double *pies_w = (double *)(p + (size_t)H * 8);     // H: running sum of <s> over this warp's datapoints
+  unsigned char *plist = p + (size_t)2 * H * 8;       // 32 lanes x 16 positions of the state being walked
+  double *WqU = stats + (size_t)H * D, *pies = WqU + (size_t)H * H;
+  double *sig = pies + H, *Ncnt = sig + 1, *Facc = Ncnt + 1;
+  const double inv_coef = 1.0 / th.hdr->coef;  // -2 sigma2
+  double acc_sig = 0.0, acc_F = 0.0, acc_N = 0.0;
+  for (int h = lane; h < H; h += 32) {
+    pies_w[h] = 0.0;
+    Efx[h] = 0ull;
+  }
+  unsigned char *pl = plist + lane * 16;
+
+  // software pipeline: registers of the NEXT datapoint (bit rows of this lane's states, their lpj, this lane's y
+  // values) and the row index of the one after it — every global read is issued a full iteration before its use
+  uint32_t nx_w[EPL][8];
+  T nx_l[EPL];
+  auto fetch = [&](int64_t bb, int64_t row) {
+    const uint64_t *Kn = K + row * k_stride_n;
+    const T *l = lpj + row * lpj_stride_n;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int s = lane + 32 * e;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) nx_w[e][k] = 0u;
+      nx_l[e] = T(0);
+      if (s < S) {
+        const uint32_t *st = (const uint32_t *)(Kn + (size_t)s * W64);
+        if ((W64 & 1) == 0) {
+#pragma unroll
+          for (int q4 = 0; q4 < 2; ++q4) {
+            if (q4 < W64 / 2) {
+              const uint4 v = *reinterpret_cast<const uint4 *>(st + 4 * q4);
+              nx_w[e][4 * q4 + 0] = v.x;
+              nx_w[e][4 * q4 + 1] = v.y;
+              nx_w[e][4 * q4 + 2] = v.z;
+              nx_w[e][4 * q4 + 3] = v.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < HW) nx_w[e][k] = st[k];
+        }
+        nx_l[e] = l[s];
+      }
+    }
+    // y is only counted for NaNs here (and widened for the fp32 mode's GEMM): an L2 prefetch instead of registers
+    const T *yn = Y + bb * ldY;
+    for (int d = lane * (int)(128 / sizeof(T)); d < D; d += 32 * (int)(128 / sizeof(T)))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(yn + d));
+  };
+  const int64_t stride = (int64_t)gridDim.x * wpb;
+  int64_t b = (int64_t)blockIdx.x * wpb + wib;
+  int64_t row_nx = 0;  // row index of datapoint b + stride
+  if (b < B) {
+    fetch(b, idx ? idx[b] : row0 + b);
+    if (b + stride < B) row_nx = idx ? idx[b + stride] : row0 + b + stride;
+  }
+  uint32_t *wl = (uint32_t *)(plist + 512) + lane * 8;  // this lane's 8 half words of the state being walked
+  for (; b < B; b += stride) {
+    uint32_t w[EPL][8];
+    double lv[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[e][k] = nx_w[e][k];
+      lv[e] = (double)nx_l[e];
+    }
+    if (b + stride < B) {
+      const int64_t row = row_nx;
+      if (b + 2 * stride < B) row_nx = idx ? idx[b + 2 * stride] : row0 + b + 2 * stride;
+      fetch(b + stride, row);
+    }
+    const T *y = Y + b * ldY;
+    // softmax weights (lpj2pjc, _utils.py:182-191)
+    double mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e)
+      if (lane + 32 * e < S) mx = fmax(mx, lv[e]);
+    mx = warp_max(mx);
+    double ex[EPL], se = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      ex[e] = lane + 32 * e < S ? exp(lv[e] - mx) : 0.0;
+      se += ex[e];
+    }
+    se = warp_sum(se);
+    int dn = 0;
+    for (int d = lane; d < D; d += 32) {
+      const T v = y[d];
+      dn += (v == v) ? 1 : 0;
+      if (Yd_out) Yd_out[b * (int64_t)D + d] = (double)v;
+    }
+    const double inv_se = 1.0 / se;
+    double part = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      if (lane + 32 * e < S) {
+        const double qs = ex[e] * inv_se;
+        const unsigned long long qfx = (unsigned long long)(qs * kEFix);
+        uint32_t nz = 0;
+        int ntot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          nz |= (w[e][k] ? 1u : 0u) << k;
+          ntot += __popc(w[e][k]);
+        }
+        *reinterpret_cast<uint4 *>(wl) = make_uint4(w[e][0], w[e][1], w[e][2], w[e][3]);  // refills index the row
+        *reinterpret_cast<uint4 *>(wl + 4) = make_uint4(w[e][4], w[e][5], w[e][6], w[e][7]);
+        double pr = 0.0;
+        uint32_t m = 0;
+        int hw = 0;
+#pragma unroll 1
+        for (int n = 0; n < ntot; ++n) {
+          if (m == 0) {
+            hw = __ffs((int)nz) - 1;
+            nz &= nz - 1;
+            m = wl[hw];
+          }
+          const int h = (hw << 5) + __ffs((int)m) - 1;
+          m &= m - 1;
+          pr += (double)__ldg(th.prior + h);
+          atomicAdd(Efx + h, qfx);
+          // (the diagonal of my_Wq is <s_h s_h> = <s_h>: it is added once per warp from pies_w at the end instead of
+          //  one RED per state and unit — all datapoints hit the same few diagonal entries, and same-address REDs
+          //  serialise in L2)
+          if (ntot <= 16) {
+#pragma unroll 1
+            for (int i = 0; i < n; ++i) atomicAdd(WqU + (size_t)pl[i] * H + h, qs);  // earlier units are smaller: upper triangle
+            pl[n] = (unsigned char)h;
+          } else {  // dense state: the earlier units straight from the bit row
+            for (int k2 = 0; k2 <= hw; ++k2) {
+              uint32_t m2 = wl[k2];
+              if (k2 == hw) m2 &= (1u << (h & 31)) - 1u;
+              while (m2) {
+                const int h2 = (k2 << 5) + __ffs((int)m2) - 1;
+                m2 &= m2 - 1;
+                atomicAdd(WqU + (size_t)h2 * H + h, qs);
+              }
+            }
+          }
+        }
+        part += qs * ((lv[e] - pr) * inv_coef);
+      }
+    }
+    acc_sig += warp_sum(part);
+    dn = warp_sum(dn);
+    acc_F += mx + log(se) + th.hdr->prior_sum - 0.5 * (double)dn * th.hdr->log_2pi_sigma2;
+    acc_N += 1.0;
+    __syncwarp();
+    for (int h = lane; h < H; h += 32) {
+      const double ev = (double)Efx[h] * (1.0 / kEFix);
+      Efx[h] = 0ull;
+      E_out[b * (int64_t)H + h] = ev;
+      pies_w[h] += ev;
+    }
+    __syncwarp();
+  }
+  for (int h = lane; h < H; h += 32) {
+    const double v = pies_w[h];
+    if (v != 0.0) {
+      atomicAdd(pies + h, v);
+      atomicAdd(WqU + (size_t)h * H + h, v);  // diag(my_Wq) = sum_n <s_h>_n
+    }
+  }
+  if (lane == 0 && acc_N != 0.0) {
+    atomicAdd(sig, acc_sig);
+    atomicAdd(Ncnt, acc_N);
+    atomicAdd(Facc, acc_F);
+  }
+}
+
 template <typename T>
 static size_t bsc_mstep_warp_bytes(int S, int H) {
   return align16((size_t)S * 8) + 2 * align16((size_t)H * 8) + (size_t)kMstepListCap * 32 * 2;
@@ -692,12 +888,17 @@ int bsc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, in
   cublasHandle_t hb;
   int rc = cublas_for_stream(st, hb);
   if (rc) return rc;
-  const size_t wbytes = bsc_mstep_warp_bytes<T>(S, H);
+  // list-walk kernel: lpj fresh from the E-step (residual from lpj), H <= 256, S <= 128
+  const bool use_list = !exact && H <= 256 && S <= 128 && !g_disable_v2;
+  size_t wbytes = use_list ? (size_t)2 * H * 8 + 512 + 1024 : bsc_mstep_warp_bytes<T>(S, H);
   int wpb = 8;
   while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmemFast) wpb >>= 1;
   TVO_REQUIRE(wbytes * wpb <= (size_t)kMaxSmemFast, "bsc_mstep: working set %zu B exceeds shared memory", wbytes);
   const size_t smem = wbytes * wpb;
-  auto kern = bsc_mstep_kernel<T>;
+  auto kern = !use_list ? bsc_mstep_kernel<T>
+              : S <= 32 ? bsc_mstep_list_kernel<T, 1>
+              : S <= 64 ? bsc_mstep_list_kernel<T, 2>
+                        : bsc_mstep_list_kernel<T, 4>;
   TVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
