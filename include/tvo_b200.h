@@ -37,7 +37,7 @@ extern "C" {
 #define TVO_EUNSUPPORTED 3
 #define TVO_ENONFINITE 4 /* reserved for host-side checks of the nonfinite flag */
 
-#define TVO_ABI_VERSION 1
+#define TVO_ABI_VERSION 2
 
 /* parent selection (tvo/variational/evo.py:223) */
 #define TVO_SEL_RANDPARENTS 0      /* batch_randparents  evo.py:436-451 */
@@ -60,12 +60,18 @@ typedef struct {
   int32_t n_parents;
   int32_t n_children; /* per parent (ignored for cross*, where it is n_parents-1) */
   int32_t n_generations;
-  int32_t reserved;
+  int32_t flags;     /* TVO_EVO_LPJ_CURRENT: lpj[idx] already holds lpj_fn(batch, K[idx]) under the current theta (the fused
+                        E-step then skips its re-score, evo.py:95) */
   double p_bf;       /* bitflip_frequency (sparseflip) */
   uint64_t seed;     /* Philox key */
   uint32_t step;     /* E-step counter (epoch * batches + batch), part of the Philox counter */
   uint32_t n_offset; /* global index of local datapoint 0 (rank offset) */
+  const double *fit_norm; /* device {m, T} of tvo_fit_norm over the batch's lpj: required by the fused E-steps for
+                             TVO_SEL_FITPARENTS (the reference's batch-global normaliser, evo.py:404-406), which they
+                             support for ONE generation (later generations need the normaliser of the previous
+                             generation's children over the whole batch: stand-alone kernels).  NULL otherwise. */
 } tvo_evo_config;
+#define TVO_EVO_LPJ_CURRENT 1
 
 /* dedup sentinel written for redundant children: (float)-1e20, as the reference's CPU path
  * (_set_redundant_lpj_to_low_CPU.pyx:17) */
@@ -179,8 +185,8 @@ int tvo_bsc_epoch_finish_f32(const double *stats, const double *sol, const float
  *      ||y||^2 - 2 (W^T y).s + s^T (W^T W) s: the batch is processed in chunks of as many datapoints
  *      as fit (one cuBLAS GEMM a = Y W plus one kernel per chunk).  scratch == NULL selects the direct
  *      column-walk form (D <= 256).  Datapoints with NaN in y always take the direct form.
- *      TVO_SEL_FITPARENTS (batch-global normaliser) is not available fused: use the stand-alone
- *      kernels. ---- */
+ *      TVO_SEL_FITPARENTS (batch-global normaliser): one generation, with cfg->fit_norm and
+ *      TVO_EVO_LPJ_CURRENT (re-score with tvo_bsc_lpj, reduce with tvo_fit_norm, then this call). ---- */
 int64_t tvo_bsc_estep_scratch_bytes(int64_t B, int32_t H, int32_t is_f64);
 /* Sparse states at 64 <= H <= 256 with randparents + sparseflip run the list-based kernel (states held as
  * sorted position lists, children scored incrementally); datapoints it cannot hold and all other shapes run

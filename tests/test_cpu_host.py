@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 30
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/tvo_b200.h but not exported"
-    assert L.tvo_abi_version() == 1
+    assert L.tvo_abi_version() == 2
 
 
 def test_ctypes_prototypes_cover_the_header():

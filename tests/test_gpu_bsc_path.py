@@ -771,3 +771,38 @@ def test_trainer_accepts_the_references_own_dataloader():
         tr = Trainer(m, loader, st)
         Fs.append([tr.em_step()["train_F"] for _ in range(3)])
     assert np.allclose(Fs[0], Fs[1], rtol=1e-12)
+
+
+@pytest.mark.parametrize("mut,P,Cn", [("randflip", 5, 3), ("sparseflip", 4, 2), ("cross_randflip", 4, None)])
+def test_fused_batch_fitparents_one_generation_matches_oracle(mut, P, Cn):
+    """The reference's `batch_fitparents` (batch-global normaliser, evo.py:404-406, quirk Q3) with ONE generation runs
+    through the FUSED kernel: re-score + deterministic (min, sum) reduction + fused select / mutate / score / dedup /
+    top-S that skips its own re-score.  K bit-exact, nsubs and lpj against the oracle, and against the stand-alone
+    kernels (two generations keep using those)."""
+    rng = np.random.default_rng(41)
+    N, H, D, S, G = 48, 12, 16, 20, 1
+    W = rng.standard_normal((D, H))
+    pies = np.full(H, 0.25)
+    Y = (rng.random((N, H)) < pies) @ W.T + 0.1 * rng.standard_normal((N, D))
+    K = rand_K(rng, N, S, H, p=0.3)
+    tvo_b200._set_device(to.device(DEV))
+    crossover = mut.startswith("cross")
+    m = BSC(H, D, dev(W), to.tensor([0.05], dtype=to.float64), dev(pies), precision=to.float64)
+    kw = dict(bitflip_frequency=1.0 / H, seed=5, K_init=dev(K))
+    if crossover:
+        st = EVOVariationalStates(N, H, S, to.float64, "batch_fitparents", mut[len("cross_"):], P, G, crossover=True, **kw)
+    else:
+        st = EVOVariationalStates(N, H, S, to.float64, "batch_fitparents", mut, P, G, n_children=Cn, **kw)
+    o = om.BSC(H, D, W, [0.05], pies)
+    Kw = K
+    for step in range(2):
+        _lib.reset_launch_count()
+        nsubs = st.update(to.arange(N, device=DEV), dev(Y), m)
+        launches = _lib.launch_count()
+        Kw, Lw, nw = oracle_estep(o, Y, Kw, np.float64, "batch_fitparents", st.config["mutation"], P, P - 1 if crossover else Cn,
+                                  G, 1.0 / H, np.arange(N), 5, step, sparsity=float(m._tvo_sparsity().item()))
+        assert np.array_equal(st.K.unpack().cpu().numpy(), Kw), f"K differs at step {step}"
+        assert nsubs == nw
+        assert np.allclose(st.lpj.cpu().numpy(), Lw, rtol=RT64, atol=RT64)
+        # prepare + lpj rows + fit_norm (2) + [flip table + GEMM +] fused kernel: no per-generation stand-alone kernels
+        assert launches <= 8, launches

@@ -26,12 +26,16 @@ class EvoConfig(C.Structure):
         ("n_parents", C.c_int32),
         ("n_children", C.c_int32),
         ("n_generations", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
         ("p_bf", C.c_double),
         ("seed", C.c_uint64),
         ("step", C.c_uint32),
         ("n_offset", C.c_uint32),
+        ("fit_norm", C.c_void_p),
     ]
+
+
+EVO_LPJ_CURRENT = 1
 
 
 _P, _I32, _I64, _U64, _U32, _F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.c_double
@@ -142,7 +146,7 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if L.tvo_abi_version() != 1:
+        if L.tvo_abi_version() != 2:
             raise TvoError("libtvo_b200.so ABI version mismatch")
         _lib = L
     return _lib

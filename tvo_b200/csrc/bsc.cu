@@ -234,9 +234,7 @@ int estep_evo_bsc_direct(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *
   EstepDims dims;
   int rc = evo_params_from_cfg(cfg, S, H, ep, dims, "estep_evo_bsc");
   if (rc) return rc;
-  TVO_REQUIRE(ep.sel != TVO_SEL_FITPARENTS,
-              "estep_evo_bsc: batch-global fitparents needs a grid-wide reduction per generation; use the unfused "
-              "kernels (or TVO_SEL_FITPARENTS_FIXED)");
+  TVO_REQUIRE(ep.sel != TVO_SEL_FITPARENTS, "estep_evo_bsc (direct form): batch-global fitparents runs in the Gram form");
   TVO_REQUIRE(!(ep.mut == TVO_MUT_SPARSEFLIP || ep.mut == TVO_MUT_CROSS_SPARSEFLIP) || sparsity,
               "estep_evo_bsc: sparseflip needs the device scalar `sparsity`");
   if (B == 0) return TVO_OK;

@@ -367,15 +367,22 @@ estep_evo_bsc_gram_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restr
     }
     PHASE_SYNC();
     const T *a_sm = A + b * (int64_t)H;  // a = W^T y row, read through L1/L2 (written by the DGEMM)
-    if (active) score_states<T, kOldInGlobal>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, plist, pcap, lane, W64);  // evo.py:95
+    if (active) {  // evo.py:95, unless the rows are current already (batch_fitparents)
+      if (ep.lpj_current) {
+        for (int i = lane; i < S; i += 32) wb.lpj[i] = lrow[i];
+        __syncwarp();
+      } else {
+        score_states<T, kOldInGlobal>(wb.oldK, S, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj, plist, pcap, lane, W64);
+      }
+    }
     for (int g = 0; g < ep.G; ++g) {
       const uint64_t *cand = g == 0 ? wb.oldK : wb.newK + (size_t)(g - 1) * Sgen * wb.rs;
       const T *cand_lpj = g == 0 ? wb.lpj : wb.lpj + S + (g - 1) * Sgen;
       uint64_t *children = wb.newK + (size_t)g * Sgen * wb.rs;
       PHASE_SYNC();
       if (active)
-        evo_generation<T>(wb, cand, cand_lpj, g == 0 ? S : Sgen, children, ep, g, n_glob, W64, H, sparsity, 0.0, 1.0,
-                          lane, g == 0 ? W64 : wb.rs);
+        evo_generation<T>(wb, cand, cand_lpj, g == 0 ? S : Sgen, children, ep, g, n_glob, W64, H, sparsity,
+                          ep.fit_norm ? ep.fit_norm[0] : 0.0, ep.fit_norm ? ep.fit_norm[1] : 1.0, lane, g == 0 ? W64 : wb.rs);
       PHASE_SYNC();
       if (active) score_states<T, kOldInGlobal>(children, Sgen, W64, H, D, th, a_sm, y, yy, has_nan, wb.lpj + S + g * Sgen, plist, pcap,
                                   lane, wb.rs);
@@ -767,9 +774,7 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   EstepDims dims;
   int rc = evo_params_from_cfg(cfg, S, H, ep, dims, "estep_evo_bsc");
   if (rc) return rc;
-  TVO_REQUIRE(ep.sel != TVO_SEL_FITPARENTS,
-              "estep_evo_bsc: batch-global fitparents needs a grid-wide reduction per generation; use the unfused "
-              "kernels (or TVO_SEL_FITPARENTS_FIXED)");
+  TVO_REQUIRE_FITPARENTS(ep, "estep_evo_bsc");
   TVO_REQUIRE(!(ep.mut == TVO_MUT_SPARSEFLIP || ep.mut == TVO_MUT_CROSS_SPARSEFLIP) || sparsity,
               "estep_evo_bsc: sparseflip needs the device scalar `sparsity`");
   TVO_REQUIRE(B >= 0 && D > 0 && ldY >= D && ldY < (1ll << 31), "estep_evo_bsc: bad sizes");

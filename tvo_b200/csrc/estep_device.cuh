@@ -544,7 +544,15 @@ struct EvoParams {
   uint2 key;
   uint32_t step, n_offset;
   const FlipEntry *flip_tab;  // sparseflip: per-popcount table (flip_table_kernel) or nullptr = compute inline
+  const double *fit_norm;     // batch_fitparents: device {m, T} of the batch (tvo_fit_norm); generation 0 only
+  int lpj_current;            // the lpj rows already hold lpj_fn(batch, K) under the current theta: no re-score
 };
+
+// shared argument check of the fused E-steps for the reference's batch-global fitness selection
+#define TVO_REQUIRE_FITPARENTS(ep, who)                                                                              \
+  TVO_REQUIRE((ep).sel != TVO_SEL_FITPARENTS || ((ep).fit_norm && (ep).lpj_current && (ep).G == 1),                  \
+              "%s: batch-global fitparents runs fused for ONE generation and needs cfg->fit_norm (tvo_fit_norm of "   \
+              "the re-scored batch) with TVO_EVO_LPJ_CURRENT; otherwise use the stand-alone kernels", who)
 
 // tab[a], a = 0..H: the two FlipClass entries of a parent with a active units
 static __global__ void flip_table_kernel(FlipEntry *tab, const double *__restrict__ sparsity_p, int H, double p_bf) {

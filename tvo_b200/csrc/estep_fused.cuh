@@ -51,15 +51,23 @@ estep_evo_fused_kernel(typename Model::Params mp, const int64_t *__restrict__ id
       __syncwarp();
     }
     __syncthreads();
-    if (active) ctx.score(mp, wb.oldK, S, W64, wb.lpj, lane);  // lpj[idx] = lpj_fn(batch, K[idx])  (evo.py:95)
+    if (active) {  // lpj[idx] = lpj_fn(batch, K[idx])  (evo.py:95), or already there (batch_fitparents: the normaliser
+                   // of generation 0 is a reduction over exactly these values)
+      if (ep.lpj_current) {
+        for (int i = lane; i < S; i += 32) wb.lpj[i] = lrow[i];
+        __syncwarp();
+      } else {
+        ctx.score(mp, wb.oldK, S, W64, wb.lpj, lane);
+      }
+    }
     for (int g = 0; g < ep.G; ++g) {
       const uint64_t *cand = g == 0 ? wb.oldK : wb.newK + (size_t)(g - 1) * Sgen * W64;
       const T *cand_lpj = g == 0 ? wb.lpj : wb.lpj + S + (g - 1) * Sgen;
       uint64_t *children = wb.newK + (size_t)g * Sgen * W64;
       __syncthreads();
       if (active)
-        evo_generation<T>(wb, cand, cand_lpj, g == 0 ? S : Sgen, children, ep, g, n_glob, W64, H, sparsity, 0.0, 1.0,
-                          lane);
+        evo_generation<T>(wb, cand, cand_lpj, g == 0 ? S : Sgen, children, ep, g, n_glob, W64, H, sparsity,
+                          ep.fit_norm ? ep.fit_norm[0] : 0.0, ep.fit_norm ? ep.fit_norm[1] : 1.0, lane);
       __syncthreads();
       if (active) ctx.score(mp, children, Sgen, W64, wb.lpj + S + g * Sgen, lane);
     }
@@ -82,9 +90,7 @@ int launch_estep_evo_fused(const typename Model::Params &mp, const int64_t *idx,
   EstepDims dims;
   int rc = evo_params_from_cfg(cfg, S, H, ep, dims, who);
   if (rc) return rc;
-  TVO_REQUIRE(ep.sel != TVO_SEL_FITPARENTS,
-              "%s: batch-global fitparents needs a grid-wide reduction per generation; use the unfused kernels (or "
-              "TVO_SEL_FITPARENTS_FIXED)", who);
+  TVO_REQUIRE_FITPARENTS(ep, who);
   TVO_REQUIRE(!(ep.mut == TVO_MUT_SPARSEFLIP || ep.mut == TVO_MUT_CROSS_SPARSEFLIP) || sparsity,
               "%s: sparseflip needs the device scalar `sparsity`", who);
   if (B == 0) return TVO_OK;

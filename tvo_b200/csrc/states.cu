@@ -70,6 +70,8 @@ int evo_params_from_cfg(const tvo_evo_config *cfg, int S, int H, EvoParams &ep, 
   ep.step = cfg->step;
   ep.n_offset = cfg->n_offset;
   ep.flip_tab = nullptr;
+  ep.fit_norm = cfg->fit_norm;
+  ep.lpj_current = (cfg->flags & TVO_EVO_LPJ_CURRENT) ? 1 : 0;
   TVO_REQUIRE(S > 0 && H > 0, "%s: S=%d H=%d must be positive", who, S, H);
   TVO_REQUIRE(ep.P >= 1 && ep.G >= 1 && ep.G < 64, "%s: need n_parents >= 1 and 1 <= n_generations < 64", who);
   TVO_REQUIRE(ep.mut >= TVO_MUT_CROSS ? ep.P >= 2 : ep.C >= 1, "%s: need n_children >= 1 (n_parents >= 2 for cross)", who);

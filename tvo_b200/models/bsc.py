@@ -180,9 +180,11 @@ class BSC(Optimized, Sampler, Reconstructor):
     def _tvo_estep_evo(self, states, idx: Tensor, batch: Tensor, cfg) -> bool:
         """Fused EVO E-step; returns False when the configuration needs the unfused kernels."""
         D, H = self._shape
-        if cfg.parent_selection == _lib.SEL["batch_fitparents"] or states.lpj.dtype != self._precision:
+        if states.lpj.dtype != self._precision:
             return False
-        if D > 256 and not self.use_gram:
+        if cfg.parent_selection == _lib.SEL["batch_fitparents"] and not (cfg.fit_norm and cfg.flags & _lib.EVO_LPJ_CURRENT):
+            return False  # batch-global normaliser: fused for one generation (EVOVariationalStates.update_device)
+        if (D > 256 or cfg.parent_selection == _lib.SEL["batch_fitparents"]) and not self.use_gram:
             return False
         Y = self._batch(batch)
         ws = self._prepare()

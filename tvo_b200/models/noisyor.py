@@ -108,8 +108,10 @@ class NoisyOR(Optimized, Sampler):
 
     def _tvo_estep_evo(self, states, idx: Tensor, batch: Tensor, cfg) -> bool:
         D, H = self._shape
-        if cfg.parent_selection == _lib.SEL["batch_fitparents"] or states.lpj.dtype != self._precision:
+        if states.lpj.dtype != self._precision:
             return False
+        if cfg.parent_selection == _lib.SEL["batch_fitparents"] and not (cfg.fit_norm and cfg.flags & _lib.EVO_LPJ_CURRENT):
+            return False  # batch-global normaliser: fused for one generation (EVOVariationalStates.update_device)
         Y = self._batch(batch)
         sparsity = self._tvo_sparsity() if cfg.mutation in (_lib.MUT["sparseflip"], _lib.MUT["cross_sparseflip"]) else None
         _lib.call(f"tvo_estep_evo_noisyor_{_lib.sfx(self._precision)}", _lib.ptr(Y), Y.stride(0), _lib.ptr(idx),

@@ -180,8 +180,10 @@ class SSSC(Sampler, Optimized, Reconstructor):
 
     def _tvo_estep_evo(self, states, idx, batch, cfg) -> bool:
         D, H = self._shape
-        if cfg.parent_selection == _lib.SEL["batch_fitparents"] or states.lpj.dtype != self._precision:
+        if states.lpj.dtype != self._precision:
             return False
+        if cfg.parent_selection == _lib.SEL["batch_fitparents"] and not (cfg.fit_norm and cfg.flags & _lib.EVO_LPJ_CURRENT):
+            return False  # batch-global normaliser: fused for one generation (EVOVariationalStates.update_device)
         Y = self._batch(batch)
         sparsity = self._tvo_sparsity() if cfg.mutation in (_lib.MUT["sparseflip"], _lib.MUT["cross_sparseflip"]) else None
         sc = self._get_scratch(idx.numel())

@@ -95,6 +95,17 @@ class EVOVariationalStates(TVOVariationalStates):
         cfg = self.evo_config()
         self._step += 1
         if hasattr(model, "_tvo_estep_evo"):
+            if cfg.parent_selection == _lib.SEL["batch_fitparents"] and cfg.n_generations == 1 \
+                    and self.lpj.dtype == getattr(model, "precision", self.lpj.dtype):
+                # the reference's fitness selection normalises by (min, sum) of the WHOLE batch's re-scored lpj
+                # (evo.py:404-406): re-score, reduce (deterministic two-pass), then the fused kernel skips its own
+                # re-score and selects with that normaliser.  Later generations would need the same reduction over
+                # the previous generation's children of the whole batch: those run through the stand-alone kernels.
+                model._tvo_lpj_rows(self, idx, batch)
+                _lib.call(f"tvo_fit_norm_{_lib.sfx(self.lpj.dtype)}", _lib.ptr(self.lpj), self.lpj.shape[1], _lib.ptr(idx),
+                          idx.numel(), self.lpj.shape[1], _lib.ptr(self._fit_norm), _lib.stream())
+                cfg.flags |= _lib.EVO_LPJ_CURRENT
+                cfg.fit_norm = self._fit_norm.data_ptr()
             if model._tvo_estep_evo(self, idx, batch, cfg):
                 return
             lpj_rows = lambda: model._tvo_lpj_rows(self, idx, batch)  # noqa: E731
