@@ -161,8 +161,8 @@ def test_sssc_fullem_train_increases_F():
 
 def test_sssc_dense_states_all_solver_levels_and_overflow():
     """States with 0..6 active units run in sub-warp groups, 7..16 with the full warp in shared memory,
-    17..32 in the warp's global scratch row, more than 32 set the overflow flag (finfo.min, raise at epoch
-    end): lpj and the M-step statistics against the oracle for a K that mixes all levels."""
+    17..32 in the warp's global scratch row, more than 32 in a pooled scratch slot sized for |s| = H (no input
+    raises): lpj and the M-step statistics against the oracle for a K that mixes all levels."""
     rng = np.random.default_rng(21)
     N, D, H, S = 6, 40, 48, 12
     W = rng.standard_normal((D, H))
@@ -193,16 +193,25 @@ def test_sssc_dense_states_all_solver_levels_and_overflow():
         a, b = getattr(m, attr).cpu().numpy(), getattr(o, attr[len("_my_"):])
         assert np.allclose(a, b, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(b).max())), attr
     m._check_overflow()  # nothing overflowed so far
-    # one state beyond 32 active units: finfo.min and a loud error at the next overflow check
+    # states beyond 32 active units (the reference evaluates any |s|, sssc.py:287-335): the slow tier in global memory
     K2 = K.copy()
     K2[2, 4, :40] = 1
+    K2[5, 0, :] = 1   # all 48 units active
+    want2 = o.log_pseudo_joint(Y, K2)
     got2 = m.log_pseudo_joint(dev(Y), dev(K2)).cpu().numpy()
-    assert got2[2, 4] == np.finfo(np.float64).min
-    mask = np.ones_like(got2, bool)
-    mask[2, 4] = False
-    assert np.allclose(got2[mask], want[mask], rtol=1e-9, atol=1e-9 * np.abs(want).max())
-    with pytest.raises(RuntimeError):
-        m._check_overflow()
+    assert np.allclose(got2, want2, rtol=1e-9, atol=1e-9 * np.abs(want2).max())
+    m._check_overflow()
+    m2 = SSSC(H, D, dev(W), dev(np.array([0.5])), dev(mus), dev(Psi), dev(pies), precision=to.float64)
+    o2 = om.SSSC(H, D, W, np.array([0.5]), mus, Psi, pies)
+    st2 = EVOVariationalStates(N, H, S, to.float64, "randparents", "randflip", 2, 1, 1, K_init=dev(K2))
+    st2.lpj[:] = dev(lpj)
+    m2.update_param_batch(to.arange(N), dev(Y), st2)
+    o2.update_param_batch(Y, K2, lpj)
+    for attr in ("_my_sum_xpt_s", "_my_sum_xpt_sz", "_my_sum_xpt_ssT", "_my_sum_xpt_szszT", "_my_sum_xpt_sz_xpt_szT",
+                 "_my_sum_y_szT", "_my_sum_diag_yyT"):
+        a, b = getattr(m2, attr).cpu().numpy(), getattr(o2, attr[len("_my_"):])
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(b).max())), attr
+    m2._check_overflow()
 
 
 def test_sssc_c3_shape_properties():

@@ -127,6 +127,7 @@ __host__ __device__ inline size_t sssc_warp_scratch_bytes() {
   const size_t g = (size_t)kSsscNG * sssc_scratch_bytes(kSsscAS), m = sssc_scratch_bytes(kSsscAM);
   return align16(g > m ? g : m);
 }
+__host__ __device__ inline size_t sssc_pool_slot_bytes(int H) { return (sssc_scratch_bytes(H) + 255) & ~(size_t)255; }
 __device__ inline SsscScratch sssc_carve(unsigned char *p, int amax) {
   SsscScratch s;
   s.R = (double *)p;
@@ -350,7 +351,12 @@ struct SsscModel {
     const void *ws;
     int H, D;
     unsigned char *big;  // global scratch, one sssc_scratch_bytes(kSsscAB) row per warp of the grid (or nullptr)
-    int *overflow;       // set when a state has more active units than can be evaluated
+    int *overflow;       // set when a state cannot be evaluated (more than kSsscAB active units and no pool)
+    // states with more than kSsscAB active units (the reference evaluates any |s|, sssc.py:287-335): a small pool
+    // of scratch slots sized for |s| = H in global memory, taken with a spin lock by the warp that needs one
+    unsigned char *pool;
+    int *pool_locks;
+    int pool_slots;
   };
   // fp64: the a = W^T y row is read where the GEMM left it (global scratch, through L1/L2) — 2 kB per warp less
   // shared memory, i.e. two more resident warps per SM at H = 256; fp32 keeps a converted fp64 copy in shared memory
@@ -423,6 +429,20 @@ struct SsscModel {
           const SsscScratch sc = sssc_carve(p.big + (size_t)wid * sssc_scratch_bytes(kSsscAB), kSsscAB);
           v = sssc_state<T, 32>(st, W64, p.H, p.D, th, a_sm, yy, ynan, sc, kSsscAB, MOMENTS, a, lane, FULL);
           sink(s, v, a, sc, kSsscAB, lane, 32, FULL);
+        } else if (p.pool) {  // the slow tier: any number of active units, scratch sized for |s| = H
+          int slot = -1;
+          if (lane == 0) {
+            int i = wid % p.pool_slots;
+            while (atomicCAS(p.pool_locks + i, 0, 1) != 0) i = i + 1 == p.pool_slots ? 0 : i + 1;
+            slot = i;
+          }
+          slot = __shfl_sync(FULL, slot, 0);
+          const SsscScratch sc = sssc_carve(p.pool + (size_t)slot * sssc_pool_slot_bytes(p.H), p.H);
+          v = sssc_state<T, 32>(st, W64, p.H, p.D, th, a_sm, yy, ynan, sc, p.H, MOMENTS, a, lane, FULL);
+          sink(s, v, a, sc, p.H, lane, 32, FULL);
+          __syncwarp();
+          __threadfence();
+          if (lane == 0) atomicExch(p.pool_locks + slot, 0);
         } else {
           if (lane == 0) *p.overflow = 1;
           sink(s, v, -1, scg, kSsscAS, lane, 32, FULL);
@@ -608,6 +628,36 @@ static int sssc_big_alloc(cudaStream_t st, int64_t warps, unsigned char **out) {
   return TVO_OK;
 }
 
+// Pool of scratch slots for states with more than kSsscAB active units: part of the per-device context, grown on
+// demand and kept; the locks are zero between kernels (every taker releases its slot).
+static unsigned char *g_sssc_pool[64];
+static size_t g_sssc_pool_bytes[64];
+static int g_sssc_pool_slots[64];
+template <typename P>
+static int sssc_pool_attach(P &p, int H) {
+  int dev = 0;
+  TVO_CUDA(cudaGetDevice(&dev));
+  TVO_REQUIRE(dev >= 0 && dev < 64, "sssc pool: device index %d out of range", dev);
+  const size_t slot = sssc_pool_slot_bytes(H);
+  int slots = (int)max((size_t)4, min((size_t)32, ((size_t)256 << 20) / slot));
+  const size_t need = slot * slots + 256;
+  if (g_sssc_pool_bytes[dev] < need) {
+    if (g_sssc_pool[dev]) TVO_CUDA(cudaFree(g_sssc_pool[dev]));
+    g_sssc_pool[dev] = nullptr;
+    g_sssc_pool_bytes[dev] = 0;
+    TVO_CUDA(cudaMalloc((void **)&g_sssc_pool[dev], need));
+    TVO_CUDA(cudaMemset(g_sssc_pool[dev], 0, 256));
+    g_sssc_pool_bytes[dev] = need;
+    g_sssc_pool_slots[dev] = slots;
+  } else {
+    slots = min(slots, g_sssc_pool_slots[dev]);
+  }
+  p.pool_locks = (int *)g_sssc_pool[dev];
+  p.pool = g_sssc_pool[dev] + 256;
+  p.pool_slots = slots;
+  return TVO_OK;
+}
+
 template <typename T>
 int sssc_prepare(const T *W, const T *sigma2, const T *mus, const T *Psi, const T *pies, int H, int D, void *ws,
                  void *stream) {
@@ -635,7 +685,11 @@ int sssc_lpj(const T *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, con
   int rc = sssc_cublas(st, hb);
   if (rc) return rc;
   const SsscTheta<T> th = sssc_theta_view<T>(ws, H, D);
-  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, nullptr, overflow};
+  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, nullptr, overflow, nullptr, nullptr, 0};
+  {
+    int rcp = sssc_pool_attach(p, H);
+    if (rcp) return rcp;
+  }
   const size_t msm = align16(SsscModel<T>::smem_bytes(p));
   int wpb = 8;
   while (wpb > 1 && msm * wpb > (size_t)227 * 1024) wpb >>= 1;
@@ -680,7 +734,11 @@ int sssc_estep(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj,
   rc = evo_params_from_cfg(cfg, S, H, ep, dims, "estep_evo_sssc");
   if (rc) return rc;
   const SsscTheta<T> th = sssc_theta_view<T>(ws, H, D);
-  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, nullptr, overflow};
+  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, nullptr, overflow, nullptr, nullptr, 0};
+  {
+    int rcp = sssc_pool_attach(p, H);
+    if (rcp) return rcp;
+  }
   rc = sssc_big_alloc(st, (int64_t)sm_count() * 3 * 8, &p.big);  // estep_evo_fused_kernel: <= 3 CTAs x 8 warps per SM
   if (rc) return rc;
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
@@ -714,7 +772,11 @@ int sssc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, i
   const SsscTheta<T> th = sssc_theta_view<T>(ws, H, D);
   const int W64 = n_words(H);
   const size_t extra = (size_t)2 * H * 8 + (size_t)S * 8 + (size_t)S * W64 * 8;
-  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, nullptr, overflow};
+  typename SsscModel<T>::Params p{Y, ldY, (const T *)scratch, ws, H, D, nullptr, overflow, nullptr, nullptr, 0};
+  {
+    int rcp = sssc_pool_attach(p, H);
+    if (rcp) return rcp;
+  }
   const size_t wbytes = align16(SsscModel<T>::smem_bytes(p) + extra);
   int wpb = 8;
   while (wpb > 1 && wbytes * wpb > (size_t)227 * 1024) wpb >>= 1;
