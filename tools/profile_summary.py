@@ -60,7 +60,7 @@ stalls = [(i, c.replace("smsp__average_warps_issue_stalled_", "").replace("_per_
           for i, c in enumerate(h) if c.startswith("smsp__average_warps_issue_stalled_") and c.endswith("_per_issue_active.ratio")]
 
 lines = [f"# {name}: {title}", "",
-         "Command (under gpurun, one B200): `python bench.py --n 131072 --steps 2 --warmup 3 --no-cpu-baseline`",
+         "Command (under gpurun, one B200): `python bench.py --n 131072 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-other`",
          "(`tools/profile_cmd.sh`): plain run first, then `ncu --metrics gpu__time_duration.sum --clock-control none -c 400`",
          f"(launch list -> `profiles/{name}_launches.csv`), then `ncu --set full --clock-control none --import-source on`",
          "on the E-step / M-step kernels.  Times under ncu are serialised and cold-cache; the bench numbers come from the plain run.",
