@@ -166,3 +166,39 @@ def test_own_gemms_match_library(N):
     E = (q[:, :, None] * to.as_tensor(a[0], device=DEV).double()).sum(dim=1)
     WpT = (E.t() @ dev(Y)).cpu().numpy()
     assert np.allclose(a[3][: H * D].reshape(H, D), WpT, rtol=1e-10, atol=1e-10 * np.abs(WpT).max())
+
+
+@pytest.mark.parametrize("N,H,D", [(1, 256, 144), (100, 256, 144), (129, 256, 144), (4099, 256, 144), (300, 128, 64), (77, 64, 40)])
+def test_tf32x3_tcgen05_gemm_matches_library_fp32(N, H, D):
+    """fp32 mode: a = Y W on the 5th-generation tensor cores (csrc/bsc_gemm_tf32.cuh: tcgen05.mma kind::tf32 with the
+    hi / lo split, accumulators in TMEM, TMA-fed) against the library SGEMM path on the same inputs: the E-step's lpj
+    agree to fp32 accuracy (1e-5 of their scale), K sets agree on all but near-ties, and the statistics to 1e-4."""
+    rng = np.random.default_rng(N + H)
+    S = 16
+    W, pies, Y, K = make(rng, N, H, D, S, 4.0 / H, 4.0 / H)
+    W, Y = W.astype(np.float32), Y.astype(np.float32)
+    tvo_b200._set_device(to.device(DEV))
+    out = {}
+    for variant in (0, 0x10000):
+        _lib.call("tvo_bsc_estep_variant", variant)
+        try:
+            m = BSC(H, D, dev(W), to.tensor([0.9], dtype=to.float32), dev(pies, to.float32), precision=to.float32)
+            st = EVOVariationalStates(N, H, S, to.float32, "randparents", "sparseflip", 4, 2, 2, bitflip_frequency=1.0 / H,
+                                      seed=8, K_init=dev(K))
+            idx = to.arange(N, device=DEV)
+            _lib.kernel_timing_enable(True)
+            nsubs = st.update(idx, dev(Y), m)
+            own_launches = _lib.kernel_timing_read(_lib.TIMED_BSC_GEMM_YW)[1]
+            _lib.kernel_timing_enable(False)
+            assert own_launches == (1 if variant == 0 else 0)  # the tcgen05 kernel really is the one that ran
+            m.update_param_batch(idx, dev(Y), st)
+            out[variant] = (st.K.unpack().cpu().numpy(), st.lpj.double().cpu().numpy(), nsubs, m._stats.cpu().numpy().copy())
+        finally:
+            _lib.call("tvo_bsc_estep_variant", 0)
+    a, b = out[0], out[0x10000]
+    same = [set(map(bytes, a[0][n])) == set(map(bytes, b[0][n])) for n in range(N)]
+    assert sum(same) >= N - max(1, N // 200), f"{N - sum(same)} of {N} K sets differ"
+    ok = np.array(same)
+    scale = np.abs(b[1]).max()
+    assert np.allclose(np.sort(a[1][ok], 1), np.sort(b[1][ok], 1), rtol=1e-5, atol=1e-5 * scale)
+    assert np.allclose(a[3], b[3], rtol=1e-4, atol=1e-4 * np.abs(b[3]).max())

@@ -2,6 +2,7 @@
 // energy, and the direct-form fused EVO E-step.  The Gram-form fused E-step and the M-step live in
 // bsc_fast.cu.
 #include "bsc_device.cuh"
+#include "bsc_gemm_tf32.cuh"
 
 namespace tvo {
 
@@ -158,6 +159,11 @@ int bsc_prepare(const T *W, const T *pies, int n_pies, const T *sigma2, int H, i
   const int blocks = (int)min((size_t)4 * sm_count(), (total + 255) / 256);
   bsc_prepare_kernel<T><<<max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(W, pies, n_pies, sigma2, H, D, ws);
   TVO_AFTER_LAUNCH("bsc_prepare");
+  if (sizeof(T) == 4) {  // fp32 model: TF32 hi / lo images of W for the tcgen05 GEMM
+    const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
+    bsc_w_tf32_images_kernel<<<max(blocks, 1), 256, 0, (cudaStream_t)stream>>>((const float *)W, (unsigned char *)th.Wg, H, D);
+    TVO_AFTER_LAUNCH("bsc_w_tf32_images");
+  }
   return TVO_OK;
 }
 

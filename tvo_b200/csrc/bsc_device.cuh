@@ -44,9 +44,13 @@ template <typename T>
 __host__ __device__ inline size_t bsc_wg_off(int H, int D) {
   return bsc_gp_off<T>(H, D) + align16((size_t)H * sizeof(double));
 }
+// fp32 model: the pre-split (TF32 hi / lo), pre-swizzled images of W for the tcgen05 GEMM (bsc_gemm_tf32.cuh):
+// per K block of 32 a hi and a lo tile of H rows x 128 bytes.  The region replaces Wg (fp64 model only).
+__host__ __device__ inline size_t bsc_wtf_bytes(int H, int D) { return (size_t)((D + 31) / 32) * 2 * H * 128; }
 template <typename T>
 __host__ __device__ inline size_t bsc_ws_bytes(int H, int D) {
-  return bsc_wg_off<T>(H, D) + (size_t)bsc_kpad16(D) * H * sizeof(double);
+  const size_t o = (bsc_wg_off<T>(H, D) + 1023) & ~(size_t)1023;
+  return o + (sizeof(T) == 8 ? (size_t)bsc_kpad16(D) * H * sizeof(double) : bsc_wtf_bytes(H, D));
 }
 
 template <typename T>
@@ -70,7 +74,7 @@ __host__ __device__ inline BscTheta<T> bsc_theta_view(const void *ws, int H, int
   t.G = (const double *)(p + bsc_gram_off<T>(H, D));
   t.G2 = (const double *)(p + bsc_gram2_off<T>(H, D));
   t.gp = (const double *)(p + bsc_gp_off<T>(H, D));
-  t.Wg = (const double *)(p + bsc_wg_off<T>(H, D));
+  t.Wg = (const double *)(p + ((bsc_wg_off<T>(H, D) + 1023) & ~(size_t)1023));  // fp32 model: the TF32 images
   t.Dpad = bsc_dpad(D);
   return t;
 }
@@ -93,8 +97,8 @@ __global__ void bsc_prepare_kernel(const T *__restrict__ W, const T *__restrict_
     const T pi = pies[n_pies == 1 ? 0 : h];
     prior[h] = log(pi / (T(1) - pi));
   }
-  {
-    double *Wg = (double *)(p + bsc_wg_off<T>(H, D));
+  if (sizeof(T) == 8) {
+    double *Wg = (double *)(p + ((bsc_wg_off<T>(H, D) + 1023) & ~(size_t)1023));
     const size_t nwg = (size_t)bsc_kpad16(D) * H;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwg; i += (size_t)gridDim.x * blockDim.x) {
       const int kk = (int)(i & 3), h = (int)((i >> 2) % H), k4 = (int)((i >> 2) / H);

@@ -15,6 +15,7 @@
 #include "bsc_device.cuh"
 #include "bsc_estep_v2.cuh"
 #include "bsc_gemm.cuh"
+#include "bsc_gemm_tf32.cuh"
 
 namespace tvo {
 
@@ -837,13 +838,17 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   }
   // a = Y W: the hand-written TMA + FP64 tensor-core kernel (bsc_gemm.cuh; also ||y||^2, so that the list-based
   // kernel does not read Y), the library GEMM for shapes it does not cover and for the fp32 mode
-  const bool own_gemm = sizeof(T) == 8 && yy_buf && !g_library_gemm && gemm_yw_supported(H, D, ldY, Y);
+  const bool own_gemm = yy_buf && !g_library_gemm &&
+                        (sizeof(T) == 8 ? gemm_yw_supported(H, D, ldY, Y) : gemm_yw_tf32_supported(H, D, ldY, Y));
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
     const int Bc = (int)min(cap, B - c0);
     if (own_gemm) {
       void *tokg;
       kernel_timing_begin(TVO_TIMED_BSC_GEMM_YW, st, &tokg);
-      cudaError_t ge = launch_gemm_yw((const double *)(Y + c0 * ldY), ldY, th.Wg, (double *)A, yy_buf, Bc, H, D, sm_count(), st);
+      cudaError_t ge = sizeof(T) == 8
+                           ? launch_gemm_yw((const double *)(Y + c0 * ldY), ldY, th.Wg, (double *)A, yy_buf, Bc, H, D, sm_count(), st)
+                           : launch_gemm_yw_tf32((const float *)(Y + c0 * ldY), ldY, (const unsigned char *)th.Wg, (float *)A,
+                                                 yy_buf, Bc, H, D, sm_count(), st);
       kernel_timing_end(tokg, st);
       if (ge != cudaSuccess) return set_error(TVO_ECUDA, "launch bsc_gemm_yw: %s", cudaGetErrorString(ge));
       count_launch();
