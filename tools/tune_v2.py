@@ -11,6 +11,7 @@ from tvo_b200.models import BSC
 from tvo_b200.variational import EVOVariationalStates
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 500000
+PREC = to.float32 if os.environ.get("PREC") == "f32" else to.float64
 variants = [int(v, 0) for v in sys.argv[2:]] or [0]
 H, D, S = 256, 144, 64
 dev = to.device("cuda:0")
@@ -19,14 +20,14 @@ g0 = to.Generator(device=dev).manual_seed(1234)
 Wgen = to.randn(D, H, dtype=to.float64, device=dev, generator=g0)
 W0 = Wgen + 0.5 * to.randn(D, H, dtype=to.float64, device=dev, generator=g0)
 s = (to.rand(N, H, device=dev, generator=g0) < 5.0 / H).double()
-Y = s @ Wgen.t() + to.randn(N, D, dtype=to.float64, device=dev, generator=g0)
+Y = (s @ Wgen.t() + to.randn(N, D, dtype=to.float64, device=dev, generator=g0)).to(PREC)
 del s
 idx = to.arange(N, device=dev)
 for v in variants:
     np.random.seed(0)
     _lib.call("tvo_bsc_estep_variant", v)
-    model = BSC(H, D, W0, to.tensor([1.0], dtype=to.float64), to.full((H,), 1.0 / H, dtype=to.float64), precision=to.float64)
-    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", n_parents=16, n_generations=2, n_children=2,
+    model = BSC(H, D, W0.to(PREC), to.tensor([1.0], dtype=PREC), to.full((H,), 1.0 / H, dtype=PREC), precision=PREC)
+    st = EVOVariationalStates(N, H, S, PREC, "randparents", "sparseflip", n_parents=16, n_generations=2, n_children=2,
                               bitflip_frequency=1.0 / H, seed=2024)
     for _ in range(6):  # same warm-up trajectory as bench.py (EM iterations from the 1/H init)
         st.update_device(idx, Y, model); model.update_param_batch(idx, Y, st); model.update_param_epoch()
