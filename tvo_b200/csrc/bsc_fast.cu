@@ -935,7 +935,7 @@ int bsc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, in
       if (rc) return rc;
       void *tokg;
       kernel_timing_begin(TVO_TIMED_BSC_GEMM_ETY, st, &tokg);
-      cudaError_t ge = launch_gemm_ety(E, Yp, ldy, (double *)part, stats, Bc, H, D, sm_count(), st);
+      cudaError_t ge = launch_gemm_ety(E, Yp, ldy, (double *)part, stats, D, Bc, H, D, sm_count(), st);
       kernel_timing_end(tokg, st);
       if (ge != cudaSuccess) return set_error(TVO_ECUDA, "launch bsc_gemm_ety: %s", cudaGetErrorString(ge));
       count_launch(2);

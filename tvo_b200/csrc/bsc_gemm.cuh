@@ -152,7 +152,7 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
           *reinterpret_cast<double2 *>(A + (size_t)row * H + wn * (8 * NB) + j * 8 + 2 * q) = make_double2(acc[i][j][0], acc[i][j][1]);
       }
     }
-    if (wn == 0) {
+    if (wn == 0 && yy_out) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         double v = ysq[i];
@@ -292,16 +292,16 @@ bsc_gemm_ety_kernel(const double *__restrict__ E, const double *__restrict__ Y, 
           make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
-// stats WpT (H x D row-major) += sum over slabs, in slab order
-static __global__ void bsc_gemm_ety_reduce_kernel(const double *__restrict__ part, double *__restrict__ WpT, int nslab, int H,
-                                                  int D) {
+// C (H x D, row stride ldC) += sum over slabs, in slab order
+static __global__ void bsc_gemm_ety_reduce_kernel(const double *__restrict__ part, double *__restrict__ C, int ldC, int nslab,
+                                                  int H, int D) {
   const int Dh = D / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * D) return;
   const int h = i / D, d = i % D, half = d >= Dh ? 1 : 0, dd = d - half * Dh;
   double s = 0.0;
   for (int sl = 0; sl < nslab; ++sl) s += part[((size_t)sl * 2 + half) * H * Dh + (size_t)h * Dh + dd];
-  WpT[i] += s;
+  C[(size_t)h * ldC + d] += s;
 }
 
 __host__ inline bool gemm_ety_supported(int H, int D, int64_t ldY, const void *Y, const void *E) {
@@ -310,8 +310,9 @@ __host__ inline bool gemm_ety_supported(int H, int D, int64_t ldY, const void *Y
 }
 __host__ inline size_t gemm_ety_part_bytes(int H, int D, int sms) { return (size_t)(sms / 2) * 2 * H * (D / 2) * 8; }
 
-__host__ inline cudaError_t launch_gemm_ety(const double *E, const double *Y, int64_t ldY, double *part, double *WpT, int B,
-                                            int H, int D, int sms, cudaStream_t st) {
+// C (H x D, row stride ldC) += E^T (H x B) Y (B x D, row stride ldY);  E is B x H contiguous
+__host__ inline cudaError_t launch_gemm_ety(const double *E, const double *Y, int64_t ldY, double *part, double *C, int ldC,
+                                            int B, int H, int D, int sms, cudaStream_t st) {
   const size_t smem = gemm_ety_smem_bytes(H, D / 2);
   const int nslab = max(1, min(sms / 2, (B + kGeKC - 1) / kGeKC));
   cudaError_t e;
@@ -329,7 +330,7 @@ __host__ inline cudaError_t launch_gemm_ety(const double *E, const double *Y, in
 #undef TVO_GETY
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  bsc_gemm_ety_reduce_kernel<<<(H * D + 255) / 256, 256, 0, st>>>(part, WpT, nslab, H, D);
+  bsc_gemm_ety_reduce_kernel<<<(H * D + 255) / 256, 256, 0, st>>>(part, C, ldC, nslab, H, D);
   return cudaGetLastError();
 }
 

@@ -14,6 +14,7 @@
 #include <cublas_v2.h>
 
 #include "estep_fused.cuh"
+#include "bsc_gemm.cuh"
 
 namespace tvo {
 
@@ -30,15 +31,22 @@ __host__ __device__ inline size_t sssc_off_mus(int H) { return sssc_off_prior() 
 __host__ __device__ inline size_t sssc_off_psi(int H) { return sssc_off_mus(H) + (size_t)H * 8; }
 __host__ __device__ inline size_t sssc_off_g(int H) { return sssc_off_psi(H) + (size_t)H * H * 8; }
 __host__ __device__ inline size_t sssc_off_wt(int H) { return align16(sssc_off_g(H) + (size_t)H * H * 8); }
+// fp64 model: W once more as Wg[k/4][h][k%4] (k zero-padded to a multiple of 16), the operand layout of the
+// hand-written FP64 tensor-core GEMM a = Y W (bsc_gemm.cuh)
+template <typename T>
+__host__ __device__ inline size_t sssc_off_wg(int H, int D) {
+  return align16(sssc_off_wt(H) + (size_t)H * sssc_dpad(D) * sizeof(T));
+}
 template <typename T>
 __host__ __device__ inline size_t sssc_ws_bytes(int H, int D) {
-  return sssc_off_wt(H) + (size_t)H * sssc_dpad(D) * sizeof(T);
+  return sssc_off_wg<T>(H, D) + (sizeof(T) == 8 ? (size_t)((D + 15) & ~15) * H * 8 : 0);
 }
 template <typename T>
 struct SsscTheta {
   const SsscThetaHdr *hdr;
   const double *prior, *mus, *Psi, *G;
   const T *Wt;
+  const double *Wg;  // fp64 model only
   int Dpad;
 };
 template <typename T>
@@ -51,6 +59,7 @@ __host__ __device__ inline SsscTheta<T> sssc_theta_view(const void *ws, int H, i
   t.Psi = (const double *)(p + sssc_off_psi(H));
   t.G = (const double *)(p + sssc_off_g(H));
   t.Wt = (const T *)(p + sssc_off_wt(H));
+  t.Wg = (const double *)(p + sssc_off_wg<T>(H, D));
   t.Dpad = sssc_dpad(D);
   return t;
 }
@@ -70,6 +79,13 @@ __global__ void sssc_prepare_kernel(const T *__restrict__ W, const T *__restrict
   for (size_t i = g0; i < (size_t)H * Dpad; i += gt) {
     const int h = (int)(i / Dpad), d = (int)(i % Dpad);
     Wt[i] = d < D ? W[(size_t)d * H + h] : T(0);
+  }
+  if (sizeof(T) == 8) {
+    double *Wg = (double *)(p + sssc_off_wg<T>(H, D));
+    for (size_t i = g0; i < (size_t)((D + 15) & ~15) * H; i += gt) {
+      const int kk = (int)(i & 3), h = (int)((i >> 2) % H), d = 4 * (int)((i >> 2) / H) + kk;
+      Wg[i] = d < D ? (double)W[(size_t)d * H + h] : 0.0;
+    }
   }
   for (size_t i = g0; i < (size_t)H * H; i += gt) {
     Ps[i] = (double)Psi[i];
@@ -599,12 +615,59 @@ static int sssc_cublas(cudaStream_t st, cublasHandle_t &h) {
     count_launch();                                                                          \
   } while (0)
 
-static int sssc_gemm_A(cublasHandle_t h, const double *Wt, int Dpad, const double *Y, int64_t ldY, double *A, int Bc, int H, int D) {
+// a = Y W: the hand-written TMA + FP64 tensor-core kernel of bsc_gemm.cuh where its shape class applies (H in
+// {64, 128, 256}, D a multiple of 16), the library GEMM otherwise and for the fp32 model
+static int sssc_gemm_A(cublasHandle_t h, const double *Wt, int Dpad, const double *Y, int64_t ldY, double *A, int Bc, int H, int D,
+                       const double *Wg = nullptr, cudaStream_t st = nullptr) {
+  if (Wg && gemm_yw_supported(H, D, ldY, Y) && ((uintptr_t)A % 16) == 0) {
+    cudaError_t e = launch_gemm_yw(Y, ldY, Wg, A, nullptr, Bc, H, D, sm_count(), st);
+    if (e != cudaSuccess) return set_error(TVO_ECUDA, "launch gemm_yw (sssc): %s", cudaGetErrorString(e));
+    count_launch();
+    return TVO_OK;
+  }
   const double one = 1.0, zero = 0.0;
   TVO_CUBLAS(cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, H, Bc, D, &one, Wt, Dpad, Y, (int)ldY, &zero, A, H));
   return TVO_OK;
 }
-static int sssc_gemm_A(cublasHandle_t h, const float *Wt, int Dpad, const float *Y, int64_t ldY, float *A, int Bc, int H, int D) {
+// slab partials of the M-step GEMMs (per-device context, grown on demand and kept)
+static double *g_sssc_part[64];
+static size_t g_sssc_part_bytes[64];
+static int sssc_part_buffer(size_t bytes, double **out) {
+  int dev = 0;
+  TVO_CUDA(cudaGetDevice(&dev));
+  TVO_REQUIRE(dev >= 0 && dev < 64, "sssc part buffer: device index %d out of range", dev);
+  if (g_sssc_part_bytes[dev] < bytes) {
+    if (g_sssc_part[dev]) TVO_CUDA(cudaFree(g_sssc_part[dev]));
+    g_sssc_part[dev] = nullptr;
+    g_sssc_part_bytes[dev] = 0;
+    TVO_CUDA(cudaMalloc((void **)&g_sssc_part[dev], bytes));
+    g_sssc_part_bytes[dev] = bytes;
+  }
+  *out = g_sssc_part[dev];
+  return TVO_OK;
+}
+// C (H x N, row stride ldC) += E^T (H x Bc) Z (Bc x N, row stride ldZ): own kernel in column blocks it covers
+// (N = D for y_szT; 128-column blocks of the H x H products), library GEMM otherwise
+static int sssc_gemm_EtZ(cublasHandle_t hb, cudaStream_t st, const double *E, const double *Z, int64_t ldZ, double *C, int ldC,
+                         int Bc, int H, int N) {
+  const int nb = gemm_ety_supported(H, N, ldZ, Z, E) ? N : (N % 128 == 0 && gemm_ety_supported(H, 128, ldZ, Z, E) ? 128 : 0);
+  if (nb) {
+    double *part = nullptr;
+    int rc = sssc_part_buffer(gemm_ety_part_bytes(H, nb, sm_count()), &part);
+    if (rc) return rc;
+    for (int c0 = 0; c0 < N; c0 += nb) {
+      cudaError_t e = launch_gemm_ety(E, Z + c0, ldZ, part, C + c0, ldC, Bc, H, nb, sm_count(), st);
+      if (e != cudaSuccess) return set_error(TVO_ECUDA, "launch gemm_ety (sssc): %s", cudaGetErrorString(e));
+      count_launch(2);
+    }
+    return TVO_OK;
+  }
+  const double one = 1.0;
+  TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, N, H, Bc, &one, Z, (int)ldZ, E, H, &one, C, ldC));
+  return TVO_OK;
+}
+static int sssc_gemm_A(cublasHandle_t h, const float *Wt, int Dpad, const float *Y, int64_t ldY, float *A, int Bc, int H, int D,
+                       const double * = nullptr, cudaStream_t = nullptr) {
   const float one = 1.f, zero = 0.f;
   TVO_CUBLAS(cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, H, Bc, D, &one, Wt, Dpad, Y, (int)ldY, &zero, A, H));
   return TVO_OK;
@@ -702,7 +765,7 @@ int sssc_lpj(const T *Y, int64_t ldY, const uint64_t *K, int64_t k_stride_n, con
   if (rc) return rc;
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
     const int Bc = (int)min(cap, B - c0);
-    rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, (T *)scratch, Bc, H, D);
+    rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, (T *)scratch, Bc, H, D, th.Wg, st);
     if (rc) return rc;
     p.Y = Y + c0 * ldY;
     const int64_t ntask = (int64_t)Bc * ((S + CH - 1) / CH);
@@ -743,7 +806,7 @@ int sssc_estep(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj,
   if (rc) return rc;
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
     const int Bc = (int)min(cap, B - c0);
-    rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, (T *)scratch, Bc, H, D);
+    rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, (T *)scratch, Bc, H, D, th.Wg, st);
     if (rc) return rc;
     p.Y = Y + c0 * ldY;
     rc = launch_estep_evo_fused<T, SsscModel<T>>(p, idx ? idx + c0 : nullptr, c0, K, lpj, cfg, sparsity, Bc, S, H, nsubs, st,
@@ -800,7 +863,7 @@ int sssc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, i
     double *X = (double *)((unsigned char *)scratch + align16((size_t)cap * H * sizeof(T)));
     double *E = X + (size_t)cap * H;
     double *Yd = f64 ? nullptr : E + (size_t)cap * H;
-    rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, A, Bc, H, D);
+    rc = sssc_gemm_A(hb, th.Wt, th.Dpad, Y + c0 * ldY, ldY, A, Bc, H, D, th.Wg, st);
     if (rc) return rc;
     p.Y = Y + c0 * ldY;
     const int grid = (int)max((int64_t)1, min((int64_t)(Bc + wpb - 1) / wpb, (int64_t)sm_count() * max(occ, 1)));
@@ -810,12 +873,16 @@ int sssc_mstep(const T *Y, int64_t ldY, const int64_t *idx, const uint64_t *K, i
     const double *Yp = f64 ? (const double *)(Y + c0 * ldY) : Yd;
     const int ldy = f64 ? (int)ldY : D;
     // y_szT^T (H x D row-major) += X^T Y                     (sssc.py:446)
-    TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, D, H, Bc, &one, Yp, ldy, X, H, &one, stats, D));
+    rc = sssc_gemm_EtZ(hb, st, X, Yp, ldy, stats, D, Bc, H, D);
+    if (rc) return rc;
     // sz_szT (H x H) += X^T X                                 (sssc.py:443)
-    TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, H, H, Bc, &one, X, H, X, H, &one, stats + HD, H));
+    rc = sssc_gemm_EtZ(hb, st, X, X, H, stats + HD, H, Bc, H, H);
+    if (rc) return rc;
     // ssz (H x H row-major, [h_s][h_kappa]) += E^T X         (sssc.py:448-450); col-major view: ssz^T = X^T E
-    if (with_ssz & 1)
-      TVO_CUBLAS(cublasDgemm(hb, CUBLAS_OP_N, CUBLAS_OP_T, H, H, Bc, &one, X, H, E, H, &one, stats + HD + 3 * HH, H));
+    if (with_ssz & 1) {
+      rc = sssc_gemm_EtZ(hb, st, E, X, H, stats + HD + 3 * HH, H, Bc, H, H);
+      if (rc) return rc;
+    }
   }
   TVO_CUDA(cudaFreeAsync(p.big, st));
   return TVO_OK;
