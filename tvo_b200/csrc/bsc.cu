@@ -57,7 +57,8 @@ template <typename T, int DPL>
 __global__ void __launch_bounds__(256)
 estep_evo_bsc_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__restrict__ idx, uint64_t *__restrict__ K,
                      T *__restrict__ lpj, const void *ws, EvoParams ep, const double *__restrict__ sparsity_p,
-                     EstepDims dims, int64_t B, int H, int D, unsigned long long *nsubs) {
+                     EstepDims dims, int64_t B, int H, int D, unsigned long long *nsubs,
+                     const int32_t *__restrict__ bsel, const int32_t *__restrict__ bsel_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
@@ -67,8 +68,11 @@ estep_evo_bsc_kernel(const T *__restrict__ Y, int64_t ldY, const int64_t *__rest
   const T coef = (T)th.hdr->coef;
   const double sparsity = sparsity_p ? *sparsity_p : 0.0;
   unsigned long long my_subs = 0;
+  // bsel: only the listed datapoints of the call (the overflow list of the list-based kernel, bsc_estep_v2.cuh)
+  if (bsel) B = *bsel_count;
 
-  for (int64_t b = (int64_t)blockIdx.x * wpb + wib; b < B; b += (int64_t)gridDim.x * wpb) {
+  for (int64_t bi = (int64_t)blockIdx.x * wpb + wib; bi < B; bi += (int64_t)gridDim.x * wpb) {
+    const int64_t b = bsel ? (int64_t)bsel[bi] : bi;
     const int64_t row = idx ? idx[b] : b;
     const uint32_t n_glob = ep.n_offset + (uint32_t)row;
     uint64_t *Krow = K + row * (int64_t)S * W64;
@@ -207,7 +211,8 @@ int evo_params_from_cfg(const tvo_evo_config *cfg, int S, int H, EvoParams &ep, 
 template <typename T, int DPL>
 int launch_estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj, const void *ws,
                          const EvoParams &ep, const double *sparsity, const EstepDims &dims, int64_t B, int H, int D,
-                         int64_t *nsubs, cudaStream_t stream) {
+                         int64_t *nsubs, cudaStream_t stream, const int32_t *bsel = nullptr,
+                         const int32_t *bsel_count = nullptr) {
   const size_t wbytes = warp_buf_bytes<T>(dims);
   int wpb = 8;
   while (wpb > 1 && wbytes * wpb > (size_t)kMaxSmem) wpb >>= 1;
@@ -220,11 +225,18 @@ int launch_estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *
   TVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
   occ = max(occ, 1);
   const int64_t want = (B + wpb - 1) / wpb;
-  const int grid = (int)max((int64_t)1, min(want, (int64_t)sm_count() * occ));
+  int grid = (int)max((int64_t)1, min(want, (int64_t)sm_count() * occ));
+  if (bsel) {  // a handful of datapoints, count known on the device only: one CTA per SM is plenty
+    grid = min(grid, sm_count());
+    kern<<<grid, wpb * 32, smem, stream>>>(Y, ldY, idx, K, lpj, ws, ep, sparsity, dims, B, H, D,
+                                           (unsigned long long *)nsubs, bsel, bsel_count);
+    TVO_AFTER_LAUNCH("estep_evo_bsc(overflow)");
+    return TVO_OK;
+  }
   void *tok;
   kernel_timing_begin(TVO_TIMED_ESTEP_EVO_BSC, stream, &tok);
   kern<<<grid, wpb * 32, smem, stream>>>(Y, ldY, idx, K, lpj, ws, ep, sparsity, dims, B, H, D,
-                                         (unsigned long long *)nsubs);
+                                         (unsigned long long *)nsubs, nullptr, nullptr);
   kernel_timing_end(tok, stream);
   TVO_AFTER_LAUNCH("estep_evo_bsc");
   return TVO_OK;
@@ -233,7 +245,7 @@ int launch_estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *
 template <typename T>
 int estep_evo_bsc_direct(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj, const void *ws,
                   const tvo_evo_config *cfg, const double *sparsity, int64_t B, int S, int H, int D, int64_t *nsubs,
-                  void *stream) {
+                  void *stream, const int32_t *bsel, const int32_t *bsel_count) {
   TVO_REQUIRE(Y && K && lpj && ws && cfg && nsubs, "estep_evo_bsc: null pointer");
   TVO_REQUIRE(B >= 0 && D > 0 && D <= 256, "estep_evo_bsc: need 0 < D <= 256 (got %d); use the unfused path", D);
   EvoParams ep;
@@ -248,7 +260,7 @@ int estep_evo_bsc_direct(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *
   cudaStream_t st = (cudaStream_t)stream;
 #define TVO_DPL_CASE(n) \
   case n:               \
-    return launch_estep_evo_bsc<T, n>(Y, ldY, idx, K, lpj, ws, ep, sparsity, dims, B, H, D, nsubs, st);
+    return launch_estep_evo_bsc<T, n>(Y, ldY, idx, K, lpj, ws, ep, sparsity, dims, B, H, D, nsubs, st, bsel, bsel_count);
   switch (bsc_dpad(D) / 32) {
     TVO_DPL_CASE(1) TVO_DPL_CASE(2) TVO_DPL_CASE(3) TVO_DPL_CASE(4) TVO_DPL_CASE(5) TVO_DPL_CASE(6) TVO_DPL_CASE(7)
     TVO_DPL_CASE(8)
@@ -328,9 +340,11 @@ int bsc_epoch_finish(const double *stats, const double *sol, const T *W_noisy, T
 }
 
 template int estep_evo_bsc_direct<double>(const double *, int64_t, const int64_t *, uint64_t *, double *, const void *,
-                                          const tvo_evo_config *, const double *, int64_t, int, int, int, int64_t *, void *);
+                                          const tvo_evo_config *, const double *, int64_t, int, int, int, int64_t *, void *,
+                                          const int32_t *, const int32_t *);
 template int estep_evo_bsc_direct<float>(const float *, int64_t, const int64_t *, uint64_t *, float *, const void *,
-                                         const tvo_evo_config *, const double *, int64_t, int, int, int, int64_t *, void *);
+                                         const tvo_evo_config *, const double *, int64_t, int, int, int, int64_t *, void *,
+                                         const int32_t *, const int32_t *);
 
 }  // namespace tvo
 

@@ -401,7 +401,8 @@ __global__ void __launch_bounds__(256, 4)
 estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                         int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
                         V2Dims dims, int64_t B, int D, unsigned long long *nsubs, int32_t *ovf_count,
-                        int32_t *__restrict__ ovf_list, uint32_t sync_mask, const double *__restrict__ yy_in) {
+                        int32_t *__restrict__ ovf_list, uint32_t sync_mask, const double *__restrict__ yy_in,
+                        int64_t ovf_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64, H = dims.H;
@@ -683,7 +684,8 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
       }
       bail = __any_sync(FULL, bail);
     }
-    if (bail && active && lane == 0) ovf_list[atomicAdd(ovf_count, 1)] = (int32_t)b;  // -> the generic kernel
+    // -> the generic kernel; row0 + b is the datapoint's index in the CALL (row0 = first datapoint of this chunk)
+    if (bail && active && lane == 0) ovf_list[atomicAdd(ovf_count, 1)] = (int32_t)(ovf_base + b);
     __syncwarp();
     V2_PHASE_SYNC();
     if (!bail)

@@ -29,7 +29,7 @@ int evo_params_from_cfg(const tvo_evo_config *cfg, int S, int H, EvoParams &ep, 
 template <typename T>
 int estep_evo_bsc_direct(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *lpj, const void *ws,
                          const tvo_evo_config *cfg, const double *sparsity, int64_t B, int S, int H, int D,
-                         int64_t *nsubs, void *stream);
+                         int64_t *nsubs, void *stream, const int32_t *bsel = nullptr, const int32_t *bsel_count = nullptr);
 
 // ------------------------------------------------------------------------------------ cuBLAS
 static cublasHandle_t g_handles[64];
@@ -70,8 +70,8 @@ static int gemm_A(cublasHandle_t h, const float *Wt, int Dpad, const float *Y, i
 // back to the driver at every synchronisation with the default release threshold — measured as sporadic host-side
 // stalls of tens of ms per E-step.)  Calls on one device are serialised by the boundary's threading contract.
 // slot 0: the E-step's staging rows; slot 1: the slab partials of the M-step GEMM (22 MB at the headline shape)
-static void *g_stage[2][64];
-static size_t g_stage_bytes[2][64];
+static void *g_stage[3][64];  // slot 2: the overflow list of the list-based E-step kernel
+static size_t g_stage_bytes[3][64];
 static int stage_buffer(size_t bytes, uint64_t **out, int slot = 0) {
   int dev = 0;
   TVO_CUDA(cudaGetDevice(&dev));
@@ -840,6 +840,19 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   // kernel does not read Y), the library GEMM for shapes it does not cover and for the fp32 mode
   const bool own_gemm = yy_buf && !g_library_gemm &&
                         (sizeof(T) == 8 ? gemm_yw_supported(H, D, ldY, Y) : gemm_yw_tf32_supported(H, D, ldY, Y));
+  // Overflow datapoints of the list-based kernel.  D <= 256: ONE list for the whole call (a per-device buffer of B
+  // entries) and one launch of the direct-form kernel at the end — it needs no a = Y W rows, so nothing of a chunk has
+  // to survive (a launch per chunk cost ~60 us each for the few datapoints it finds: 4 % of the E-step).  Larger D:
+  // the Gram-form kernel per chunk.
+  const bool ovf_deferred = use_v2 && D <= 256 && B < (1ll << 31);
+  if (ovf_deferred) {
+    uint64_t *buf = nullptr;
+    rc = stage_buffer((size_t)16 + (size_t)B * 4, &buf, 2);
+    if (rc) return rc;
+    ovf_count = (int32_t *)buf;
+    ovf_list = ovf_count + 4;
+    TVO_CUDA(cudaMemsetAsync(ovf_count, 0, 16, st));
+  }
   for (int64_t c0 = 0; c0 < B; c0 += cap) {
     const int Bc = (int)min(cap, B - c0);
     if (own_gemm) {
@@ -859,14 +872,15 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
     const int grid = (int)max((int64_t)1, min((int64_t)(Bc + wpb - 1) / wpb, (int64_t)sm_count() * occ));
     void *tok;
     if (use_v2) {
-      TVO_CUDA(cudaMemsetAsync(ovf_count, 0, 16, st));
+      if (!ovf_deferred) TVO_CUDA(cudaMemsetAsync(ovf_count, 0, 16, st));
       const int grid2 = (int)max((int64_t)1, min((int64_t)(Bc + 7) / 8, (int64_t)sm_count() * occ2));
       kernel_timing_begin(TVO_TIMED_ESTEP_EVO_BSC, st, &tok);
       kern2<<<grid2, 256, v2_smem, st>>>(Y + c0 * ldY, ldY, A, idx ? idx + c0 : nullptr, c0, K, lpj, ws, ep, v2, Bc, D,
                                          (unsigned long long *)nsubs, ovf_count, ovf_list, g_v2_sync_mask,
-                                         own_gemm ? yy_buf : nullptr);
+                                         own_gemm ? yy_buf : nullptr, ovf_deferred ? c0 : 0);
       kernel_timing_end(tok, st);
       TVO_AFTER_LAUNCH("estep_evo_bsc_v2");
+      if (ovf_deferred) continue;
       // overflow datapoints: the generic kernel reads their count on the device (an empty list costs one idle launch)
       kern<<<min(grid, sm_count()), wpb * 32, smem, st>>>(Y + c0 * ldY, ldY, A, idx ? idx + c0 : nullptr, c0, K, lpj, ws, ep,
                                                           sparsity, dims, Bc, H, D, (unsigned long long *)nsubs, stage_rows,
@@ -880,6 +894,8 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
     kernel_timing_end(tok, st);
     TVO_AFTER_LAUNCH("estep_evo_bsc_gram");
   }
+  if (ovf_deferred)
+    return estep_evo_bsc_direct<T>(Y, ldY, idx, K, lpj, ws, cfg, sparsity, B, S, H, D, nsubs, stream, ovf_list, ovf_count);
   return TVO_OK;
 }
 
