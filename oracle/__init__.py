@@ -16,7 +16,7 @@ Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks it against
 The one place where the oracle *defines* rather than restates behaviour is the
 random stream: the reference draws from torch's / numpy's global generators
 (evo.py:263,325,363,414,440), which cannot be reproduced on a GPU.  The oracle
-instead specifies a counter-based Philox4x32-10 stream (``oracle.philox``) and
+instead specifies a counter-based Philox4x32-7 stream (``oracle.philox``) and
 consumes it with exactly the reference's sampling semantics (uniform parent
 subsets, one distinct bit per child, independent per-bit flips with p0/p1, ...).
 The CUDA kernels implement the same stream, so candidate sets are bit-identical

@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).
 
-Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3",
-SC'11; Random123 v1.14 ``philox.h``).  It replaces the reference's global torch /
+Philox4x32 with ROUNDS = 7 rounds (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3",
+SC'11; Random123 v1.14 ``philox.h``: "Philox4x32-7", the smallest round count that passes BigCrush with margin;
+the library default of 10 only adds safety margin).  It replaces the reference's global torch /
 numpy generators (tvo/variational/evo.py:263,325,363,414,440;
 RandomSampledVarStates.py:57) with an addressable stream so that a datapoint's
 candidates depend only on (seed, E-step counter, global datapoint index,
@@ -40,14 +41,18 @@ def make_tag(step, gen, purpose):
     return np.uint32(((int(step) & 0x7FFFFF) << 9) | ((int(gen) & 63) << 3) | (int(purpose) & 7))
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
-    """Vectorised Philox4x32-10.  All inputs broadcast; returns 4 uint32 arrays."""
+ROUNDS = 7  # part of the stream specification (csrc/common.cuh: kPhiloxRounds)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1, rounds=None):
+    """Vectorised Philox4x32-R (R = ROUNDS unless given).  All inputs broadcast; returns 4 uint32 arrays.
+    (The name is historical: rounds=10 gives Random123's philox4x32_10, pinned by its known-answer vectors.)"""
     c0, c1, c2, c3 = np.broadcast_arrays(*(np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3)))
     c0, c1, c2, c3 = c0.copy(), c1.copy(), c2.copy(), c3.copy()
     k0 = np.uint32(k0)
     k1 = np.uint32(k1)
     with np.errstate(over="ignore"):
-        for _ in range(10):
+        for _ in range(ROUNDS if rounds is None else rounds):
             p0 = M0 * c0.astype(np.uint64)
             p1 = M1 * c2.astype(np.uint64)
             hi0 = (p0 >> np.uint64(32)).astype(np.uint32)

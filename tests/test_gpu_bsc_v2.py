@@ -165,7 +165,9 @@ def test_own_gemms_match_library(N):
     q = to.softmax(lp, dim=1)
     E = (q[:, :, None] * to.as_tensor(a[0], device=DEV).double()).sum(dim=1)
     WpT = (E.t() @ dev(Y)).cpu().numpy()
-    assert np.allclose(a[3][: H * D].reshape(H, D), WpT, rtol=1e-10, atol=1e-10 * np.abs(WpT).max())
+    # <s> is accumulated in 2^-56 fixed point: absolute accuracy S 2^-56 ~ 1e-15 per unit and datapoint (N = 1 with a
+    # dominant empty state has |WpT| ~ 1e-37 altogether)
+    assert np.allclose(a[3][: H * D].reshape(H, D), WpT, rtol=1e-10, atol=1e-10 * np.abs(WpT).max() + 1e-14 * N * np.abs(Y).max())
 
 
 @pytest.mark.parametrize("N,H,D", [(1, 256, 144), (100, 256, 144), (129, 256, 144), (4099, 256, 144), (300, 128, 64), (77, 64, 40)])

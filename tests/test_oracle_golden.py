@@ -477,3 +477,22 @@ def test_tvae_layer0_helpers():
     for r, s in enumerate(K.reshape(-1, 70)):
         ref[np.flatnonzero(s)] += g[r]
     assert np.allclose(gw, ref, rtol=1e-13, atol=1e-13)
+
+
+def test_philox_known_answers_random123():
+    """The counter-based stream is Philox4x32 (Salmon et al. SC'11) with 7 rounds; the restatement is pinned on the
+    known-answer vectors of Random123 v1.14 (`kat_vectors`: philox4x32 10 and 7 rounds; zero, all-ones and pi-digit
+    counter / key)."""
+    from oracle import philox as px
+    kats = {
+        10: [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+             ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+             ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+              (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))],
+        7: [((0, 0, 0, 0), (0, 0), (0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48))],
+    }
+    for rounds, cases in kats.items():
+        for ctr, key, want in cases:
+            got = px.philox4x32_10(*[np.uint32(c) for c in ctr], np.uint32(key[0]), np.uint32(key[1]), rounds=rounds)
+            assert tuple(int(x) for x in got) == want, (rounds, ctr)
+    assert px.ROUNDS == 7

@@ -38,12 +38,15 @@ __host__ __device__ inline int n_words(int H) { return (H + 63) >> 6; }
 __host__ __device__ inline int pad32(int D) { return (D + 31) & ~31; }
 
 // ------------------------------------------------------------------------------------ Philox
-// Philox4x32-10 (Salmon et al. SC'11).  Same stream definition as oracle/philox.py.
+// Philox4x32 with kPhiloxRounds = 7 rounds (Salmon et al. SC'11: 7 is the smallest round count that passes BigCrush
+// with margin, "Philox4x32-7"; Random123's default of 10 adds safety margin only).  Same stream definition as
+// oracle/philox.py — the round count is part of the stream specification.
+constexpr int kPhiloxRounds = 7;
 // __noinline__: ~75 SASS instructions and a dozen call sites — one shared copy keeps the fused kernels
 // inside the instruction cache (ncu: 35% of warp stalls were instruction-fetch misses when inlined)
 static __device__ __noinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kPhiloxRounds; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
