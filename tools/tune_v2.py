@@ -27,6 +27,8 @@ for v in variants:
     np.random.seed(0)
     _lib.call("tvo_bsc_estep_variant", v)
     model = BSC(H, D, W0.to(PREC), to.tensor([1.0], dtype=PREC), to.full((H,), 1.0 / H, dtype=PREC), precision=PREC)
+    if os.environ.get("CHUNK"):
+        model.scratch_datapoints = int(os.environ["CHUNK"])
     st = EVOVariationalStates(N, H, S, PREC, "randparents", "sparseflip", n_parents=16, n_generations=2, n_children=2,
                               bitflip_frequency=1.0 / H, seed=2024)
     for _ in range(6):  # same warm-up trajectory as bench.py (EM iterations from the 1/H init)

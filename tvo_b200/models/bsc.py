@@ -76,7 +76,8 @@ class BSC(Optimized, Sampler, Reconstructor):
         self._fresh = None  # (theta versions, batch ptr/version): lpj in `states` was computed from these
         self._last_F = None
         self.use_gram = True  # Gram-form fused E-step (False: direct column-walk form, D <= 256)
-        self.scratch_datapoints = 131072  # chunk size of the Gram E-step / M-step GEMMs (scratch = chunk*H*8 B)
+        self.scratch_datapoints = 524288  # chunk size of the Gram E-step / M-step GEMMs (scratch ~ chunk*(H*8+12) B = 1.1 GB at
+        #                                   H = 256; 131072 cost 2.5 % of the E-step and 13 % of the M-step in launch tails)
         self._scratch = None
         self.W_solver = "gpu"  # "gpu": Cholesky on the device with lstsq as fallback; "gpu_lstsq": torch.linalg.lstsq
         #                        on the device (as the reference under TVO_GPU); "cpu": rank-revealing gelsy on the host
@@ -98,7 +99,7 @@ class BSC(Optimized, Sampler, Reconstructor):
 
     def _get_scratch(self, B: int) -> Tensor:
         D, H = self._shape
-        n = min(max(int(B), 1), int(self.scratch_datapoints))
+        n = min(max(int(B), 1), int(self.scratch_datapoints), max(1024, (2 << 30) // (H * 8)))  # at most ~2 GB of scratch
         # chunk rows (a = W^T y / E and the fp64 copy of Y for fp32 models) + the E-step's sparseflip table / overflow list
         f64 = int(self._precision == to.float64)
         nbytes = max(_lib.lib().tvo_bsc_estep_scratch_bytes(n, H, f64), _lib.lib().tvo_bsc_mstep_scratch_bytes(n, H, D, f64))
