@@ -391,12 +391,13 @@ def _other_configs(to, dev, hbm_peak, peak_src, steps=3, warmup=2):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import workloads
     out = {}
-    for key, make, N in (("configs[2] C3", workloads.make_c3, 200_000), ("configs[3] C4", workloads.make_c4, 500_000),
+    for key, make, N in (("configs[1] C2, converged model (workload realism: denser states)", workloads.make_c2_converged, 500_000),
+                         ("configs[2] C3", workloads.make_c3, 200_000), ("configs[3] C4", workloads.make_c4, 500_000),
                          ("configs[4] C5 (one GPU's 1/8 share would be 125k)", workloads.make_c5, 100_000)):
         try:
             wl = make(dev, N)
             sampler = ClockSampler(dev.index or 0, None)
-            r = _time_em(to, None, 1, wl, steps, warmup, sampler)
+            r = _time_em(to, None, 1, wl, steps, 60 if "converged" in key else warmup, sampler)
             ach = wl["alg_bytes_per_dp"] * N / (r["estep_ms"] * 1e-3) / 1e9
             out[key] = {
                 "workload": wl["name"], "N": N, "steps": steps, "warmup": warmup,

@@ -17,7 +17,8 @@ def _alg_bytes(D, wy, S, H, w):
     return D * wy + 2 * S * ((H + 63) // 64) * 8 + S * w
 
 
-def make_bsc(dev, N, H, D, S, P, C, G, pi_gen, prec=to.float64, seed=3, states_seed=5, n_offset=0, data_seed=None):
+def make_bsc(dev, N, H, D, S, P, C, G, pi_gen, prec=to.float64, seed=3, states_seed=5, n_offset=0, data_seed=None,
+             at_generating_parameters=False):
     """C2 / C5: W_gen ~ N(0,1), s ~ Bern(pi_gen), Y = W s + N(0,1); init W = W_gen + 0.5 N(0,1), pi = 1/H, sigma2 = 1;
     EVO randparents + sparseflip, p_bf = 1/H.  `seed` fixes theta (identical on all ranks), `data_seed` the shard."""
     from tvo_b200.models import BSC
@@ -32,17 +33,28 @@ def make_bsc(dev, N, H, D, S, P, C, G, pi_gen, prec=to.float64, seed=3, states_s
         Y[b0:b1] = (s @ Wgen.t() + to.randn(b1 - b0, D, dtype=to.float64, device=dev, generator=gd)).to(prec)
     del s
     np.random.seed(0)  # K init: the reference's scheme, S unique Bernoulli(1/H) states repeated for every datapoint
-    model = BSC(H, D, W0.to(prec), to.tensor([1.0], dtype=prec), to.full((H,), 1.0 / H, dtype=prec), precision=prec)
+    if at_generating_parameters:  # a converged model: theta = the generating parameters, states as dense as the data
+        W0, pi0 = Wgen, pi_gen
+    else:
+        pi0 = 1.0 / H
+    model = BSC(H, D, W0.to(prec), to.tensor([1.0], dtype=prec), to.full((H,), pi0, dtype=prec), precision=prec)
     states = EVOVariationalStates(N, H, S, prec, "randparents", "sparseflip", n_parents=P, n_generations=G, n_children=C,
                                   bitflip_frequency=1.0 / H, seed=states_seed)
     states.n_offset = n_offset
     w = 8 if prec == to.float64 else 4
-    name = (f"BSC H{H} D{D} S{S} EVO(randparents,sparseflip,P{P},C{C},G{G}) {'fp64' if w == 8 else 'fp32'}")
+    name = (f"BSC H{H} D{D} S{S} EVO(randparents,sparseflip,P{P},C{C},G{G}) {'fp64' if w == 8 else 'fp32'}"
+            + (" at the generating parameters (pi = 5/H)" if at_generating_parameters else ""))
     return dict(model=model, states=states, Y=Y, name=name, H=H, D=D, S=S, alg_bytes_per_dp=_alg_bytes(D, w, S, H, w))
 
 
 def make_c2(dev, N, **kw):
     return make_bsc(dev, N, 256, 144, 64, 16, 2, 2, 5.0 / 256, **kw)
+
+
+def make_c2_converged(dev, N, **kw):
+    """configs[1] with theta at the generating parameters: after a few E-steps K holds states as dense as the data
+    (mean |s| ~ 4-5 instead of ~1.1 early in training from the pi = 1/H initialisation)."""
+    return make_bsc(dev, N, 256, 144, 64, 16, 2, 2, 5.0 / 256, at_generating_parameters=True, **kw)
 
 
 def make_c5(dev, N, **kw):
