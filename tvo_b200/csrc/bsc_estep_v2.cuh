@@ -17,7 +17,7 @@
 // Same random stream, same draws and the same results as the generic kernel (estep_device.cuh) and the oracle:
 // candidate selection, flip counts, rejection order and the n-th-remaining rule are restated on lists.
 //
-// Datapoints the lists cannot hold — a state with more than 15 active units, more than 8 added units in one child,
+// Datapoints the lists cannot hold — a state or child with more than 15 active units,
 // a NaN in y (nansum form), the (practically unreachable) rejection cap — are appended to an overflow list and
 // processed by the generic kernel in a second launch; nothing has been written for them.
 #pragma once
@@ -26,7 +26,7 @@
 namespace tvo {
 
 constexpr int kV2MaxList = 15;  // positions per list
-constexpr int kV2MaxAdd = 8;    // added units per child (sorted bytes in one 64-bit register)
+constexpr int kV2MaxAdd = 15;   // added units per child (sorted bytes in a 16-byte shared-memory slot of the lane)
 
 struct V2Dims {
   int S, Snew, Sgen, P, C, G, W64, H;
@@ -562,7 +562,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
           uint4 r = make_uint4(0u, 0u, 0u, 0u);
           // zero bits: k0 of the H - a candidates by rejection over all H positions (H - a >= 49: the dense class,
           // never its complement form)
-          uint64_t add = 0;  // added positions, ascending bytes
+          unsigned char *ab = (unsigned char *)hash + lane * 16;  // added positions, ascending (the hash region is idle here)
           int ka = 0;
           if (k0 > kV2MaxAdd) {
             bail = true;
@@ -580,16 +580,16 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
 #pragma unroll 1
               for (int i = 0; i < a; ++i) taken |= ((uint32_t)pb[i] == pos);
               int below = 0;
-              uint64_t aa = add;
 #pragma unroll 1
-              for (int q = 0; q < ka; ++q, aa >>= 8) {
-                const uint32_t z = (uint32_t)aa & 0xFFu;
+              for (int q = 0; q < ka; ++q) {
+                const uint32_t z = ab[q];
                 taken |= (z == pos);
                 below += (z < pos) ? 1 : 0;
               }
               if (!taken) {  // sorted insert at byte `below`
-                const uint64_t lowmask = below >= 8 ? ~0ull : ((1ull << (8 * below)) - 1ull);
-                add = (add & lowmask) | ((uint64_t)pos << (8 * below)) | ((add & ~lowmask) << 8);
+#pragma unroll 1
+                for (int q = ka; q > below; --q) ab[q] = ab[q - 1];
+                ab[below] = (unsigned char)pos;
                 ++ka;
               }
             }
@@ -638,10 +638,9 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
             dl -= t1;
           }
           {
-            uint64_t aq = add;
 #pragma unroll 1
-            for (int q = 0; q < ka; ++q, aq >>= 8) {
-              const uint32_t z = (uint32_t)aq & 0xFFu;
+            for (int q = 0; q < ka; ++q) {
+              const uint32_t z = ab[q];
               double t1 = dsm[z];
               const double *g2 = G2 + (size_t)z * H;
               for (uint32_t mm = kept; mm;) {
@@ -649,9 +648,8 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
                 mm &= mm - 1;
                 t1 += g2[pb[i2]];
               }
-              uint64_t a2 = add;
 #pragma unroll 1
-              for (int q2 = 0; q2 < q; ++q2, a2 >>= 8) t1 += g2[(uint32_t)a2 & 0xFFu];
+              for (int q2 = 0; q2 < q; ++q2) t1 += g2[ab[q2]];
               dl += t1;
             }
           }
@@ -661,8 +659,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
           if (nc <= kV2MaxList) {
             unsigned char *cb = (unsigned char *)(lists + child);
             int m = 0, q = 0;
-            uint64_t ar = add;  // the added positions not yet written, ascending from the low byte
-            uint32_t nextz = ka ? (uint32_t)ar & 0xFFu : 256u;
+            uint32_t nextz = ka ? (uint32_t)ab[0] : 256u;  // the next added position not yet written
             for (uint32_t mm = kept; mm;) {
               const int i = __ffs((int)mm) - 1;
               mm &= mm - 1;
@@ -670,13 +667,12 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
               while (nextz < e) {
                 cb[m++] = (unsigned char)nextz;
                 ++q;
-                ar >>= 8;
-                nextz = q < ka ? (uint32_t)ar & 0xFFu : 256u;
+                nextz = q < ka ? (uint32_t)ab[q] : 256u;
               }
               cb[m++] = (unsigned char)e;
             }
 #pragma unroll 1
-            for (; q < ka; ++q, ar >>= 8) cb[m++] = (unsigned char)((uint32_t)ar & 0xFFu);
+            for (; q < ka; ++q) cb[m++] = ab[q];
             cb[15] = (unsigned char)m;
           }
           lpjs[child] = lpjs[src] + dl;
