@@ -31,6 +31,9 @@ from tvo_b200.variational._packed import PackedStates, as_packed
 from tvo_b200.variational._utils import mean_posterior, state_marginals
 
 
+_SIDE = {}  # device -> (side stream, pinned 2-double buffer) for the factorisation flags of update_param_epoch
+
+
 class BSC(Optimized, Sampler, Reconstructor):
     def __init__(
         self,
@@ -74,6 +77,7 @@ class BSC(Optimized, Sampler, Reconstructor):
         self._stats = to.zeros(H * D + H * H + H + 3, dtype=to.float64, device=device)
         self._ws = None
         self._fresh = None  # (theta versions, batch ptr/version): lpj in `states` was computed from these
+        self._ws_token = None  # (theta versions, stream) the workspace was digested from
         self._last_F = None
         self.use_gram = True  # Gram-form fused E-step (False: direct column-walk form, D <= 256)
         self.scratch_datapoints = 524288  # chunk size of the Gram E-step / M-step GEMMs (scratch ~ chunk*(H*8+12) B = 1.1 GB at
@@ -141,6 +145,13 @@ class BSC(Optimized, Sampler, Reconstructor):
         nbytes = _lib.lib().tvo_bsc_theta_ws_bytes(H, D, int(prec == to.float64))
         if self._ws is None or self._ws.numel() != nbytes or self._ws.device != W.device:
             self._ws = to.empty(nbytes, dtype=to.uint8, device=W.device)
+            self._ws_token = None
+        # theta unchanged since the last digestion on this stream (in-place torch writes bump the tensors' versions,
+        # update_param_epoch drops the token): the E-step and the M-step of one batch share one digestion
+        token = (self._theta_token(), _lib.stream())
+        if self._ws_token == token:
+            return self._ws
+        self._ws_token = token
         _lib.call(f"tvo_bsc_prepare_{_lib.sfx(prec)}", _lib.ptr(W), _lib.ptr(pies), pies.numel(), _lib.ptr(s2), H, D,
                   _lib.ptr(self._ws), _lib.stream())
         return self._ws
@@ -271,6 +282,7 @@ class BSC(Optimized, Sampler, Reconstructor):
         self._last_F = self._stats[-1].clone()
         self._last_N = self.my_N.clone()
         self._fresh = None  # theta changes under the lpj stored in the states
+        self._ws_token = None
         prec = self._precision
         Wold_noisy = theta["W"] + 0.1 * to.randn_like(theta["W"])  # always drawn, as in the reference (bsc.py:174)
         WpT = self._stats[: H * D].view(H, D)
@@ -284,9 +296,23 @@ class BSC(Optimized, Sampler, Reconstructor):
                       _lib.stream())
             L, info = to.linalg.cholesky_ex(self._wq_full)
             dg = to.diagonal(L)
-            flags = to.stack([info.to(to.float64), dg.min() / dg.max()]).tolist()  # one host read per EM iteration
-            if flags[0] == 0 and flags[1] > 1e-6:  # cond(my_Wq) ~ (max/min pivot)^2 < 1e12
-                sol = to.cholesky_solve(WpT, L)
+            flags_dev = to.stack([info.to(to.float64), dg.min() / dg.max()])
+            # one host read per EM iteration, taken on a side stream while the triangular solves already run on the
+            # launching stream (the solution is dropped if the factorisation turns out unusable)
+            dev = self._stats.device
+            if dev not in _SIDE:
+                _SIDE[dev] = (to.cuda.Stream(device=dev), to.empty(2, dtype=to.float64).pin_memory())
+            side, flags_host = _SIDE[dev]
+            factored = to.cuda.Event()
+            factored.record()
+            sol = to.cholesky_solve(WpT, L)
+            with to.cuda.stream(side):
+                side.wait_event(factored)
+                flags_host.copy_(flags_dev, non_blocking=True)
+                side.synchronize()
+            flags = flags_host.tolist()
+            if not (flags[0] == 0 and flags[1] > 1e-6):  # cond(my_Wq) ~ (max/min pivot)^2 < 1e12
+                sol = None
         if sol is None:
             try:
                 Wq = self._wq_full if (self.W_solver == "gpu" and direct) else self.my_Wq
