@@ -67,6 +67,10 @@ def make(rng, N, H, D, S, p_state, pies_val, dense_rows=(), nan_rows=()):
     (130, 30, 100, 20, 3, 2, 1.5),   # three words, S' = 120
     (200, 16, 128, 32, 4, 1, 1.0),   # S = S' = 128 (EPL 4)
     (256, 40, 17, 5, 7, 2, 6.0),     # many flips per child: more than 8 added units happen -> overflow hand-back
+    (257, 24, 40, 8, 3, 2, 1.5),     # two-byte positions (H > 256), five words (odd), d_h gathered from the a row
+    (600, 32, 50, 10, 2, 2, 3.0),    # ten words
+    (1024, 64, 128, 16, 4, 2, 1.0),  # BASELINE configs[4] (D reduced for the oracle)
+    (1000, 20, 24, 6, 5, 1, 8.0),    # many flips per child at H > 256
 ])
 def test_v2_matches_oracle_and_generic(H, D, S, P, Cn, G, pbf_mult):
     rng = np.random.default_rng(H * 7 + S)

@@ -26,7 +26,27 @@
 namespace tvo {
 
 constexpr int kV2MaxList = 15;  // positions per list
-constexpr int kV2MaxAdd = 15;   // added units per child (sorted bytes in a 16-byte shared-memory slot of the lane)
+constexpr int kV2MaxAdd = 15;   // added units per child (sorted positions in a 16-entry shared-memory slot of the lane)
+
+// Position type PT: one byte for H <= 256 (a list = one uint4), two bytes for 256 < H <= 1024 (BASELINE configs[4]:
+// a list = two uint4).  Entry 15 holds the count either way.
+template <typename PT>
+struct PLT;
+template <>
+struct PLT<unsigned char> {
+  static constexpr int kBytes = 16;
+  static constexpr uint32_t kNone = 256u;  // larger than any position
+};
+template <>
+struct PLT<unsigned short> {
+  static constexpr int kBytes = 32;
+  static constexpr uint32_t kNone = 65536u;
+};
+__host__ __device__ inline int v2_list_bytes(int H) { return H <= 256 ? 16 : 32; }
+// d_h = gp_h - 2 coef a_h staged in shared memory for all H units (H <= 256), or gathered from the a row on demand
+// (H > 256: a datapoint touches a few hundred of the 1024 units, staging would cost 8 kB per warp and halve the
+// resident warps)
+__host__ __device__ inline bool v2_stage_d(int H) { return H <= 256; }
 
 struct V2Dims {
   int S, Snew, Sgen, P, C, G, W64, H;
@@ -37,16 +57,18 @@ struct V2Dims {
 // hash region: the dedup hashes, afterwards the survivors of the merge (8-byte composite keys or 4-byte indices)
 __host__ __device__ inline size_t v2_hash_bytes(const V2Dims &d) {
   const size_t h = (size_t)hash_len(d.S, d.Snew) * 4, k = (size_t)d.Snew * 8;
-  return align16(h > k ? h : k);
+  const size_t ab = (size_t)32 * v2_list_bytes(d.H);  // during mutation: one slot of added positions per lane
+  const size_t m = h > k ? h : k;
+  return align16(m > ab ? m : ab);
 }
 __host__ __device__ inline size_t v2_warp_bytes(const V2Dims &d) {
   const int nI = d.P > d.S ? d.P : d.S;
-  return (size_t)(d.S + d.Snew) * 16 + align16((size_t)(d.S + d.Snew) * 8) + v2_hash_bytes(d) + align16((size_t)nI * 4) +
-         align16((size_t)d.H * 8);
+  return (size_t)(d.S + d.Snew) * v2_list_bytes(d.H) + align16((size_t)(d.S + d.Snew) * 8) + v2_hash_bytes(d) +
+         align16((size_t)nI * 4) + (v2_stage_d(d.H) ? align16((size_t)d.H * 8) : 0);
 }
 
 __host__ inline void v2_finish(V2Dims &d) {
-  d.off_lpj = (d.S + d.Snew) * 16;
+  d.off_lpj = (d.S + d.Snew) * v2_list_bytes(d.H);
   d.off_hash = d.off_lpj + (int)align16((size_t)(d.S + d.Snew) * 8);
   d.off_iscr = d.off_hash + (int)v2_hash_bytes(d);
   d.off_d = d.off_iscr + (int)align16((size_t)(d.P > d.S ? d.P : d.S) * 4);
@@ -56,22 +78,50 @@ __host__ inline void v2_finish(V2Dims &d) {
 
 __host__ inline bool v2_supported(const EvoParams &ep, const V2Dims &d) {
   return ep.sel == TVO_SEL_RANDPARENTS && ep.mut == TVO_MUT_SPARSEFLIP && ep.flip_tab != nullptr && d.H >= 64 &&
-         d.H <= 256 && d.S <= 128 && d.Sgen <= 128 && d.Snew <= 128;
+         d.H <= 1024 && d.S <= 128 && d.Sgen <= 128 && d.Snew <= 128;
 }
 
 // ---- position lists ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool pl_equal(const uint4 &a, const uint4 &b) {
   return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) == 0u;
 }
-__device__ __forceinline__ uint32_t pl_hash(const uint4 &l) {
-  uint32_t h = (l.x * 0x9E3779B1u) ^ (l.y * 0x85EBCA77u) ^ (l.z * 0xC2B2AE3Du) ^ (l.w * 0x27D4EB2Fu);
+__device__ __forceinline__ uint32_t pl_mix(const uint4 &l) {
+  return (l.x * 0x9E3779B1u) ^ (l.y * 0x85EBCA77u) ^ (l.z * 0xC2B2AE3Du) ^ (l.w * 0x27D4EB2Fu);
+}
+// lists of a warp: `base` + i * PLT<PT>::kBytes
+template <typename PT>
+__device__ __forceinline__ PT *pl_at(unsigned char *base, int i) {
+  return (PT *)(base + (size_t)i * PLT<PT>::kBytes);
+}
+template <typename PT>
+__device__ __forceinline__ const PT *pl_at(const unsigned char *base, int i) {
+  return (const PT *)(base + (size_t)i * PLT<PT>::kBytes);
+}
+template <typename PT>
+__device__ __forceinline__ void pl_clear(unsigned char *base, int i) {
+  uint4 *q = (uint4 *)(base + (size_t)i * PLT<PT>::kBytes);
+  q[0] = make_uint4(0u, 0u, 0u, 0u);
+  if (PLT<PT>::kBytes == 32) q[1] = make_uint4(0u, 0u, 0u, 0u);
+}
+template <typename PT>
+__device__ __forceinline__ bool pl_same(const unsigned char *base, int i, int j) {
+  const uint4 *a = (const uint4 *)(base + (size_t)i * PLT<PT>::kBytes), *b = (const uint4 *)(base + (size_t)j * PLT<PT>::kBytes);
+  bool eq = pl_equal(a[0], b[0]);
+  if (PLT<PT>::kBytes == 32) eq = eq && pl_equal(a[1], b[1]);
+  return eq;
+}
+template <typename PT>
+__device__ __forceinline__ uint32_t pl_hash(const unsigned char *base, int i) {
+  const uint4 *a = (const uint4 *)(base + (size_t)i * PLT<PT>::kBytes);
+  uint32_t h = pl_mix(a[0]);
+  if (PLT<PT>::kBytes == 32) h = (h * 0x165667B1u) ^ pl_mix(a[1]) ^ (h >> 13);
   h ^= h >> 15;
   return h | 1u;  // odd: the zero padding of the hash runs never matches
 }
 
 // ---- dedup (same scan as mark_redundant_cpl, states compared as lists) ------------------------------------------
-template <typename T, int CPL>
-__device__ __forceinline__ void v2_mark_redundant_cpl(const uint4 *lists, double *lpjs, const uint32_t *hash, int S,
+template <typename T, int CPL, typename PT>
+__device__ __forceinline__ void v2_mark_redundant_cpl(const unsigned char *lists, double *lpjs, const uint32_t *hash, int S,
                                                       int Snew, int lane) {
   const int Sp = hash_old_pad(S), Snp = (Snew + 3) & ~3;
   const uint32_t *ho = hash, *hn = hash + Sp;
@@ -131,13 +181,12 @@ __device__ __forceinline__ void v2_mark_redundant_cpl(const uint4 *lists, double
     for (int t = 0; t < CPL; ++t) {
       const int c = c0 + 32 * t + lane;
       if (c < Snew && hit[t] >= 0) {
-        const uint4 mine = lists[S + c];
-        bool dup = pl_equal(lists[hit[t]], mine);
+        bool dup = pl_same<PT>(lists, hit[t], S + c);
         if (!dup) {  // hash collision: exhaustive rescan (practically never)
           for (int j2 = 0; j2 < S && !dup; ++j2)
-            if (ho[j2] == hc[t]) dup = pl_equal(lists[j2], mine);
+            if (ho[j2] == hc[t]) dup = pl_same<PT>(lists, j2, S + c);
           for (int j2 = c + 1; j2 < Snew && !dup; ++j2)
-            if (hn[j2] == hc[t]) dup = pl_equal(lists[S + j2], mine);
+            if (hn[j2] == hc[t]) dup = pl_same<PT>(lists, S + j2, S + c);
         }
         if (dup) lpjs[S + c] = (double)LowLpj<T>::v();
       }
@@ -396,7 +445,7 @@ __device__ __forceinline__ bool v2_select_merge_ck(const double *lpjs, uint64_t 
 // ---- the kernel -----------------------------------------------------------------------------------------------
 // ES / EG / EN: elements per lane that hold S, S_gen and S_new (1, 2 or 4): only the networks of one shape class are
 // compiled into a kernel (the instruction cache is the scarce resource here)
-template <typename T, int ES, int EG, int EN>
+template <typename T, int ES, int EG, int EN, typename PT = unsigned char>
 __global__ void __launch_bounds__(256, 4)
 estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ A, const int64_t *__restrict__ idx,
                         int64_t row0, uint64_t *__restrict__ K, T *__restrict__ lpj, const void *ws, EvoParams ep,
@@ -408,11 +457,12 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
   const int S = dims.S, Snew = dims.Snew, Sgen = dims.Sgen, W64 = dims.W64, H = dims.H;
   const BscTheta<T> th = bsc_theta_view<T>(ws, H, D);
   unsigned char *p = smem_raw + wib * dims.warp_bytes;
-  uint4 *lists = (uint4 *)p;                        // S old + Snew children
+  constexpr bool kStageD = sizeof(PT) == 1;         // == v2_stage_d(H)
+  unsigned char *lists = p;                         // S old + Snew children, PLT<PT>::kBytes each
   double *lpjs = (double *)(p + dims.off_lpj);      // their lpj, fp64
   uint32_t *hash = (uint32_t *)(p + dims.off_hash);  // dedup hashes; survivor list of the merge afterwards
   int32_t *iscr = (int32_t *)(p + dims.off_iscr);   // chosen parents (P); order of the merged set (S)
-  double *dsm = (double *)(p + dims.off_d);         // d_h = gp_h - 2 coef a_h of this datapoint, all H units
+  double *dsm = (double *)(p + dims.off_d);         // d_h = gp_h - 2 coef a_h of this datapoint, all H units (kStageD)
   const double coef = th.hdr->coef, m2c = -2.0 * coef;
   const double *__restrict__ G2 = th.G2;
   const double *__restrict__ gp = th.gp;
@@ -449,7 +499,10 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
     }
     const double yyc = yy * coef;
     __syncwarp();  // the previous datapoint's readers of this warp's shared memory are done
-    if ((H & 1) == 0 && sizeof(T) == 8) {  // coalesced read of the a row, two units per lane
+#define V2_D(h) (kStageD ? dsm[h] : fma(m2c, (double)a_row[h], gp[h]))
+    if (!kStageD) {
+      // d_h gathered on demand
+    } else if ((H & 1) == 0 && sizeof(T) == 8) {  // coalesced read of the a row, two units per lane
       for (int h = 2 * lane; h < H; h += 64) {
         const double2 av = *reinterpret_cast<const double2 *>(a_row + h), gv = *reinterpret_cast<const double2 *>(gp + h);
         *reinterpret_cast<double2 *>(dsm + h) = make_double2(fma(m2c, av.x, gv.x), fma(m2c, av.y, gv.y));
@@ -464,8 +517,8 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
     for (int s0 = 0; s0 < S && active; s0 += 32) {
       const int s = s0 + lane;
       if (s < S) {
-        lists[s] = make_uint4(0u, 0u, 0u, 0u);
-        unsigned char *lb = (unsigned char *)(lists + s);
+        pl_clear<PT>(lists, s);
+        PT *lb = pl_at<PT>(lists, s);
         const uint32_t *st = (const uint32_t *)(Krow + (size_t)s * W64);  // 2 W64 half words
         // which half words are non-empty and how many units are active; then ONE loop over the active units that
         // re-reads a half word (an L1 hit) only when the current one is used up: the warp iterates max-over-lanes |s|
@@ -501,13 +554,13 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
           }
           const int h = (hw << 5) + __ffs((int)m) - 1;
           m &= m - 1;
-          acc += dsm[h];
+          acc += V2_D(h);
           const double *g2 = G2 + (size_t)h * H;
 #pragma unroll 1
           for (int i = 0; i < n; ++i) acc += g2[lb[i]];
-          lb[n] = (unsigned char)h;
+          lb[n] = (PT)h;
         }
-        lb[15] = (unsigned char)ntot;
+        lb[15] = (PT)ntot;
         lpjs[s] = acc;
       }
     }
@@ -539,7 +592,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
         const int j = j0 + lane;
         if (j < Sgen) {
           const int src = cand_base + iscr[(j * dims.cinv) >> 16];  // j / C
-          const unsigned char *pb = (const unsigned char *)(lists + src);  // the parent's list
+          const PT *pb = pl_at<PT>(lists, src);  // the parent's list
           const int a = (int)pb[15];
           // flip counts (batch_sparseflip evo.py:310-329 as Binomial counts, mutate_sparseflip of estep_device.cuh)
           const FlipEntry *te = ep.flip_tab + a;
@@ -562,7 +615,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
           uint4 r = make_uint4(0u, 0u, 0u, 0u);
           // zero bits: k0 of the H - a candidates by rejection over all H positions (H - a >= 49: the dense class,
           // never its complement form)
-          unsigned char *ab = (unsigned char *)hash + lane * 16;  // added positions, ascending (the hash region is idle here)
+          PT *ab = pl_at<PT>((unsigned char *)hash, lane);  // added positions, ascending (the hash region is idle here)
           int ka = 0;
           if (k0 > kV2MaxAdd) {
             bail = true;
@@ -589,7 +642,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
               if (!taken) {  // sorted insert at byte `below`
 #pragma unroll 1
                 for (int q = ka; q > below; --q) ab[q] = ab[q - 1];
-                ab[below] = (unsigned char)pos;
+                ab[below] = (PT)pos;
                 ++ka;
               }
             }
@@ -628,7 +681,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
             const int i = __ffs((int)f) - 1;
             f &= f - 1;
             const uint32_t h = pb[i];
-            double t1 = dsm[h];
+            double t1 = V2_D(h);
             const double *g2 = G2 + (size_t)h * H;
             for (uint32_t mm = kept | f; mm;) {  // kept units and the removed ones after i
               const int i2 = __ffs((int)mm) - 1;
@@ -641,7 +694,7 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
 #pragma unroll 1
             for (int q = 0; q < ka; ++q) {
               const uint32_t z = ab[q];
-              double t1 = dsm[z];
+              double t1 = V2_D(z);
               const double *g2 = G2 + (size_t)z * H;
               for (uint32_t mm = kept; mm;) {
                 const int i2 = __ffs((int)mm) - 1;
@@ -655,25 +708,25 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
           }
           // the child's list: kept entries merged with the added positions, ascending
           const int child = S + g * Sgen + j;
-          lists[child] = make_uint4(0u, 0u, 0u, 0u);
+          pl_clear<PT>(lists, child);
           if (nc <= kV2MaxList) {
-            unsigned char *cb = (unsigned char *)(lists + child);
+            PT *cb = pl_at<PT>(lists, child);
             int m = 0, q = 0;
-            uint32_t nextz = ka ? (uint32_t)ab[0] : 256u;  // the next added position not yet written
+            uint32_t nextz = ka ? (uint32_t)ab[0] : PLT<PT>::kNone;  // the next added position not yet written
             for (uint32_t mm = kept; mm;) {
               const int i = __ffs((int)mm) - 1;
               mm &= mm - 1;
               const uint32_t e = pb[i];
               while (nextz < e) {
-                cb[m++] = (unsigned char)nextz;
+                cb[m++] = (PT)nextz;
                 ++q;
-                nextz = q < ka ? (uint32_t)ab[q] : 256u;
+                nextz = q < ka ? (uint32_t)ab[q] : PLT<PT>::kNone;
               }
-              cb[m++] = (unsigned char)e;
+              cb[m++] = (PT)e;
             }
 #pragma unroll 1
             for (; q < ka; ++q) cb[m++] = ab[q];
-            cb[15] = (unsigned char)m;
+            cb[15] = (PT)m;
           }
           lpjs[child] = lpjs[src] + dl;
         }
@@ -689,10 +742,10 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
     // ---- dedup: a child equal to a later child or to an old state is redundant (_set_redundant_lpj_to_low) ----
     {
       const int Sp = hash_old_pad(S), Snp = (Snew + 3) & ~3;
-      for (int i = lane; i < Sp; i += 32) hash[i] = i < S ? pl_hash(lists[i]) : 0u;
-      for (int i = lane; i < Snp; i += 32) hash[Sp + i] = i < Snew ? pl_hash(lists[S + i]) : 0u;
+      for (int i = lane; i < Sp; i += 32) hash[i] = i < S ? pl_hash<PT>(lists, i) : 0u;
+      for (int i = lane; i < Snp; i += 32) hash[Sp + i] = i < Snew ? pl_hash<PT>(lists, S + i) : 0u;
       __syncwarp();
-      v2_mark_redundant_cpl<T, EN>(lists, lpjs, hash, S, Snew, lane);
+      v2_mark_redundant_cpl<T, EN, PT>(lists, lpjs, hash, S, Snew, lane);
       __syncwarp();
     }
 
@@ -710,25 +763,54 @@ estep_evo_bsc_v2_kernel(const T *__restrict__ Y, int64_t ldY, const T *__restric
     for (int p0 = 0; p0 < S; p0 += 32) {
       const int pos = p0 + lane;
       if (pos < S) {
-        const unsigned char *ob = (const unsigned char *)(lists + iscr[pos]);
+        const PT *ob = pl_at<PT>(lists, iscr[pos]);
         const int n = (int)ob[15];
-        uint64_t wd[4] = {0ull, 0ull, 0ull, 0ull};
-        for (int i = 0; i < n; ++i) {
-          const uint32_t h = ob[i];
-          const uint64_t bit = 1ull << (h & 63u);
-          const uint32_t w = h >> 6;
+        uint64_t *dst = Krow + (size_t)pos * W64;
+        if (sizeof(PT) == 1) {  // W64 <= 4
+          uint64_t wd[4] = {0ull, 0ull, 0ull, 0ull};
+          for (int i = 0; i < n; ++i) {
+            const uint32_t h = ob[i];
+            const uint64_t bit = 1ull << (h & 63u);
+            const uint32_t w = h >> 6;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (w == (uint32_t)k) wd[k] |= bit;
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (w == (uint32_t)k) wd[k] |= bit;
+            if (k < W64) dst[k] = wd[k];
+        } else {  // the list is ascending: one pass over the words, two per 16-byte store when the row allows it
+          int i = 0;
+          uint32_t h = n ? (uint32_t)ob[0] : PLT<PT>::kNone;
+          if ((W64 & 1) == 0) {
+            for (int k = 0; k < W64; k += 2) {
+              uint64_t w0 = 0ull, w1 = 0ull;
+              while ((h >> 6) == (uint32_t)k) {
+                w0 |= 1ull << (h & 63u);
+                h = ++i < n ? (uint32_t)ob[i] : PLT<PT>::kNone;
+              }
+              while ((h >> 6) == (uint32_t)(k + 1)) {
+                w1 |= 1ull << (h & 63u);
+                h = ++i < n ? (uint32_t)ob[i] : PLT<PT>::kNone;
+              }
+              *reinterpret_cast<ulonglong2 *>(dst + k) = make_ulonglong2(w0, w1);
+            }
+          } else {
+            for (int k = 0; k < W64; ++k) {
+              uint64_t w0 = 0ull;
+              while ((h >> 6) == (uint32_t)k) {
+                w0 |= 1ull << (h & 63u);
+                h = ++i < n ? (uint32_t)ob[i] : PLT<PT>::kNone;
+              }
+              dst[k] = w0;
+            }
+          }
         }
-        uint64_t *dst = Krow + (size_t)pos * W64;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < W64) dst[k] = wd[k];
       }
     }
   }
 #undef V2_PHASE_SYNC
+#undef V2_D
   if (lane == 0 && my_subs) atomicAdd(nsubs, my_subs);
 }
 

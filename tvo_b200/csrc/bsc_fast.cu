@@ -819,7 +819,7 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
     TVO_AFTER_LAUNCH("flip_table");
     ep.flip_tab = tab;
   }
-  // list-based kernel (bsc_estep_v2.cuh) for sparse states at 64 <= H <= 256, randparents + sparseflip; the generic
+  // list-based kernel (bsc_estep_v2.cuh) for sparse states at 64 <= H <= 1024, randparents + sparseflip; the generic
   // kernel then takes the datapoints it handed back (overflow list) — or everything when the shape is not covered
   V2Dims v2{S, dims.Snew, dims.Sgen, ep.P, ep.C, ep.G, dims.W64, H, 0, 0, 0, 0, 0, 0};
   v2_finish(v2);
@@ -827,7 +827,9 @@ int estep_evo_bsc(const T *Y, int64_t ldY, const int64_t *idx, uint64_t *K, T *l
   const bool use_v2 = use_tab && v2_supported(ep, v2) && v2_smem <= (size_t)kMaxSmemFast && !g_disable_v2;
   const int eS = S <= 32 ? 1 : S <= 64 ? 2 : 4, eG = dims.Sgen <= 32 ? 1 : dims.Sgen <= 64 ? 2 : 4,
             eN = dims.Snew <= 32 ? 1 : dims.Snew <= 64 ? 2 : 4;
-  auto kern2 = eS == 1 && eG == 1 && eN == 1   ? estep_evo_bsc_v2_kernel<T, 1, 1, 1>
+  // H > 256 (two-byte positions, d_h gathered): one catch-all shape class
+  auto kern2 = H > 256                         ? estep_evo_bsc_v2_kernel<T, 4, 4, 4, unsigned short>
+               : eS == 1 && eG == 1 && eN == 1 ? estep_evo_bsc_v2_kernel<T, 1, 1, 1>
                : eS <= 2 && eG == 1 && eN <= 2 ? estep_evo_bsc_v2_kernel<T, 2, 1, 2>
                                                : estep_evo_bsc_v2_kernel<T, 4, 4, 4>;
   int occ2 = 1;
