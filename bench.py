@@ -519,7 +519,7 @@ def run_gpu(args):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"
         clocks = r["clocks"]
         estep_ms, total_ms = r["estep_ms"], r["total_ms"]
-        # dominant kernel = the fused EVO E-step kernel; its launches (one per chunk of <= 131072 datapoints) are timed
+        # dominant kernel = the fused EVO E-step kernel; its launches (one per chunk of <= 524288 datapoints) are timed
         # individually with CUDA events on the launching stream (tvo_kernel_timing_*)
         k_n = max(r["k_n"], 1)
         dp_per_launch = N * args.steps / k_n
@@ -562,7 +562,7 @@ def run_gpu(args):
                             "(double-buffered copy stream), substitution count read back each step; bytes are per rank"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "estep_evo_bsc_v2_kernel<double,2,1,2>" if HEADLINE else "estep_evo_bsc_gram_kernel<double,1>",
+                         "kernel": "estep_evo_bsc_v2_kernel<double,2,1,2>" if HEADLINE else "estep_evo_bsc_v2_kernel<double,4,4,4,unsigned short>",
                          "launch_ms": launch_ms, "launches_timed": r["k_n"], "datapoints_per_launch": dp_per_launch,
                          "algorithmic_bytes_per_datapoint": ALG_BYTES_PER_DP,
                          "traffic_source": "profiles/traffic.json (ncu --set full dram bytes per datapoint x datapoints per launch)",
@@ -571,7 +571,7 @@ def run_gpu(args):
                          "note": ("the kernel's DRAM traffic equals its algorithmic bytes (+ the a = W^T y row), but it is "
                                   "bound by instruction issue (selection, mutation, dedup, sort on sparse bit states; see "
                                   "issue_roofline), not by HBM; DESIGN.md section 5") if HEADLINE
-                         else "large-H*S variant of the kernel (one CTA per SM, latency-bound): profiles/r01j_c5.md"},
+                         else "list-based kernel with two-byte positions (H > 256), d_h gathered from the a row; a = Y W by the library DGEMM at this H"},
         }
         if weak is not None:
             line["weak"] = weak
@@ -597,7 +597,8 @@ def main():
                     help="datapoints of the whole job, sharded over the GPUs (strong scaling; the north star's N = 1M)")
     ap.add_argument("--n-weak", type=int, default=1_000_000, help="datapoints per GPU of the extra weak-scaling run")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-chunk", type=int, default=131072)
+    ap.add_argument("--e2e-chunk", type=int, default=32768,
+                    help="datapoints per host->device copy of the e2e leg (smaller: shorter un-overlapped tail)")
     ap.add_argument("--cpu-n", type=int, default=8192, help="datapoints of the reference arm's sample")
     ap.add_argument("--cpu-n-per-core", type=int, default=4096, help="datapoints per core of the port fallback")
     ap.add_argument("--port-baseline", action="store_true", help="time the oracle port even if baseline/_ref exists")
