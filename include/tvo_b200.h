@@ -173,10 +173,20 @@ int tvo_select_topS_f32(const uint64_t *new_states, const float *new_lpj, uint64
  *      fix_theta (sanity.py:76-88) applied: non-finite W entries <- W_noisy (bsc.py:174), pi clamped to
  *      [1e-5, 1-1e-5], sigma2 >= 1e-5, non-finite pi / sigma2 keep their old values. ---- */
 int tvo_bsc_symmetrize(const double *upper, double *full, int32_t H, void *stream);
+/*      tvo_bsc_epoch_solve: the solve itself (bsc.py:177-181, W^T = my_Wq^-1 my_Wp^T) for H <= 256 as a hand-written
+ *      blocked Cholesky (one CTA) + substitution (one CTA per column) straight from the packed statistics `stats`
+ *      ([WpT (H*D) | WqU (H*H upper) | ...], tvo_bsc_stats_len).  `work`: tvo_bsc_epoch_solve_work_doubles(H) doubles
+ *      (0: H not covered); `sol`: H x D;  `flags` (2 device doubles): [0] = 0 or 1 + index of the first non-positive
+ *      pivot, [1] = min/max of the factor's diagonal — the caller falls back to lstsq, as the reference does on a
+ *      failed solve, when [0] != 0 or [1] is tiny.  Deterministic: identical on every rank given identical stats. */
+int64_t tvo_bsc_epoch_solve_work_doubles(int32_t H);
+int tvo_bsc_epoch_solve(const double *stats, double *work, double *sol, double *flags, int32_t H, int32_t D, void *stream);
+/*      `guard` (device, may be NULL) = the flags of tvo_bsc_epoch_solve: when they report an unusable factorisation the
+ *      call writes nothing, so it can be queued before the host has read the flags. */
 int tvo_bsc_epoch_finish_f64(const double *stats, const double *sol, const double *W_noisy, double *W, double *pies,
-                             int32_t n_pies, double *sigma2, int32_t H, int32_t D, void *stream);
+                             int32_t n_pies, double *sigma2, int32_t H, int32_t D, const double *guard, void *stream);
 int tvo_bsc_epoch_finish_f32(const double *stats, const double *sol, const float *W_noisy, float *W, float *pies,
-                             int32_t n_pies, float *sigma2, int32_t H, int32_t D, void *stream);
+                             int32_t n_pies, float *sigma2, int32_t H, int32_t D, const double *guard, void *stream);
 
 /* ---- fused E-step for BSC: replaces EVOVariationalStates.update (evo.py:80-115) end to end:
  *      re-score K under theta, G generations of select+mutate+score with the children kept in

@@ -137,13 +137,14 @@ def test_v2_incremental_lpj_equals_full_rescore():
         assert to.unique(rows, dim=0).shape[0] == N * S  # no duplicate state inside any K_n
 
 
-@pytest.mark.parametrize("N", [1, 15, 17, 64, 200, 4099])
-def test_own_gemms_match_library(N):
+@pytest.mark.parametrize("N,H,D", [(1, 256, 144), (15, 256, 144), (17, 256, 144), (64, 256, 144), (200, 256, 144),
+                                   (4099, 256, 144), (333, 512, 48), (130, 1024, 256), (70, 768, 16)])
+def test_own_gemms_match_library(N, H, D):
     """The hand-written TMA + FP64 tensor-core GEMMs (csrc/bsc_gemm.cuh: a = Y W with ||y||^2 for the E-step,
     WpT += E^T Y for the M-step) against the library GEMM path (tvo_bsc_estep_variant bit 16) on the same inputs,
     including partial 64-row tiles and partial 16-datapoint chunks: identical K, lpj / statistics to 1e-12."""
     rng = np.random.default_rng(N)
-    H, D, S = 256, 144, 16
+    S = 16  # H > 256: a = Y W in column panels of 256 (the M-step GEMM of those shapes is the library's either way)
     W, pies, Y, K = make(rng, N, H, D, S, 4.0 / H, 4.0 / H)
     tvo_b200._set_device(to.device(DEV))
     out = {}

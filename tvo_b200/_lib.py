@@ -58,6 +58,8 @@ _PROTOS = {
     "tvo_bsc_mstep_scratch_bytes": [_I64, _I32, _I32, _I32],
     "tvo_bsc_estep_variant": [_I32],
     "tvo_bsc_symmetrize": [_P, _P, _I32, _P],
+    "tvo_bsc_epoch_solve_work_doubles": [_I32],
+    "tvo_bsc_epoch_solve": [_P, _P, _P, _P, _I32, _I32, _P],
     "tvo_random_states": [_P, _P, _I64, _I32, _I32, _F64, _U64, _U32, _U32, _P],
     "tvo_noisyor_theta_ws_bytes": [_I32, _I32, _I32],
     "tvo_noisyor_stats_len": [_I32, _I32],
@@ -71,7 +73,7 @@ _PROTOS = {
 for _sfx in ("f64", "f32"):
     _PROTOS.update({
         f"tvo_bsc_prepare_{_sfx}": [_P, _P, _I32, _P, _I32, _I32, _P, _P],
-        f"tvo_bsc_epoch_finish_{_sfx}": [_P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _P],
+        f"tvo_bsc_epoch_finish_{_sfx}": [_P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P],
         f"tvo_bsc_lpj_{_sfx}": [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P],
         f"tvo_evo_generation_{_sfx}": [_P, _I64, _P, _I64, _P, _I32, _I32, _P, C.POINTER(EvoConfig), _I32, _P, _P,
                                        _I64, _I32, _P],
@@ -120,6 +122,7 @@ _RESTYPES = {
     "tvo_sssc_theta_ws_bytes": _I64,
     "tvo_sssc_stats_len": _I64,
     "tvo_sssc_scratch_bytes": _I64,
+    "tvo_bsc_epoch_solve_work_doubles": _I64,
     "tvo_mixture_ws_bytes": _I64,
     "tvo_mixture_stats_len": _I64,
     "tvo_mixture_scratch_bytes": _I64,

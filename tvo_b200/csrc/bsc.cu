@@ -3,6 +3,7 @@
 // bsc_fast.cu.
 #include "bsc_device.cuh"
 #include "bsc_gemm_tf32.cuh"
+#include "bsc_chol.cuh"
 
 namespace tvo {
 
@@ -297,7 +298,10 @@ static __global__ void bsc_symmetrize_kernel(const double *__restrict__ U, doubl
 template <typename T>
 __global__ void bsc_epoch_finish_kernel(const double *__restrict__ stats, const double *__restrict__ sol,
                                         const T *__restrict__ W_noisy, T *__restrict__ W, T *__restrict__ pies, int n_pies,
-                                        T *__restrict__ sigma2, int H, int D) {
+                                        T *__restrict__ sigma2, int H, int D, const double *__restrict__ guard) {
+  // guard = the flags of tvo_bsc_epoch_solve: an unusable factorisation leaves theta untouched (the host, which
+  // reads the same flags, then takes the reference's lstsq route and calls this kernel again without a guard)
+  if (guard && !(guard[0] == 0.0 && guard[1] > 1.0e-6)) return;
   const double *my_pies = stats + (size_t)H * D + (size_t)H * H;
   const double N = my_pies[H + 1];
   const T lo = (T)1.0e-5, hi = (T)(1.0 - 1.0e-5);
@@ -330,11 +334,11 @@ __global__ void bsc_epoch_finish_kernel(const double *__restrict__ stats, const 
 
 template <typename T>
 int bsc_epoch_finish(const double *stats, const double *sol, const T *W_noisy, T *W, T *pies, int n_pies, T *sigma2, int H,
-                     int D, void *stream) {
+                     int D, const double *guard, void *stream) {
   TVO_REQUIRE(stats && W_noisy && W && pies && sigma2, "bsc_epoch_finish: null pointer");
   TVO_REQUIRE(H > 0 && D > 0 && (n_pies == 1 || n_pies == H), "bsc_epoch_finish: bad sizes");
   bsc_epoch_finish_kernel<T><<<min((H * D + 255) / 256, 4 * sm_count()), 256, 0, (cudaStream_t)stream>>>(
-      stats, sol, W_noisy, W, pies, n_pies, sigma2, H, D);
+      stats, sol, W_noisy, W, pies, n_pies, sigma2, H, D, guard);
   TVO_AFTER_LAUNCH("bsc_epoch_finish");
   return TVO_OK;
 }
@@ -358,12 +362,26 @@ int tvo_bsc_symmetrize(const double *upper, double *full, int32_t H, void *strea
   return TVO_OK;
 }
 int tvo_bsc_epoch_finish_f64(const double *stats, const double *sol, const double *W_noisy, double *W, double *pies,
-                             int32_t n_pies, double *sigma2, int32_t H, int32_t D, void *stream) {
-  return bsc_epoch_finish<double>(stats, sol, W_noisy, W, pies, n_pies, sigma2, H, D, stream);
+                             int32_t n_pies, double *sigma2, int32_t H, int32_t D, const double *guard, void *stream) {
+  return bsc_epoch_finish<double>(stats, sol, W_noisy, W, pies, n_pies, sigma2, H, D, guard, stream);
 }
 int tvo_bsc_epoch_finish_f32(const double *stats, const double *sol, const float *W_noisy, float *W, float *pies,
-                             int32_t n_pies, float *sigma2, int32_t H, int32_t D, void *stream) {
-  return bsc_epoch_finish<float>(stats, sol, W_noisy, W, pies, n_pies, sigma2, H, D, stream);
+                             int32_t n_pies, float *sigma2, int32_t H, int32_t D, const double *guard, void *stream) {
+  return bsc_epoch_finish<float>(stats, sol, W_noisy, W, pies, n_pies, sigma2, H, D, guard, stream);
+}
+int64_t tvo_bsc_epoch_solve_work_doubles(int32_t H) { return chol_supported(H) ? (int64_t)chol_work_doubles(H) : 0; }
+int tvo_bsc_epoch_solve(const double *stats, double *work, double *sol, double *flags, int32_t H, int32_t D, void *stream) {
+  TVO_REQUIRE(stats && work && sol && flags, "bsc_epoch_solve: null pointer");
+  TVO_REQUIRE(chol_supported(H) && D > 0, "bsc_epoch_solve: H = %d is outside 1..256 (use the library solve)", H);
+  const size_t smem = chol_factor_smem(H);
+  TVO_CUDA(cudaFuncSetAttribute(bsc_chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bsc_chol_factor_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(stats + (size_t)H * D, H, work, flags);
+  TVO_AFTER_LAUNCH("bsc_chol_factor");
+  const size_t smem_s = chol_solve_smem(H);
+  TVO_CUDA(cudaFuncSetAttribute(bsc_chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+  bsc_chol_solve_kernel<<<D, 256, smem_s, (cudaStream_t)stream>>>(work, stats, sol, flags, H, D);
+  TVO_AFTER_LAUNCH("bsc_chol_solve");
+  return TVO_OK;
 }
 int64_t tvo_bsc_theta_ws_bytes(int32_t H, int32_t D, int32_t is_f64) {
   return (int64_t)(is_f64 ? bsc_ws_bytes<double>(H, D) : bsc_ws_bytes<float>(H, D));

@@ -49,8 +49,10 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 }
 
 // ------------------------------------------------------------------------------------ A = Y W, yy = ||y||^2
-// CTA tile: 64 datapoints x all H columns, K in chunks of 16.  8 MMA warps as 2 (M) x 4 (N): warp tile 32 x H/4
-// (NB = H/32 n-blocks of 8 columns); warp 8 is the TMA producer.  Persistent over the 64-row tiles.
+// CTA tile: 64 datapoints x one PANEL of 32 NB <= 256 columns (all H columns for H <= 256; H = 512 / 768 / 1024 —
+// BASELINE configs[4] — as 2 / 3 / 4 panels of 256), K in chunks of 16.  8 MMA warps as 2 (M) x 4 (N): warp tile
+// 32 x 8 NB; warp 8 is the TMA producer.  Persistent over the (row tile, panel) work items, the panels of a row tile
+// adjacent in the order so that the tile of Y is re-read from L2.
 constexpr int kGyBM = 64, kGyKC = 16, kGyStages = 4;
 constexpr int kGyARow = kGyKC + 4;  // doubles per shared-memory row of the Y chunk: 160 B = 8 words mod 32
 
@@ -62,15 +64,16 @@ __host__ __device__ inline size_t gemm_yw_smem_bytes(int H) { return kGyStages *
 template <int NB>  // n-blocks per warp: H = 32 NB
 __global__ void __launch_bounds__(288, 1)
 bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__restrict__ Wg, double *__restrict__ A,
-                   double *__restrict__ yy_out, int B, int D) {
-  constexpr int H = 32 * NB;
+                   double *__restrict__ yy_out, int B, int D, int Hfull) {
+  constexpr int H = 32 * NB;  // columns of a panel
+  const int npanel = Hfull / H;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t stage_bytes = gemm_yw_stage_bytes(H);
   uint64_t *full = (uint64_t *)(smem_raw + kGyStages * stage_bytes);
   uint64_t *empty = full + kGyStages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = bsc_kpad16(D) / kGyKC;
-  const int ntile = (B + kGyBM - 1) / kGyBM;
+  const int ntile = ((B + kGyBM - 1) / kGyBM) * npanel;  // work items
   if (threadIdx.x == 0) {
     for (int s = 0; s < kGyStages; ++s) {
       mbar_init(full + s, 1);
@@ -80,11 +83,12 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
   }
   __syncthreads();
   if (warp == 8) {
-    // ---- producer: per stage 64 row segments of Y (128 B each) + one contiguous K-chunk of Wg ----
+    // ---- producer: per stage 64 row segments of Y (128 B each) + the K-chunk of the panel's columns of Wg (one
+    //      contiguous copy when the panel is all of H, else one per k/4 slice) ----
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
-      const int r0 = t * kGyBM, rows = min(kGyBM, B - r0);
+      const int r0 = (t / npanel) * kGyBM, rows = min(kGyBM, B - r0), n0 = (t % npanel) * H;
       for (int c = 0; c < nchunk; ++c) {
         mbar_wait(empty + stage, phase ^ 1u);
         double *As = (double *)(smem_raw + stage * stage_bytes);
@@ -93,7 +97,12 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
         __syncwarp();
         for (int r = lane; r < rows; r += 32)
           tma_bulk_g2s(As + r * kGyARow, Y + (int64_t)(r0 + r) * ldY + c * kGyKC, kGyKC * 8, full + stage);
-        if (lane == 0) tma_bulk_g2s(Bs, Wg + (size_t)c * kGyKC * H, kGyKC * H * 8, full + stage);
+        if (npanel == 1) {
+          if (lane == 0) tma_bulk_g2s(Bs, Wg + (size_t)c * kGyKC * H, kGyKC * H * 8, full + stage);
+        } else if (lane < kGyKC / 4) {
+          tma_bulk_g2s(Bs + (size_t)lane * H * 4, Wg + ((size_t)(c * (kGyKC / 4) + lane) * Hfull + n0) * 4, H * 4 * 8,
+                       full + stage);
+        }
         if (++stage == kGyStages) {
           stage = 0;
           phase ^= 1u;
@@ -108,7 +117,7 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
   int stage = 0;
   uint32_t phase = 0;
   for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
-    const int r0 = t * kGyBM;
+    const int r0 = (t / npanel) * kGyBM, n0 = (t % npanel) * H;
     double acc[4][NB][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -149,10 +158,11 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
       if (row < B) {
 #pragma unroll
         for (int j = 0; j < NB; ++j)
-          *reinterpret_cast<double2 *>(A + (size_t)row * H + wn * (8 * NB) + j * 8 + 2 * q) = make_double2(acc[i][j][0], acc[i][j][1]);
+          *reinterpret_cast<double2 *>(A + (size_t)row * Hfull + n0 + wn * (8 * NB) + j * 8 + 2 * q) =
+              make_double2(acc[i][j][0], acc[i][j][1]);
       }
     }
-    if (wn == 0 && yy_out) {
+    if (wn == 0 && yy_out && n0 == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         double v = ysq[i];
@@ -167,20 +177,21 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
 
 // host: true if the shape is covered (else the caller uses the library GEMM)
 __host__ inline bool gemm_yw_supported(int H, int D, int64_t ldY, const void *Y) {
-  return (H == 64 || H == 128 || H == 256) && (D % kGyKC) == 0 && (ldY % 2) == 0 && ((uintptr_t)Y % 16) == 0 &&
-         gemm_yw_smem_bytes(H) <= (size_t)227 * 1024;
+  return (H == 64 || H == 128 || (H % 256 == 0 && H <= 4096)) && (D % kGyKC) == 0 && (ldY % 2) == 0 && ((uintptr_t)Y % 16) == 0 &&
+         gemm_yw_smem_bytes(H > 256 ? 256 : H) <= (size_t)227 * 1024;
 }
 
 __host__ inline cudaError_t launch_gemm_yw(const double *Y, int64_t ldY, const double *Wg, double *A, double *yy, int B, int H,
                                            int D, int sms, cudaStream_t st) {
-  const size_t smem = gemm_yw_smem_bytes(H);
-  const int grid = min(sms, (B + kGyBM - 1) / kGyBM);
+  const int Hp = H > 256 ? 256 : H;  // panel width
+  const size_t smem = gemm_yw_smem_bytes(Hp);
+  const int grid = min(sms, ((B + kGyBM - 1) / kGyBM) * (H / Hp));
   cudaError_t e;
 #define TVO_GYW(NBV)                                                                                          \
   e = cudaFuncSetAttribute(bsc_gemm_yw_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return e;                                                                            \
-  bsc_gemm_yw_kernel<NBV><<<grid, 288, smem, st>>>(Y, ldY, Wg, A, yy, B, D);
-  if (H == 256) {
+  bsc_gemm_yw_kernel<NBV><<<grid, 288, smem, st>>>(Y, ldY, Wg, A, yy, B, D, H);
+  if (Hp == 256) {
     TVO_GYW(8)
   } else if (H == 128) {
     TVO_GYW(4)

@@ -78,6 +78,8 @@ class BSC(Optimized, Sampler, Reconstructor):
         self._ws = None
         self._fresh = None  # (theta versions, batch ptr/version): lpj in `states` was computed from these
         self._ws_token = None  # (theta versions, stream) the workspace was digested from
+        self._chol_work = None  # factor / flags of the hand-written epoch solve (H <= 256)
+        self._chol_sol = None
         self._last_F = None
         self.use_gram = True  # Gram-form fused E-step (False: direct column-walk form, D <= 256)
         self.scratch_datapoints = 524288  # chunk size of the Gram E-step / M-step GEMMs (scratch ~ chunk*(H*8+12) B = 1.1 GB at
@@ -148,7 +150,7 @@ class BSC(Optimized, Sampler, Reconstructor):
             self._ws_token = None
         # theta unchanged since the last digestion on this stream (in-place torch writes bump the tensors' versions,
         # update_param_epoch drops the token): the E-step and the M-step of one batch share one digestion
-        token = (self._theta_token(), _lib.stream())
+        token = (self._theta_token(), _lib.stream().value)  # c_void_p objects compare by identity
         if self._ws_token == token:
             return self._ws
         self._ws_token = token
@@ -266,16 +268,18 @@ class BSC(Optimized, Sampler, Reconstructor):
     def update_param_epoch(self) -> None:
         """bsc.py:160-204.  One all-reduce of the packed statistics, then on every rank: the solve of
         my_Wq W^T = my_Wp^T and ONE kernel (tvo_bsc_epoch_finish) that turns the solution and the statistics into the
-        new theta in place, fix_theta included.  With more than one rank a packed broadcast of theta from rank 0
-        follows (cuSOLVER / LAPACK are not guaranteed bit-reproducible across processes; the reference broadcasts
-        W, pies, sigma2 separately, sanity.py:40).
+        new theta in place, fix_theta included.
 
         W_solver "gpu" (default): my_Wq is symmetric positive semi-definite, so the system is solved by a Cholesky
-        factorisation (potrf + potrs: 0.3 ms at H = 256 against 1.0 ms for the QR behind torch.linalg.lstsq, which
-        is what the reference calls under TVO_GPU); if the factorisation fails or its pivots signal a condition
-        number beyond ~1e12 (a unit that was never active), torch.linalg.lstsq takes over, and if that raises the
-        reference's fallback applies (W <- W + 0.1 randn, bsc.py:174,180-181).  "gpu_lstsq": always lstsq on the
-        device; "cpu": the host's rank-revealing gelsy (the reference's CPU path)."""
+        factorisation — for H <= 256 by the hand-written kernels of csrc/bsc_chol.cuh (tvo_bsc_epoch_solve: 2 launches,
+        deterministic, so every rank derives bit-identical theta from the all-reduced statistics and NO broadcast
+        follows), for larger H by potrf + potrs through torch; torch.linalg.lstsq (the QR the reference calls under
+        TVO_GPU) takes over if the factorisation fails, its pivots signal a condition number beyond ~1e12 (a unit
+        that was never active) or the solution is not finite, and if that raises the reference's fallback applies
+        (W <- W + 0.1 randn, bsc.py:174,180-181).  "gpu_lstsq": always lstsq on the device; "cpu": the host's
+        rank-revealing gelsy (the reference's CPU path).  After any library solve a packed broadcast of theta from
+        rank 0 follows when there is more than one rank (cuSOLVER / LAPACK are not guaranteed bit-reproducible across
+        processes; the reference broadcasts W, pies, sigma2 separately, sanity.py:40)."""
         theta = self.theta
         D, H = self.shape
         all_reduce(self._stats)
@@ -290,32 +294,57 @@ class BSC(Optimized, Sampler, Reconstructor):
                                              theta[k].device == self._stats.device for k in theta)
         sol = None
         if self.W_solver == "gpu" and direct:
-            if self._wq_full is None or self._wq_full.device != self._stats.device:
-                self._wq_full = to.empty((H, H), dtype=to.float64, device=self._stats.device)
-            _lib.call("tvo_bsc_symmetrize", _lib.ptr(self._stats[H * D: H * D + H * H]), _lib.ptr(self._wq_full), H,
-                      _lib.stream())
-            L, info = to.linalg.cholesky_ex(self._wq_full)
-            dg = to.diagonal(L)
-            flags_dev = to.stack([info.to(to.float64), dg.min() / dg.max()])
-            # one host read per EM iteration, taken on a side stream while the triangular solves already run on the
-            # launching stream (the solution is dropped if the factorisation turns out unusable)
             dev = self._stats.device
             if dev not in _SIDE:
                 _SIDE[dev] = (to.cuda.Stream(device=dev), to.empty(2, dtype=to.float64).pin_memory())
             side, flags_host = _SIDE[dev]
-            factored = to.cuda.Event()
-            factored.record()
-            sol = to.cholesky_solve(WpT, L)
-            with to.cuda.stream(side):
-                side.wait_event(factored)
+            nwork = _lib.lib().tvo_bsc_epoch_solve_work_doubles(H)
+            if nwork > 0:
+                # H <= 256: blocked Cholesky + substitution kernels straight from the packed statistics (csrc/bsc_chol.cuh),
+                # then the finishing kernel GUARDED by the factorisation flags on the device: the whole update is queued
+                # before the host reads the flags (one small device-to-host copy per EM iteration, nothing behind it)
+                if self._chol_work is None or self._chol_work.numel() != nwork + 2 or self._chol_work.device != dev:
+                    self._chol_work = to.empty(nwork + 2, dtype=to.float64, device=dev)
+                    self._chol_sol = to.empty((H, D), dtype=to.float64, device=dev)
+                flags_dev = self._chol_work[nwork:]
+                sol = self._chol_sol
+                _lib.call("tvo_bsc_epoch_solve", _lib.ptr(self._stats), _lib.ptr(self._chol_work), _lib.ptr(sol),
+                          _lib.ptr(flags_dev), H, D, _lib.stream())
+                _lib.call(f"tvo_bsc_epoch_finish_{_lib.sfx(prec)}", _lib.ptr(self._stats), _lib.ptr(sol),
+                          _lib.ptr(Wold_noisy.contiguous()), _lib.ptr(theta["W"]), _lib.ptr(theta["pies"]),
+                          theta["pies"].numel(), _lib.ptr(theta["sigma2"]), H, D, _lib.ptr(flags_dev), _lib.stream())
                 flags_host.copy_(flags_dev, non_blocking=True)
-                side.synchronize()
-            flags = flags_host.tolist()
-            if not (flags[0] == 0 and flags[1] > 1e-6):  # cond(my_Wq) ~ (max/min pivot)^2 < 1e12
-                sol = None
+                to.cuda.current_stream().synchronize()
+                flags = flags_host.tolist()
+                if flags[0] == 0 and flags[1] > 1e-6:  # cond(my_Wq) ~ (max/min pivot)^2 < 1e12
+                    # deterministic solve on bit-identical all-reduced statistics: theta agrees on every rank without
+                    # a broadcast ("theta update then runs identically on every rank")
+                    self._stats.zero_()
+                    return
+                sol = None  # theta untouched: the reference's lstsq route below
+            else:
+                if self._wq_full is None or self._wq_full.device != dev:
+                    self._wq_full = to.empty((H, H), dtype=to.float64, device=dev)
+                _lib.call("tvo_bsc_symmetrize", _lib.ptr(self._stats[H * D: H * D + H * H]), _lib.ptr(self._wq_full), H,
+                          _lib.stream())
+                L, info = to.linalg.cholesky_ex(self._wq_full)
+                dg = to.diagonal(L)
+                flags_dev = to.stack([info.to(to.float64), dg.min() / dg.max()])
+                # one host read per EM iteration, taken on a side stream while the triangular solves already run on
+                # the launching stream (the solution is dropped if the factorisation turns out unusable)
+                factored = to.cuda.Event()
+                factored.record()
+                sol = to.cholesky_solve(WpT, L)
+                with to.cuda.stream(side):
+                    side.wait_event(factored)
+                    flags_host.copy_(flags_dev, non_blocking=True)
+                    side.synchronize()
+                flags = flags_host.tolist()
+                if not (flags[0] == 0 and flags[1] > 1e-6):
+                    sol = None
         if sol is None:
             try:
-                Wq = self._wq_full if (self.W_solver == "gpu" and direct) else self.my_Wq
+                Wq = self.my_Wq
                 sol = (to.linalg.lstsq(Wq.cpu(), WpT.cpu())[0].to(WpT.device) if self.W_solver == "cpu"
                        else to.linalg.lstsq(Wq, WpT)[0])
             except RuntimeError:
@@ -326,7 +355,7 @@ class BSC(Optimized, Sampler, Reconstructor):
             sol = None if sol is None else sol.contiguous()
             _lib.call(f"tvo_bsc_epoch_finish_{_lib.sfx(prec)}", _lib.ptr(self._stats), _lib.ptr(sol),
                       _lib.ptr(Wold_noisy.contiguous()), _lib.ptr(theta["W"]), _lib.ptr(theta["pies"]),
-                      theta["pies"].numel(), _lib.ptr(theta["sigma2"]), H, D, _lib.stream())
+                      theta["pies"].numel(), _lib.ptr(theta["sigma2"]), H, D, None, _lib.stream())
         else:  # user-rebound theta tensors (other dtype / device / strides): the reference's torch expressions
             N = self.my_N
             policy = self.policy
@@ -338,6 +367,7 @@ class BSC(Optimized, Sampler, Reconstructor):
             fix_theta(theta_new, policy)
             for key in theta:
                 theta[key][:] = theta_new[key].to(device=theta[key].device, dtype=theta[key].dtype)
+        # library solvers (cuSOLVER / LAPACK) are not guaranteed bit-reproducible across processes: broadcast after those
         if tvo_b200.get_run_policy() == "mpi" and to.distributed.is_initialized() and to.distributed.get_world_size() > 1:
             flat = to.cat([theta[k].reshape(-1) for k in theta])
             broadcast(flat)
