@@ -43,6 +43,12 @@ if rank == 0:
     m_s, st_s, out_s = run(0, N, "seq")
 global_settings._set_run_policy("mpi")
 Ks = parallel.gather_from_processes(st_d._Kp)
+# theta must be BIT-identical on every rank WITHOUT a broadcast (deterministic hand-written solve on the all-reduced
+# statistics, csrc/bsc_chol.cuh): gather every rank's theta and compare
+flat = to.cat([m_d.theta[k].reshape(-1) for k in sorted(m_d.theta)]).contiguous()
+allflat = [to.empty_like(flat) for _ in range(world)]
+dist.all_gather(allflat, flat)
+assert all(to.equal(allflat[0], f) for f in allflat), "theta differs between the ranks"
 if rank == 0:
     assert to.equal(Ks, st_s._Kp), "sharded K differs from single-GPU K"
     for a, b in zip(out_d, out_s):

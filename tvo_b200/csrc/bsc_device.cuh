@@ -9,7 +9,8 @@ struct BscThetaHdr {
   double prior_sum;       // sum_h log(1-pi_h)     (bsc.py:127-131)
   double log_2pi_sigma2;  // log(2 pi sigma2)      (bsc.py:132)
   double sigma2;
-  double pad[4];
+  double sparsity;        // mean_h pi_h in the model's precision: `sparsity` of the sparseflip mutation (evo.py:109)
+  double pad[3];
 };
 
 __host__ __device__ inline int bsc_dpad(int D) { return D <= 256 ? pad32(D) : ((D + 255) & ~255); }
@@ -123,14 +124,20 @@ __global__ void bsc_prepare_kernel(const T *__restrict__ W, const T *__restrict_
     }
   }
   if (blockIdx.x == 0 && threadIdx.x < 32) {
-    double s = 0.0;
+    double s = 0.0, pm = 0.0;
     if (n_pies == 1) {
       s = (double)H * (double)log(T(1) - pies[0]);
+      pm = (double)pies[0];
     } else {
-      for (int h = threadIdx.x; h < H; h += 32) s += (double)log(T(1) - pies[h]);
+      for (int h = threadIdx.x; h < H; h += 32) {
+        s += (double)log(T(1) - pies[h]);
+        pm += (double)pies[h];
+      }
       s = warp_sum(s);
+      pm = (double)(T)(warp_sum(pm) / (double)H);
     }
     if (threadIdx.x == 0) {
+      hdr->sparsity = pm;
       const T s2 = sigma2[0];
       hdr->coef = (double)(T(-0.5) / s2);
       hdr->prior_sum = s;

@@ -164,7 +164,9 @@ class BSC(Optimized, Sampler, Reconstructor):
 
     # --- hooks used by the tvo_b200 variational states -------------------------------------------
     def _tvo_sparsity(self) -> Tensor:
-        return self._theta["pies"].mean().to(to.float64).reshape(1)
+        """mean(pies) (evo.py:109) as a device double: computed by the theta digestion (BscThetaHdr::sparsity, byte 32
+        of the workspace) — no extra reduction kernel per E-step."""
+        return self._prepare()[32:40].view(to.float64)
 
     def _tvo_lpj_packed(self, batch: Tensor, packed: Tensor, H: int, k_broadcast: bool = False, ws=None) -> Tensor:
         """lpj (B,S) for packed states (B or 1, S, W64)."""
@@ -314,8 +316,10 @@ class BSC(Optimized, Sampler, Reconstructor):
                           _lib.ptr(Wold_noisy.contiguous()), _lib.ptr(theta["W"]), _lib.ptr(theta["pies"]),
                           theta["pies"].numel(), _lib.ptr(theta["sigma2"]), H, D, _lib.ptr(flags_dev), _lib.stream())
                 flags_host.copy_(flags_dev, non_blocking=True)
+                self._prepare()  # digest the new theta now (G = W^T W, Wg, priors): runs while the host waits for the flags
                 to.cuda.current_stream().synchronize()
                 flags = flags_host.tolist()
+                self._ws_token = self._ws_token if flags[0] == 0 and flags[1] > 1e-6 else None
                 if flags[0] == 0 and flags[1] > 1e-6:  # cond(my_Wq) ~ (max/min pivot)^2 < 1e12
                     # deterministic solve on bit-identical all-reduced statistics: theta agrees on every rank without
                     # a broadcast ("theta update then runs identically on every rank")
