@@ -558,8 +558,11 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": N_total / (e2e_ms * 1e-3), "unit": "datapoints/s", "h2d_bytes_per_step": N * D * 8,
                     "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms,
+                    "h2d_gbs_per_gpu": N * D * 8 / (e2e_ms * 1e-3) / 1e9,
                     "what": "E-step via EVOVariationalStates.update_device on chunks copied from pinned host memory "
-                            "(double-buffered copy stream), substitution count read back each step; bytes are per rank"},
+                            "(double-buffered copy stream), substitution count read back each step; bytes are per rank; "
+                            "the leg is bound by the PCIe copy of Y (h2d_gbs_per_gpu), the E-step of all chunks but the "
+                            "last is hidden behind it"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "estep_evo_bsc_v2_kernel<double,2,1,2>" if HEADLINE else "estep_evo_bsc_v2_kernel<double,4,4,4,unsigned short>",
