@@ -540,6 +540,85 @@ def test_estep_baseline_shape_properties():
     assert int(m.my_N.item()) == N
 
 
+@pytest.mark.parametrize("H,D,S,P,Cn,G,gen_units,boundary", [
+    (256, 144, 64, 16, 2, 2, 5.0, 524288),     # BASELINE configs[1] at the north-star N
+    (1024, 256, 128, 16, 4, 2, 8.0, 262144),   # BASELINE configs[4]: one GPU holding all of N = 1M
+], ids=["configs1", "configs4"])
+def test_estep_full_size_properties_and_oracle_subset(H, D, S, P, Cn, G, gen_units, boundary):
+    """BASELINE configs[1] / configs[4] at their FULL size (BSC, randparents + sparseflip, fp64, N = 1M: several scratch
+    chunks per launch, every CTA in its steady state): size-independent properties over all datapoints, a bit-exact
+    oracle comparison on 8 of them inside the full launch, independence of the result from how the datapoints are
+    batched, and the M-step / free-energy sums against a two-halves evaluation."""
+    if to.cuda.get_device_properties(0).total_memory < 100 * 2 ** 30:
+        pytest.skip("needs ~60 GB of device memory")
+    N = 1_000_000
+    tvo_b200._set_device(to.device(DEV))
+    g = to.Generator(device=DEV).manual_seed(3)
+    Wgen = to.randn(D, H, dtype=to.float64, device=DEV, generator=g)
+    W0 = Wgen + 0.5 * to.randn(D, H, dtype=to.float64, device=DEV, generator=g)
+    Y = to.empty(N, D, dtype=to.float64, device=DEV)
+    for a in range(0, N, 125_000):  # generated in slices: the (N, H) activity matrix never exists
+        Y[a:a + 125_000] = (to.rand(125_000, H, device=DEV, generator=g) < gen_units / H).double() @ Wgen.t()
+    Y += to.randn(N, D, dtype=to.float64, device=DEV, generator=g)
+    pies = np.full(H, 1.0 / H)
+    np.random.seed(0)
+    m = BSC(H, D, W0, to.tensor([1.0], dtype=to.float64), dev(pies), precision=to.float64)
+    st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", P, G, Cn, bitflip_frequency=1.0 / H, seed=21)
+    np.random.seed(0)
+    st2 = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", P, G, Cn, bitflip_frequency=1.0 / H, seed=21)
+    assert to.equal(st._Kp, st2._Kp)
+    idx = to.arange(N, device=DEV)
+    sub = np.array([0, 1, boundary - 1, boundary, 700001, 999_998, 999_999, 123_456])  # both sides of a chunk boundary
+    o = om.BSC(H, D, W0.cpu().numpy(), [1.0], pies)
+    from tvo_b200.variational._packed import unpack
+    Kw = unpack(st._Kp[dev(sub)], H).cpu().numpy()
+    Ysub = Y[dev(sub)].cpu().numpy()
+    prev_best = None
+    for it in range(2):
+        Kw, Lw, _ = oracle_estep(o, Ysub, Kw, np.float64, "randparents", "sparseflip", P, Cn, G, 1.0 / H, sub, 21, it,
+                                 sparsity=float(m._tvo_sparsity().item()))
+        nsubs = st.update(idx, Y, m)
+        assert 0 < nsubs <= N * S
+        lpj = st.lpj
+        assert bool((lpj[:, 1:] >= lpj[:, :-1]).all())                       # ascending, best last
+        if prev_best is not None:
+            assert bool((lpj[:, -1] >= prev_best - 1e-9).all())              # best never gets worse
+        prev_best = lpj[:, -1].clone()
+        assert to.allclose(m._tvo_lpj_packed(Y, st._Kp, H), lpj, rtol=1e-12, atol=1e-9)  # stored lpj == lpj of stored K
+        # no duplicate states inside any K_n (exact): the S states of every datapoint sorted lexicographically by their
+        # words (stable sorts, least significant word first), equal neighbours would be duplicates; over a quarter of
+        # the datapoints, spread over the whole range
+        Kp = st._Kp[it::4]
+        order = to.arange(S, device=DEV).expand(Kp.shape[0], S).contiguous()
+        for w in range(Kp.shape[2] - 1, -1, -1):
+            order = order.gather(1, Kp[..., w].gather(1, order).sort(dim=1, stable=True).indices)
+        srt = Kp.gather(1, order[..., None].expand(-1, -1, Kp.shape[2]))
+        assert not bool((srt[:, 1:] == srt[:, :-1]).all(dim=2).any())
+        del srt, order
+        got = unpack(st._Kp[dev(sub)], H).cpu().numpy()
+        assert np.array_equal(got, Kw), f"K differs from the oracle at step {it}"
+        assert np.allclose(lpj[dev(sub)].cpu().numpy(), Lw, rtol=RT64, atol=RT64)
+        # the same E-step fed in three uneven batches in another order: identical K, lpj and substitutions
+        cuts = [(600_000, N), (0, 250_001), (250_001, 600_000)]
+        nsubs2 = 0
+        for a, b in cuts:
+            st2._step = it  # the E-step counter of the candidate stream counts E-steps, not calls
+            nsubs2 += st2.update(idx[a:b], Y[a:b], m)
+        assert nsubs2 == nsubs
+        assert to.equal(st2._Kp, st._Kp) and to.equal(st2.lpj, st.lpj)
+    # M-step statistics and free energy: one call over 1M datapoints == two halves (accumulator linearity)
+    m._stats.zero_()
+    m.update_param_batch(idx, Y, st)
+    a = m._stats.clone()
+    m._stats.zero_()
+    m.update_param_batch(idx[: N // 2], Y[: N // 2], st)
+    m.update_param_batch(idx[N // 2:], Y[N // 2:], st)
+    assert to.allclose(a, m._stats, rtol=1e-11, atol=1e-9)
+    assert int(m.my_N.item()) == N
+    F = float(m._stats[-1].item())
+    assert abs(F - m.free_energy(idx, Y, st)) <= 1e-10 * abs(F)
+
+
 # ----------------------------------------------------------------------------- trainer / generic models
 def test_estep_c5_shape_properties_and_oracle_subset():
     """BASELINE configs[4] shape (BSC H=1024 D=256 S=128, P=16 C=4 G=2 => S'=128, fp64): the size-independent

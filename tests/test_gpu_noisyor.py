@@ -248,16 +248,18 @@ def test_noisyor_estep_c4_shape_properties():
     assert to.allclose(st.lpj[:5000][ok].double(), ref[ok], rtol=1e-4, atol=1e-4 * float(ref[ok].abs().max()))
 
 
-def test_noisyor_c4_shape_estep_batch_fitparents_oracle_subset():
+@pytest.mark.parametrize("N", [20_000, 500_000], ids=["20k", "configs3_full_size"])
+def test_noisyor_c4_shape_estep_batch_fitparents_oracle_subset(N):
     """BASELINE configs[3] shape (NoisyOR D=100 H=64 S=64, fp32, crossover + randflip, P=8, G=1) with the REFERENCE's
-    parent selection `batch_fitparents` (batch-global normaliser, evo.py:404-406) inside a 20k-datapoint launch,
+    parent selection `batch_fitparents` (batch-global normaliser, evo.py:404-406) inside a 20k-datapoint launch and at
+    its full size N = 500k,
     against the oracle on 12 of the datapoints.  The normaliser (m, T) is a function of the whole batch's lpj, so the
     oracle takes it from the batch lpj (fit_norm of the same fp32 values); parents and children are then bit-identical
     by construction of the stream, and the merged K sets must be equal (fp32 rounding may reorder a near-tie: one
     datapoint of slack), lpj within 1e-4."""
     tvo_b200._set_device(to.device(DEV))
     rng = np.random.default_rng(17)
-    N, H, D, S, P = 20_000, 64, 100, 64, 8
+    H, D, S, P = 64, 100, 64, 8
     W = (rng.random((D, H)) * 0.9 + 0.05).astype(np.float32)
     pies = np.full(H, 2.0 / H, np.float32)
     Y = (rng.random((N, D)) < 0.2).astype(np.uint8)
@@ -268,7 +270,7 @@ def test_noisyor_c4_shape_estep_batch_fitparents_oracle_subset():
     st.n_offset = 300
     idx = to.arange(N, device=DEV)
     Yd = dev(Y)
-    sub = np.array([0, 1, 2, 3, 500, 4097, 9999, 10000, 12345, 19997, 19998, 19999])
+    sub = np.array([0, 1, 2, 3, 500, 4097, 9999, 10000, 12345, N - 3, N - 2, N - 1])
     for step in range(2):
         K_before = st.K.unpack()[dev(sub)].cpu().numpy()
         lpj_batch = m.log_pseudo_joint(Yd, st.K).cpu().numpy()           # what the E-step re-scores (evo.py:95)

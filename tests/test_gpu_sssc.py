@@ -16,6 +16,8 @@ if to.cuda.is_available():
     from tvo_b200.utils.data import TVODataLoader
     from tvo_b200.variational import EVOVariationalStates, FullEM
 
+if to.cuda.is_available():
+    from tvo_b200.variational import _packed as pk
 from oracle import evo as oevo
 from oracle import models as om
 from oracle import states as ost
@@ -252,15 +254,16 @@ def test_sssc_c3_shape_properties():
     m._check_overflow()
 
 
-def test_sssc_c3_shape_oracle_subset():
+@pytest.mark.parametrize("N", [20_000, 200_000], ids=["20k", "configs2_full_size"])
+def test_sssc_c3_shape_oracle_subset(N):
     """BASELINE configs[2] shape (SSSC D=64 H=256 S=32, EVO randparents + sparseflip P=8 C=4 G=1, fp64) inside a
-    20k-datapoint launch, so that the wide-CTA tier (16 warps, 4 lanes per state) is the one running: E-step K
+    20k-datapoint launch and at its full size N = 200k, so that the wide-CTA tier (16 warps, 4 lanes per state) is the one running: E-step K
     bit-exact and lpj to 1e-10 against the oracle on 10 of the datapoints, two consecutive E-steps; M-step statistics
     of those datapoints against `om.SSSC` (same kernel tier: it is picked by the shape, not the batch size) and
     additivity of the 20k launch over (subset, complement)."""
     tvo_b200._set_device(to.device(DEV))
     rng = np.random.default_rng(31)
-    N, H, D, S, P, Cn, G = 20_000, 256, 64, 32, 8, 4, 1
+    H, D, S, P, Cn, G = 256, 64, 32, 8, 4, 1
     Wg = rng.standard_normal((D, H))
     s = rng.random((N, H)) < 4.0 / H
     Y = (s * rng.standard_normal((N, H))) @ Wg.T + (0.1 ** 0.5) * rng.standard_normal((N, D))
@@ -273,11 +276,10 @@ def test_sssc_c3_shape_oracle_subset():
     o = om.SSSC(H, D, W0, np.array([0.1]), mus, Psi, pies)
     np.random.seed(0)
     st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", P, G, Cn, bitflip_frequency=1.0 / H, seed=77)
-    K0 = st.K.unpack().cpu().numpy()
-    sub = np.array([0, 1, 2, 777, 5000, 9999, 10000, 15001, 19998, 19999])
+    sub = np.array([0, 1, 2, 777, 5000, 9999, 10000, 15001, N - 2, N - 1])
     idx = to.arange(N, device=DEV)
     Yd = dev(Y)
-    Kw = K0[sub]
+    Kw = st.K.unpack()[dev(sub)].cpu().numpy() if N <= 20_000 else pk.unpack(st._Kp[dev(sub)], H).cpu().numpy()
     sparsity = float(m._tvo_sparsity().item())
     for step in range(2):
         lpj = o.log_pseudo_joint(Y[sub], Kw)
@@ -287,7 +289,7 @@ def test_sssc_c3_shape_oracle_subset():
         ost.update_states_for_batch(new_s, new_l, np.arange(len(sub)), Kw, lpj)
         nsubs = st.update(idx, Yd, m)
         assert 0 < nsubs <= N * S
-        got = st.K.unpack()[dev(sub)].cpu().numpy()
+        got = pk.unpack(st._Kp[dev(sub)], H).cpu().numpy()
         assert np.array_equal(got, Kw), f"K differs from the oracle at step {step}"
         assert np.allclose(st.lpj[dev(sub)].cpu().numpy(), lpj, rtol=1e-10, atol=1e-10 * np.abs(lpj).max())
     # M-step: the subset against the oracle, then additivity of the full launch
