@@ -392,6 +392,8 @@ def _other_configs(to, dev, hbm_peak, peak_src, steps=3, warmup=2):
     import workloads
     out = {}
     for key, make, N in (("configs[1] C2, converged model (workload realism: denser states)", workloads.make_c2_converged, 500_000),
+                         ("configs[1] C2 in the stated fp32 mode (a = Y W on tcgen05 kind::tf32 + TMEM, 3xTF32 split)",
+                          workloads.make_c2_fp32, 500_000),
                          ("configs[2] C3", workloads.make_c3, 200_000), ("configs[3] C4", workloads.make_c4, 500_000),
                          ("configs[4] C5 (one GPU's 1/8 share would be 125k)", workloads.make_c5, 100_000)):
         try:

@@ -57,6 +57,11 @@ def make_c2_converged(dev, N, **kw):
     return make_bsc(dev, N, 256, 144, 64, 16, 2, 2, 5.0 / 256, at_generating_parameters=True, **kw)
 
 
+def make_c2_fp32(dev, N, **kw):
+    """configs[1] in the stated fp32 mode: a = Y W runs on tcgen05 (kind::tf32, 3xTF32 split, TMEM accumulators)."""
+    return make_bsc(dev, N, 256, 144, 64, 16, 2, 2, 5.0 / 256, prec=to.float32, **kw)
+
+
 def make_c5(dev, N, **kw):
     return make_bsc(dev, N, 1024, 256, 128, 16, 4, 2, 8.0 / 1024, **kw)
 
