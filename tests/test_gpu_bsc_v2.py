@@ -209,3 +209,33 @@ def test_tf32x3_tcgen05_gemm_matches_library_fp32(N, H, D):
     scale = np.abs(b[1]).max()
     assert np.allclose(np.sort(a[1][ok], 1), np.sort(b[1][ok], 1), rtol=1e-5, atol=1e-5 * scale)
     assert np.allclose(a[3], b[3], rtol=1e-4, atol=1e-4 * np.abs(b[3]).max())
+
+
+@pytest.mark.parametrize("H,D,S,P,Cn,G", [(256, 144, 64, 16, 2, 2), (600, 32, 50, 10, 2, 2), (1024, 64, 128, 16, 4, 2)])
+def test_v2_fp32_mode_matches_generic_kernel(H, D, S, P, Cn, G):
+    """fp32 mode of the list-based kernel (one- and two-byte positions) against the generic fused kernel on the same
+    inputs: the candidates are bit-identical by construction of the stream, the two kernels round lpj differently
+    (fp64 accumulation cast to fp32 vs fp32 arithmetic), so the K sets agree on all but near-ties and lpj to 1e-5."""
+    rng = np.random.default_rng(H + S)
+    N = 300
+    W, pies, Y, K = make(rng, N, H, D, S, min(0.3, 3.0 / H), min(0.3, 3.0 / H), dense_rows=(7,), nan_rows=(11,))
+    W, Y = W.astype(np.float32), Y.astype(np.float32)
+    tvo_b200._set_device(to.device(DEV))
+    out = {}
+    for variant in (0, 1):
+        _lib.call("tvo_bsc_estep_variant", variant)
+        try:
+            m = BSC(H, D, dev(W), to.tensor([1.1], dtype=to.float32), dev(pies, to.float32), precision=to.float32)
+            st = EVOVariationalStates(N, H, S, to.float32, "randparents", "sparseflip", P, G, Cn, bitflip_frequency=1.5 / H,
+                                      seed=4, K_init=dev(K))
+            nsubs = st.update(to.arange(N, device=DEV), dev(Y), m)
+            out[variant] = (st.K.unpack().cpu().numpy(), st.lpj.double().cpu().numpy(), nsubs)
+        finally:
+            _lib.call("tvo_bsc_estep_variant", 0)
+    a, b = out[0], out[1]
+    same = np.array([set(map(bytes, a[0][n])) == set(map(bytes, b[0][n])) for n in range(N)])
+    assert same.sum() >= N - 3, f"{N - same.sum()} of {N} K sets differ"
+    fin = same & ~np.isnan(b[1]).any(axis=1)
+    scale = np.abs(b[1][fin]).max()
+    assert np.allclose(np.sort(a[1][fin], 1), np.sort(b[1][fin], 1), rtol=1e-5, atol=1e-5 * scale)
+    assert bool((np.diff(a[1][fin], axis=1) >= 0).all())
