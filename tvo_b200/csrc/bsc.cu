@@ -160,8 +160,10 @@ int bsc_prepare(const T *W, const T *pies, int n_pies, const T *sigma2, int H, i
   TVO_REQUIRE(W && pies && sigma2 && ws, "bsc_prepare: null pointer");
   TVO_REQUIRE(H > 0 && D > 0, "bsc_prepare: H=%d D=%d must be positive", H, D);
   TVO_REQUIRE(n_pies == 1 || n_pies == H, "bsc_prepare: n_pies=%d must be 1 or H=%d", n_pies, H);
-  const size_t total = (size_t)H * bsc_dpad(D);
-  const int blocks = (int)min((size_t)4 * sm_count(), (total + 255) / 256);
+  // one thread per element of the largest array (H x Dpad transposes, H x H Gram matrix): every G_hh' is one serial
+  // walk over D, so the kernel's time is that walk's latency times the number of passes a thread makes
+  const size_t total = max((size_t)H * bsc_dpad(D), (size_t)H * H);
+  const int blocks = (int)min((size_t)8 * sm_count(), (total + 255) / 256);
   bsc_prepare_kernel<T><<<max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(W, pies, n_pies, sigma2, H, D, ws);
   TVO_AFTER_LAUNCH("bsc_prepare");
   if (sizeof(T) == 4) {  // fp32 model: TF32 hi / lo images of W for the tcgen05 GEMM
