@@ -180,6 +180,8 @@ int tvo_bsc_symmetrize(const double *upper, double *full, int32_t H, void *strea
  *      pivot, [1] = min/max of the factor's diagonal — the caller falls back to lstsq, as the reference does on a
  *      failed solve, when [0] != 0 or [1] is tiny.  Deterministic: identical on every rank given identical stats. */
 int64_t tvo_bsc_epoch_solve_work_doubles(int32_t H);
+/*      tvo_bsc_epoch_solve_variant(1) selects the one-CTA factorisation instead of the 8-CTA cluster (A/B tests). */
+int tvo_bsc_epoch_solve_variant(int32_t single_cta);
 int tvo_bsc_epoch_solve(const double *stats, double *work, double *sol, double *flags, int32_t H, int32_t D, void *stream);
 /*      `guard` (device, may be NULL) = the flags of tvo_bsc_epoch_solve: when they report an unusable factorisation the
  *      call writes nothing, so it can be queued before the host has read the flags. */

@@ -38,10 +38,14 @@ def run_solve(stats, H, D):
     return sol.cpu().numpy(), work[nwork:].cpu().numpy(), work[:nwork].cpu().numpy()
 
 
-@pytest.mark.parametrize("H,D", [(1, 1), (8, 16), (31, 5), (32, 144), (33, 20), (64, 40), (100, 33), (200, 150),
-                                 (255, 7), (256, 144)])
-def test_epoch_solve_matches_fp64_solve(H, D):
+@pytest.mark.parametrize("single_cta", [0, 1], ids=["cluster", "one_cta"])
+@pytest.mark.parametrize("H,D", [(1, 1), (8, 16), (31, 5), (32, 144), (33, 20), (64, 40), (65, 9), (100, 33), (128, 64),
+                                 (200, 150), (255, 7), (256, 144)])
+def test_epoch_solve_matches_fp64_solve(H, D, single_cta):
+    """Both factorisation kernels (the 8-CTA cluster for H > 64, the one-CTA kernel) against numpy's fp64 Cholesky /
+    solve of the same matrix."""
     tvo_b200._set_device(to.device(DEV))
+    _lib.call("tvo_bsc_epoch_solve_variant", single_cta)
     rng = np.random.default_rng(100 * H + D)
     stats, Wq, WpT = packed_stats(rng, H, D)
     sol, flags, work = run_solve(stats, H, D)
@@ -57,6 +61,7 @@ def test_epoch_solve_matches_fp64_solve(H, D):
     assert resid < 1e-13, resid
     assert np.allclose(sol, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max())
     sol2, _, _ = run_solve(stats, H, D)
+    _lib.call("tvo_bsc_epoch_solve_variant", 0)
     assert np.array_equal(sol, sol2)  # deterministic: what makes the theta broadcast unnecessary
 
 

@@ -59,6 +59,7 @@ _PROTOS = {
     "tvo_bsc_estep_variant": [_I32],
     "tvo_bsc_symmetrize": [_P, _P, _I32, _P],
     "tvo_bsc_epoch_solve_work_doubles": [_I32],
+    "tvo_bsc_epoch_solve_variant": [_I32],
     "tvo_bsc_epoch_solve": [_P, _P, _P, _P, _I32, _I32, _P],
     "tvo_random_states": [_P, _P, _I64, _I32, _I32, _F64, _U64, _U32, _U32, _P],
     "tvo_noisyor_theta_ws_bytes": [_I32, _I32, _I32],

@@ -371,14 +371,26 @@ int tvo_bsc_epoch_finish_f32(const double *stats, const double *sol, const float
                              int32_t n_pies, float *sigma2, int32_t H, int32_t D, const double *guard, void *stream) {
   return bsc_epoch_finish<float>(stats, sol, W_noisy, W, pies, n_pies, sigma2, H, D, guard, stream);
 }
+static int g_chol_single_cta = 0;  // tvo_bsc_epoch_solve_variant(1): the one-CTA factorisation (tests compare the two)
+int tvo_bsc_epoch_solve_variant(int32_t single_cta) {
+  g_chol_single_cta = single_cta ? 1 : 0;
+  return TVO_OK;
+}
 int64_t tvo_bsc_epoch_solve_work_doubles(int32_t H) { return chol_supported(H) ? (int64_t)chol_work_doubles(H) : 0; }
 int tvo_bsc_epoch_solve(const double *stats, double *work, double *sol, double *flags, int32_t H, int32_t D, void *stream) {
   TVO_REQUIRE(stats && work && sol && flags, "bsc_epoch_solve: null pointer");
   TVO_REQUIRE(chol_supported(H) && D > 0, "bsc_epoch_solve: H = %d is outside 1..256 (use the library solve)", H);
-  const size_t smem = chol_factor_smem(H);
-  TVO_CUDA(cudaFuncSetAttribute(bsc_chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  bsc_chol_factor_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(stats + (size_t)H * D, H, work, flags);
-  TVO_AFTER_LAUNCH("bsc_chol_factor");
+  if (H > 64 && !g_chol_single_cta) {  // a cluster of 8 CTAs (the rows of a panel dealt out in tiles of 8)
+    const size_t smem = chol_cluster_smem(H);
+    TVO_CUDA(cudaFuncSetAttribute(bsc_chol_factor_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bsc_chol_factor_cluster_kernel<<<kChCl, 256, smem, (cudaStream_t)stream>>>(stats + (size_t)H * D, H, work, flags);
+    TVO_AFTER_LAUNCH("bsc_chol_factor_cluster");
+  } else {
+    const size_t smem = chol_factor_smem(H);
+    TVO_CUDA(cudaFuncSetAttribute(bsc_chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bsc_chol_factor_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(stats + (size_t)H * D, H, work, flags);
+    TVO_AFTER_LAUNCH("bsc_chol_factor");
+  }
   const size_t smem_s = chol_solve_smem(H);
   TVO_CUDA(cudaFuncSetAttribute(bsc_chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
   bsc_chol_solve_kernel<<<D, 256, smem_s, (cudaStream_t)stream>>>(work, stats, sol, flags, H, D);
