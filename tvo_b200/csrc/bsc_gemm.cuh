@@ -49,9 +49,10 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 }
 
 // ------------------------------------------------------------------------------------ A = Y W, yy = ||y||^2
-// CTA tile: 64 datapoints x one PANEL of 32 NB <= 256 columns (all H columns for H <= 256; H = 512 / 768 / 1024 —
-// BASELINE configs[4] — as 2 / 3 / 4 panels of 256), K in chunks of 16.  8 MMA warps as 2 (M) x 4 (N): warp tile
-// 32 x 8 NB; warp 8 is the TMA producer.  Persistent over the (row tile, panel) work items, the panels of a row tile
+// CTA tile: 64 datapoints x one PANEL of 32 NB <= 256 columns (16 MMA warps as 4 (M) x 4 (N) since the end of round 2:
+// twice the warps per scheduler hide the fragment loads — 82 -> ~90 % of the DGEMM peak; 8 warps as 2 x 4 before) (all H columns for H <= 256; H = 512 / 768 / 1024 —
+// BASELINE configs[4] — as 2 / 3 / 4 panels of 256), K in chunks of 16.  4 WM MMA warps as WM (M) x 4 (N): warp tile
+// 64 / WM x 8 NB; the last warp is the TMA producer.  Persistent over the (row tile, panel) work items, the panels of a row tile
 // adjacent in the order so that the tile of Y is re-read from L2.
 constexpr int kGyBM = 64, kGyKC = 16, kGyStages = 4;
 constexpr int kGyARow = kGyKC + 4;  // doubles per shared-memory row of the Y chunk: 160 B = 8 words mod 32
@@ -61,11 +62,12 @@ __host__ __device__ inline size_t gemm_yw_stage_bytes(int H) {
 }
 __host__ __device__ inline size_t gemm_yw_smem_bytes(int H) { return kGyStages * gemm_yw_stage_bytes(H) + 2 * kGyStages * 8 + 16; }
 
-template <int NB>  // n-blocks per warp: H = 32 NB
-__global__ void __launch_bounds__(288, 1)
+template <int NB, int WM = 4>  // NB n-blocks per warp: panel = 32 NB columns;  WM x 4 MMA warps, 64 / WM rows each
+__global__ void __launch_bounds__(32 * (4 * WM + 1), 1)
 bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__restrict__ Wg, double *__restrict__ A,
                    double *__restrict__ yy_out, int B, int D, int Hfull) {
   constexpr int H = 32 * NB;  // columns of a panel
+  constexpr int MI = kGyBM / WM / 8, NWARP = 4 * WM;  // 8-row blocks per warp; MMA warps
   const int npanel = Hfull / H;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t stage_bytes = gemm_yw_stage_bytes(H);
@@ -77,12 +79,12 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
   if (threadIdx.x == 0) {
     for (int s = 0; s < kGyStages; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, 8);
+      mbar_init(empty + s, NWARP);
     }
     mbar_fence_init();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == NWARP) {
     // ---- producer: per stage 64 row segments of Y (128 B each) + the K-chunk of the panel's columns of Wg (one
     //      contiguous copy when the panel is all of H, else one per k/4 slice) ----
     int stage = 0;
@@ -112,35 +114,37 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
     return;
   }
   // ---- MMA warps ----
-  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4
+  const int wm = warp >> 2, wn = warp & 3;  // WM x 4
   const int g = lane >> 2, q = lane & 3;    // fragment row / column group, k index
   int stage = 0;
   uint32_t phase = 0;
   for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
     const int r0 = (t / npanel) * kGyBM, n0 = (t % npanel) * H;
-    double acc[4][NB][2];
+    double acc[MI][NB][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
       for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    double ysq[4] = {0.0, 0.0, 0.0, 0.0};
+    double ysq[MI];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) ysq[i] = 0.0;
     for (int c = 0; c < nchunk; ++c) {
       mbar_wait(full + stage, phase);
       const double *As = (const double *)(smem_raw + stage * stage_bytes);
       const double *Bs = As + kGyBM * kGyARow;
 #pragma unroll
       for (int k4 = 0; k4 < kGyKC / 4; ++k4) {
-        double a[4], b[NB];
+        double a[MI], b[NB];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[(wm * 32 + i * 8 + g) * kGyARow + k4 * 4 + q];
+        for (int i = 0; i < MI; ++i) a[i] = As[(wm * (8 * MI) + i * 8 + g) * kGyARow + k4 * 4 + q];
 #pragma unroll
         for (int j = 0; j < NB; ++j) b[j] = Bs[((size_t)k4 * H + wn * (8 * NB) + j * 8 + g) * 4 + q];
         if (wn == 0) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) ysq[i] = fma(a[i], a[i], ysq[i]);
+          for (int i = 0; i < MI; ++i) ysq[i] = fma(a[i], a[i], ysq[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
           for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
@@ -153,8 +157,8 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
     }
     // epilogue: C fragment rows g, columns 2q, 2q+1 of every 8 x 8 block
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = r0 + wm * 32 + i * 8 + g;
+    for (int i = 0; i < MI; ++i) {
+      const int row = r0 + wm * (8 * MI) + i * 8 + g;
       if (row < B) {
 #pragma unroll
         for (int j = 0; j < NB; ++j)
@@ -164,11 +168,11 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
     }
     if (wn == 0 && yy_out && n0 == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < MI; ++i) {
         double v = ysq[i];
         v += __shfl_xor_sync(FULL, v, 1);
         v += __shfl_xor_sync(FULL, v, 2);
-        const int row = r0 + wm * 32 + i * 8 + g;
+        const int row = r0 + wm * (8 * MI) + i * 8 + g;
         if (q == 0 && row < B) yy_out[row] = v;
       }
     }
@@ -190,7 +194,7 @@ __host__ inline cudaError_t launch_gemm_yw(const double *Y, int64_t ldY, const d
 #define TVO_GYW(NBV)                                                                                          \
   e = cudaFuncSetAttribute(bsc_gemm_yw_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return e;                                                                            \
-  bsc_gemm_yw_kernel<NBV><<<grid, 288, smem, st>>>(Y, ldY, Wg, A, yy, B, D, H);
+  bsc_gemm_yw_kernel<NBV><<<grid, 32 * 17, smem, st>>>(Y, ldY, Wg, A, yy, B, D, H);
   if (Hp == 256) {
     TVO_GYW(8)
   } else if (H == 128) {
@@ -204,7 +208,7 @@ __host__ inline cudaError_t launch_gemm_yw(const double *Y, int64_t ldY, const d
 
 // ------------------------------------------------------------------------------------ WpT += E^T Y
 // C (H x D) += sum_b E[b][:]^T Y[b][:]: M = h, N = d, K = b (the datapoints).  The grid is 2 x nslab CTAs: CTA (half,
-// slab) accumulates H x D/2 over its contiguous range of datapoints in registers (8 MMA warps x 8 MB rows x all D/2
+// slab) accumulates H x D/2 over its contiguous range of datapoints in registers (NW MMA warps x 8 MB rows x all D/2
 // columns) and writes the partial to `part[slab][half]`; bsc_gemm_ety_reduce_kernel adds the partials to the statistics
 // in slab order (deterministic, unlike a split-K with atomics).  K-chunk: 16 datapoints = 16 rows of E (2 kB each)
 // + 16 half rows of Y per stage, one TMA bulk copy per row; row strides are 8 words mod 32 (conflict-free fragments).
@@ -218,10 +222,10 @@ __host__ __device__ inline size_t gemm_ety_smem_bytes(int H, int Dh) {
   return kGeStages * gemm_ety_stage_bytes(H, Dh) + 2 * kGeStages * 8 + 16;
 }
 
-template <int MB, int NBH>  // H = 64 MB, D = 16 NBH
-__global__ void __launch_bounds__(288, 1)
+template <int MB, int NBH, int NW = 8>  // NW MMA warps of 8 MB rows each: H = 8 MB NW;  D = 16 NBH
+__global__ void __launch_bounds__(32 * NW + 32, 1)
 bsc_gemm_ety_kernel(const double *__restrict__ E, const double *__restrict__ Y, int64_t ldY, double *__restrict__ part, int B) {
-  constexpr int H = 64 * MB, Dh = 8 * NBH;
+  constexpr int H = 8 * MB * NW, Dh = 8 * NBH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int erow = gemm_ety_erow(H), yrow = gemm_ety_yrow(Dh);
   const size_t stage_bytes = gemm_ety_stage_bytes(H, Dh);
@@ -235,12 +239,12 @@ bsc_gemm_ety_kernel(const double *__restrict__ E, const double *__restrict__ Y, 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kGeStages; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, 8);
+      mbar_init(empty + s, NW);
     }
     mbar_fence_init();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == NW) {
     int stage = 0;
     uint32_t phase = 0;
     for (int c = c_lo; c < c_hi; ++c) {
@@ -327,16 +331,16 @@ __host__ inline cudaError_t launch_gemm_ety(const double *E, const double *Y, in
   const size_t smem = gemm_ety_smem_bytes(H, D / 2);
   const int nslab = max(1, min(sms / 2, (B + kGeKC - 1) / kGeKC));
   cudaError_t e;
-#define TVO_GETY(MBV, NBV)                                                                                          \
-  e = cudaFuncSetAttribute(bsc_gemm_ety_kernel<MBV, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-  if (e != cudaSuccess) return e;                                                                                  \
-  bsc_gemm_ety_kernel<MBV, NBV><<<2 * nslab, 288, smem, st>>>(E, Y, ldY, part, B);
+#define TVO_GETY(MBV, NBV, NWV)                                                                                          \
+  e = cudaFuncSetAttribute(bsc_gemm_ety_kernel<MBV, NBV, NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e != cudaSuccess) return e;                                                                                       \
+  bsc_gemm_ety_kernel<MBV, NBV, NWV><<<2 * nslab, 32 * NWV + 32, smem, st>>>(E, Y, ldY, part, B);
   if (D == 144) {
-    TVO_GETY(4, 9)
+    TVO_GETY(2, 9, 16)
   } else if (D == 128) {
-    TVO_GETY(4, 8)
+    TVO_GETY(2, 8, 16)
   } else {
-    TVO_GETY(4, 4)
+    TVO_GETY(2, 4, 16)
   }
 #undef TVO_GETY
   e = cudaGetLastError();
