@@ -52,7 +52,7 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // CTA tile: 64 datapoints x one PANEL of 32 NB <= 256 columns (16 MMA warps as 4 (M) x 4 (N) since the end of round 2:
 // twice the warps per scheduler hide the fragment loads — 82 -> ~90 % of the DGEMM peak; 8 warps as 2 x 4 before) (all H columns for H <= 256; H = 512 / 768 / 1024 —
 // BASELINE configs[4] — as 2 / 3 / 4 panels of 256), K in chunks of 16.  4 WM MMA warps as WM (M) x 4 (N): warp tile
-// 64 / WM x 8 NB; four more warps are the producers.  Persistent over the (row tile, panel) work items, the panels of a row tile
+// 64 / WM x 8 NB; the last warp is the TMA producer.  Persistent over the (row tile, panel) work items, the panels of a row tile
 // adjacent in the order so that the tile of Y is re-read from L2.
 constexpr int kGyBM = 64, kGyKC = 16, kGyStages = 4;
 constexpr int kGyARow = kGyKC + 4;  // doubles per shared-memory row of the Y chunk: 160 B = 8 words mod 32
@@ -62,9 +62,8 @@ __host__ __device__ inline size_t gemm_yw_stage_bytes(int H) {
 }
 __host__ __device__ inline size_t gemm_yw_smem_bytes(int H) { return kGyStages * gemm_yw_stage_bytes(H) + 2 * kGyStages * 8 + 16; }
 
-constexpr int kGyProd = 4;  // producer warps (16 rows of the Y chunk each; the first one also issues the W copy)
 template <int NB, int WM = 4>  // NB n-blocks per warp: panel = 32 NB columns;  WM x 4 MMA warps, 64 / WM rows each
-__global__ void __launch_bounds__(32 * (4 * WM + kGyProd), 1)
+__global__ void __launch_bounds__(32 * (4 * WM + 1), 1)
 bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__restrict__ Wg, double *__restrict__ A,
                    double *__restrict__ yy_out, int B, int D, int Hfull) {
   constexpr int H = 32 * NB;  // columns of a panel
@@ -79,19 +78,15 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
   const int ntile = ((B + kGyBM - 1) / kGyBM) * npanel;  // work items
   if (threadIdx.x == 0) {
     for (int s = 0; s < kGyStages; ++s) {
-      mbar_init(full + s, kGyProd + 1);
+      mbar_init(full + s, 1);
       mbar_init(empty + s, NWARP);
     }
     mbar_fence_init();
   }
   __syncthreads();
-  if (warp >= NWARP) {
-    // ---- producers.  The K-chunk of the panel's columns of Wg arrives by TMA (one contiguous bulk copy when the panel
-    //      is all of H, else one per k/4 slice; issued by the first producer warp).  The 64 x 16 chunk of Y is copied
-    //      by the four producer warps with 16-byte loads and stores (16 rows each, four vectors per lane): as 64 bulk
-    //      copies of 128 bytes per stage it held the kernel at 82 % of the DGEMM peak — the copy engine's cost is per
-    //      request, not per byte.  Each stage's barrier counts the W bytes and one arrival per producer warp. ----
-    const int pw = warp - NWARP;
+  if (warp == NWARP) {
+    // ---- producer: per stage 64 row segments of Y (128 B each) + the K-chunk of the panel's columns of Wg (one
+    //      contiguous copy when the panel is all of H, else one per k/4 slice) ----
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
@@ -100,30 +95,16 @@ bsc_gemm_yw_kernel(const double *__restrict__ Y, int64_t ldY, const double *__re
         mbar_wait(empty + stage, phase ^ 1u);
         double *As = (double *)(smem_raw + stage * stage_bytes);
         double *Bs = As + kGyBM * kGyARow;
-        if (pw == 0) {
-          if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(kGyKC * H * 8));
-          __syncwarp();
-          if (npanel == 1) {
-            if (lane == 0) tma_bulk_g2s(Bs, Wg + (size_t)c * kGyKC * H, kGyKC * H * 8, full + stage);
-          } else if (lane < kGyKC / 4) {
-            tma_bulk_g2s(Bs + (size_t)lane * H * 4, Wg + ((size_t)(c * (kGyKC / 4) + lane) * Hfull + n0) * 4, H * 4 * 8,
-                         full + stage);
-          }
-        }
-        double2 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {  // vector 32 i + lane of this warp's 16 rows x 8 vectors
-          const int r = 16 * pw + ((32 * i + lane) >> 3), seg = (32 * i + lane) & 7;
-          v[i] = r < rows ? *reinterpret_cast<const double2 *>(Y + (int64_t)(r0 + r) * ldY + c * kGyKC + 2 * seg)
-                          : make_double2(0.0, 0.0);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = 16 * pw + ((32 * i + lane) >> 3), seg = (32 * i + lane) & 7;
-          *reinterpret_cast<double2 *>(As + r * kGyARow + 2 * seg) = v[i];
-        }
+        if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(rows * kGyKC * 8 + kGyKC * H * 8));
         __syncwarp();
-        if (lane == 0) mbar_arrive(full + stage);
+        for (int r = lane; r < rows; r += 32)
+          tma_bulk_g2s(As + r * kGyARow, Y + (int64_t)(r0 + r) * ldY + c * kGyKC, kGyKC * 8, full + stage);
+        if (npanel == 1) {
+          if (lane == 0) tma_bulk_g2s(Bs, Wg + (size_t)c * kGyKC * H, kGyKC * H * 8, full + stage);
+        } else if (lane < kGyKC / 4) {
+          tma_bulk_g2s(Bs + (size_t)lane * H * 4, Wg + ((size_t)(c * (kGyKC / 4) + lane) * Hfull + n0) * 4, H * 4 * 8,
+                       full + stage);
+        }
         if (++stage == kGyStages) {
           stage = 0;
           phase ^= 1u;
@@ -213,7 +194,7 @@ __host__ inline cudaError_t launch_gemm_yw(const double *Y, int64_t ldY, const d
 #define TVO_GYW(NBV)                                                                                          \
   e = cudaFuncSetAttribute(bsc_gemm_yw_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return e;                                                                            \
-  bsc_gemm_yw_kernel<NBV><<<grid, 32 * (16 + kGyProd), smem, st>>>(Y, ldY, Wg, A, yy, B, D, H);
+  bsc_gemm_yw_kernel<NBV><<<grid, 32 * 17, smem, st>>>(Y, ldY, Wg, A, yy, B, D, H);
   if (Hp == 256) {
     TVO_GYW(8)
   } else if (H == 128) {
