@@ -239,3 +239,35 @@ def test_v2_fp32_mode_matches_generic_kernel(H, D, S, P, Cn, G):
     scale = np.abs(b[1][fin]).max()
     assert np.allclose(np.sort(a[1][fin], 1), np.sort(b[1][fin], 1), rtol=1e-5, atol=1e-5 * scale)
     assert bool((np.diff(a[1][fin], axis=1) >= 0).all())
+
+
+def test_own_gemms_match_library_many_tiles_per_cta():
+    """The hand-written GEMMs where every CTA walks MANY tiles / slabs (N = 300 000: 4688 row tiles of a = Y W over 148
+    persistent CTAs; the small cases above give each CTA at most one tile): K identical to the library-GEMM path, the
+    stored lpj equal to a direct re-score, the M-step statistics equal.  A producer / consumer race in the mbarrier
+    pipeline shows up here as a few stale rows (one such variant was caught by exactly this comparison)."""
+    N, H, D, S = 300_000, 256, 144, 64
+    tvo_b200._set_device(to.device(DEV))
+    g = to.Generator(device=DEV).manual_seed(9)
+    Wg = to.randn(D, H, dtype=to.float64, device=DEV, generator=g)
+    Y = (to.rand(N, H, device=DEV, generator=g) < 5.0 / H).double() @ Wg.t() + to.randn(N, D, dtype=to.float64, device=DEV, generator=g)
+    W0 = Wg + 0.5 * to.randn(D, H, dtype=to.float64, device=DEV, generator=g)
+    idx = to.arange(N, device=DEV)
+    out = {}
+    for variant in (0, 0x10000):
+        _lib.call("tvo_bsc_estep_variant", variant)
+        try:
+            np.random.seed(0)
+            m = BSC(H, D, W0, to.tensor([1.0], dtype=to.float64), to.full((H,), 1.0 / H, dtype=to.float64), precision=to.float64)
+            st = EVOVariationalStates(N, H, S, to.float64, "randparents", "sparseflip", 16, 2, 2, bitflip_frequency=1.0 / H, seed=3)
+            for _ in range(2):
+                nsubs = st.update(idx, Y, m)
+            full = m._tvo_lpj_packed(Y, st._Kp, H)
+            assert to.allclose(full, st.lpj, rtol=1e-12, atol=1e-9)
+            m.update_param_batch(idx, Y, st)
+            out[variant] = (st._Kp.clone(), nsubs, m._stats.clone())
+        finally:
+            _lib.call("tvo_bsc_estep_variant", 0)
+    a, b = out[0], out[0x10000]
+    assert to.equal(a[0], b[0]) and a[1] == b[1]
+    assert to.allclose(a[2], b[2], rtol=1e-10, atol=1e-10 * float(b[2].abs().max()))
